@@ -1,0 +1,1079 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_common.hpp).
+// In-process emulation of P MPI ranks running the reference OMP backend + solver:
+//   mesh / decomposition  src/mesh.f90:37-306, src/mesh_content.f90:72-253
+//   allocator padding     src/allocator.f90:64-93
+//   index maps            src/ordering.f90:13-87
+//   backend ops           src/backend/omp/backend.f90:145-810
+//   solver sequences      src/solver.f90:214-389,603-739, src/vector_calculus.f90:40-332
+//   time integration      src/time_integrator.f90:70-300
+//   Poisson 000           src/poisson_fft.f90:120-226,654-882,
+//                         src/backend/omp/kernels/spectral_processing.f90:7-106
+//   TGV case + monitors   src/case/tgv.f90:41-72, src/case/base_case.f90:246-330,
+//                         src/postprocess/monitoring.f90:46-90
+// Every rank's data lives in this process; sendrecv_fields / MPI_Allreduce become copies / sums.
+#pragma once
+#include "orc_fft.hpp"
+#include "orc_kernels.hpp"
+
+namespace orc {
+
+// ------------------------------------------------------------------ ordering.f90:13-67 (1-based)
+inline void get_index_ijk(int& i, int& j, int& k, int dir_i, int dir_j, int dir_k, int dir, int sz,
+                          int nx_p, int ny_p, int /*nz_p*/) {
+  switch (dir) {
+    case DIR_X: i = dir_j; j = ((dir_k - 1) % (ny_p / sz)) * sz + dir_i; k = 1 + (dir_k - 1) / (ny_p / sz); break;
+    case DIR_Y: i = ((dir_k - 1) % (nx_p / sz)) * sz + dir_i; j = dir_j; k = 1 + (dir_k - 1) / (nx_p / sz); break;
+    case DIR_Z: i = ((dir_k - 1) % (nx_p / sz)) * sz + dir_i; j = 1 + (dir_k - 1) / (nx_p / sz); k = dir_j; break;
+    default: i = dir_i; j = dir_j; k = dir_k; break;
+  }
+}
+inline void get_index_dir(int& dir_i, int& dir_j, int& dir_k, int i, int j, int k, int dir, int sz,
+                          int nx_p, int ny_p, int /*nz_p*/) {
+  switch (dir) {
+    case DIR_X: dir_i = (j - 1) % sz + 1; dir_j = i; dir_k = (ny_p / sz) * (k - 1) + 1 + (j - 1) / sz; break;
+    case DIR_Y: dir_i = (i - 1) % sz + 1; dir_j = j; dir_k = (nx_p / sz) * (k - 1) + 1 + (i - 1) / sz; break;
+    case DIR_Z: dir_i = (i - 1) % sz + 1; dir_j = k; dir_k = (nx_p / sz) * (j - 1) + 1 + (i - 1) / sz; break;
+    default: dir_i = i; dir_j = j; dir_k = k; break;
+  }
+}
+// ordering.f90:69-87
+inline void get_index_reordering(int& oi, int& oj, int& ok, int ii, int ij, int ik, int dir_from,
+                                 int dir_to, int sz, const int cart_padded[3]) {
+  int i, j, k;
+  get_index_ijk(i, j, k, ii, ij, ik, dir_from, sz, cart_padded[0], cart_padded[1], cart_padded[2]);
+  get_index_dir(oi, oj, ok, i, j, k, dir_to, sz, cart_padded[0], cart_padded[1], cart_padded[2]);
+}
+
+// ------------------------------------------------------------------ allocator.f90:64-93
+struct Alloc {
+  int sz = SZ;
+  int dims_padded_dir[5][3];  // [dir][0..2], dir = 1..4
+  int n_groups_dir[4];        // [dir], dir = 1..3
+  size_t ngrid = 0;
+  void init(const int dims[3], int sz_) {
+    sz = sz_;
+    int nx = dims[0], ny = dims[1], nz = dims[2];
+    auto fmod_ = [](int a, int b) { return a - (a / b) * b; };  // Fortran mod (sign of dividend)
+    int nx_p = nx - 1 + fmod_(-(nx - 1), sz) + sz;
+    int ny_p = ny - 1 + fmod_(-(ny - 1), sz) + sz;
+    int nz_p = nz;
+    ngrid = (size_t)nx_p * ny_p * nz_p;
+    n_groups_dir[1] = ny_p * nz_p / sz;
+    n_groups_dir[2] = nx_p * nz_p / sz;
+    n_groups_dir[3] = nx_p * ny_p / sz;
+    int d1[3] = {sz, nx_p, n_groups_dir[1]}, d2[3] = {sz, ny_p, n_groups_dir[2]},
+        d3[3] = {sz, nz_p, n_groups_dir[3]}, d4[3] = {nx_p, ny_p, nz_p};
+    for (int q = 0; q < 3; ++q) {
+      dims_padded_dir[1][q] = d1[q]; dims_padded_dir[2][q] = d2[q];
+      dims_padded_dir[3][q] = d3[q]; dims_padded_dir[4][q] = d4[q];
+    }
+  }
+  const int* padded(int dir) const { return dims_padded_dir[dir]; }
+  int n_groups(int dir) const { return n_groups_dir[dir]; }
+};
+
+// ------------------------------------------------------------------ mesh
+struct Geo {  // mesh_content.f90:6-27 (per rank: coordinates are rank-local slices of the global axis)
+  double d[3], L[3], alpha[3] = {0, 0, 0}, beta[3] = {1, 1, 1};
+  std::string stretching[3] = {"uniform", "uniform", "uniform"};
+  bool stretched[3] = {false, false, false};
+  std::vector<double> vert_coords[3], midp_coords[3], vert_ds[3], vert_ds2[3], vert_d2s[3], midp_ds[3],
+      midp_ds2[3], midp_d2s[3];
+};
+
+struct RankMesh {
+  int nrank = 0;
+  int nrank_dir[3], n_offset[3], pprev[3], pnext[3];
+  int vert_dims[3], cell_dims[3];
+  int BCs[3][2];
+  Geo geo;
+};
+
+struct GlobalMesh {
+  int global_vert_dims[3], global_cell_dims[3];
+  int BCs_global[3][2];
+  bool periodic_BC[3];
+  int nproc_dir[3], nproc = 1;
+  double L[3], d[3];
+};
+
+// mesh.f90:196-261
+inline void get_dims_dataloc(int dims[3], int data_loc, const int vert[3], const int cell[3]) {
+  switch (data_loc) {
+    case VERT: dims[0] = vert[0]; dims[1] = vert[1]; dims[2] = vert[2]; break;
+    case CELL: dims[0] = cell[0]; dims[1] = cell[1]; dims[2] = cell[2]; break;
+    case X_FACE: dims[0] = vert[0]; dims[1] = cell[1]; dims[2] = cell[2]; break;
+    case Y_FACE: dims[0] = cell[0]; dims[1] = vert[1]; dims[2] = cell[2]; break;
+    case Z_FACE: dims[0] = cell[0]; dims[1] = cell[1]; dims[2] = vert[2]; break;
+    case X_EDGE: dims[0] = cell[0]; dims[1] = vert[1]; dims[2] = vert[2]; break;
+    case Y_EDGE: dims[0] = vert[0]; dims[1] = cell[1]; dims[2] = vert[2]; break;
+    case Z_EDGE: dims[0] = vert[0]; dims[1] = vert[1]; dims[2] = cell[2]; break;
+    default: fail("Unknown location in get_dims_dataloc");
+  }
+}
+// mesh.f90:263-306
+inline int get_n_dir(const RankMesh& m, int dir, int data_loc) {
+  int n_cell = m.cell_dims[dir - 1], n_vert = m.vert_dims[dir - 1], n = n_vert;
+  switch (data_loc) {
+    case CELL: n = n_cell; break;
+    case VERT: n = n_vert; break;
+    case X_FACE: if (dir != DIR_X) n = n_cell; break;
+    case Y_FACE: if (dir != DIR_Y) n = n_cell; break;
+    case Z_FACE: if (dir != DIR_Z) n = n_cell; break;
+    case X_EDGE: if (dir == DIR_X) n = n_cell; break;
+    case Y_EDGE: if (dir == DIR_Y) n = n_cell; break;
+    case Z_EDGE: if (dir == DIR_Z) n = n_cell; break;
+    default: fail("Unknown direction in get_n_dir");
+  }
+  return n;
+}
+
+// mesh_content.f90:142-253
+inline void obtain_coordinates(Geo& g, const int vert_dims[3], const int cell_dims[3], const int n_offset[3]) {
+  for (int dir = 0; dir < 3; ++dir) {
+    int nv = vert_dims[dir], nc = cell_dims[dir];
+    g.vert_coords[dir].assign(nv, 0); g.vert_ds[dir].assign(nv, 1); g.vert_ds2[dir].assign(nv, 1);
+    g.vert_d2s[dir].assign(nv, 0);
+    g.midp_coords[dir].assign(nc, 0); g.midp_ds[dir].assign(nc, 1); g.midp_ds2[dir].assign(nc, 1);
+    g.midp_d2s[dir].assign(nc, 0);
+    if (g.stretching[dir] == "uniform") {
+      g.stretched[dir] = false;
+      g.alpha[dir] = 0;
+      for (int i = 1; i <= nv; ++i) g.vert_coords[dir][i - 1] = (n_offset[dir] + i - 1) * g.d[dir];
+      for (int i = 1; i <= nc; ++i) g.midp_coords[dir][i - 1] = (n_offset[dir] + i - 0.5) * g.d[dir];
+    } else {
+      g.stretched[dir] = true;
+      const std::string& st = g.stretching[dir];
+      double L_inf = g.L[dir] / 2, beta = g.beta[dir];
+      double alpha = std::fabs((L_inf - std::sqrt((pi * beta) * (pi * beta) + L_inf * L_inf)) / (2 * beta * L_inf));
+      g.alpha[dir] = alpha;
+      double r = std::sqrt((alpha * beta + 1) / (alpha * beta));
+      double cst = std::sqrt(beta) / (2 * std::sqrt(alpha) * std::sqrt(alpha * beta + 1));
+      double s = g.d[dir] / g.L[dir];
+      auto eta = [&](double idx) {
+        if (st == "centred") return idx * s;
+        if (st == "top-bottom") return idx * s - 0.5;
+        if (st == "bottom") return idx * s / 2 - 0.5;
+        fail("Invalid stretching type");
+      };
+      auto fill = [&](double y, double& coord, double& ds, double& ds2, double& d2s) {
+        double sp = std::sin(pi * y), cp = std::cos(pi * y);
+        coord = cst * std::atan2(r * sp, cp) * (2 * alpha * beta - std::cos(2 * pi * y) + 1) / (sp * sp + alpha * beta) + pi * cst;
+        ds = g.L[dir] * (alpha / pi + sp * sp / (pi * beta));
+        ds2 = ds * ds;
+        d2s = 2 * cp * sp / beta;
+      };
+      for (int i = 1; i <= nv; ++i)
+        fill(eta((double)(i + n_offset[dir] - 1)), g.vert_coords[dir][i - 1], g.vert_ds[dir][i - 1],
+             g.vert_ds2[dir][i - 1], g.vert_d2s[dir][i - 1]);
+      for (int i = 1; i <= nc; ++i)
+        fill(eta(i + n_offset[dir] - 0.5), g.midp_coords[dir][i - 1], g.midp_ds[dir][i - 1],
+             g.midp_ds2[dir][i - 1], g.midp_d2s[dir][i - 1]);
+      if (st == "centred") {
+        for (auto& x : g.vert_coords[dir]) x -= L_inf;
+        for (auto& x : g.midp_coords[dir]) x -= L_inf;
+      } else if (st == "bottom") {
+        for (auto& x : g.vert_coords[dir]) x = 2 * x;
+        for (auto& x : g.vert_d2s[dir]) x = x / 2;
+        for (auto& x : g.midp_coords[dir]) x = 2 * x;
+        for (auto& x : g.midp_d2s[dir]) x = x / 2;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ fields
+struct WField {  // one field_t per emulated rank
+  std::vector<std::vector<double>> r;
+  int dir = DIR_X, data_loc = NULL_LOC;
+};
+
+struct RankBufs {  // omp/backend.f90:24-30,84-112
+  Halo u_recv_s, u_recv_e, u_send_s, u_send_e, v_recv_s, v_recv_e, v_send_s, v_send_e, w_recv_s,
+      w_recv_e, w_send_s, w_send_e, du_send_s, du_send_e, du_recv_s, du_recv_e, dud_send_s, dud_send_e,
+      dud_recv_s, dud_recv_e, d2u_send_s, d2u_send_e, d2u_recv_s, d2u_recv_e;
+};
+
+struct SolverConfig {
+  double Re = 1600, dt = 1e-3;
+  std::string time_intg = "RK3", der1st = "compact6", der2nd = "compact6", interpl = "classic",
+              stagder = "compact6";
+};
+
+class World {
+ public:
+  GlobalMesh gm;
+  std::vector<RankMesh> rm;
+  Alloc alloc;
+  int P = 1;
+  std::vector<RankBufs> bufs;
+  std::vector<Dirps> xdirps, ydirps, zdirps;  // per rank
+  std::vector<std::unique_ptr<WField>> owned;  // every block ever created
+  std::vector<WField*> pool;                   // LIFO free list (allocator.f90:113-162)
+  SolverConfig cfg;
+  double nu = 0, dt = 0;
+  long long ngrid_global = 0;
+  // solver state
+  WField *u = nullptr, *v = nullptr, *w = nullptr;
+  // time integrator (time_integrator.f90:11-26)
+  int ti_istep = 1, ti_istage = 1, ti_order = 3, ti_nstep = 1, ti_nstage = 3, ti_nolds = 3;
+  bool ti_is_ab = false;
+  double ti_coeffs[5][5], ti_rk_b[5][5], ti_rk_a[4][4][5];
+  std::vector<std::vector<WField*>> olds;  // olds[var][j]
+  // poisson (poisson_fft.f90)
+  int nx_spec = 0, ny_spec = 0, nz_spec = 0;
+  std::vector<cplx> waves, c_x;
+  std::vector<double> ax, bx, ay, by, az, bz;
+  std::vector<cplx> kx, ky, kz, exs, eys, ezs, k2x, k2y, k2z;
+
+  // ---------------------------------------------------------------- construction (mesh.f90:37-194)
+  World(const int dims_global[3], const int nproc_dir[3], const double L[3], const int bcs[3][2],
+        const SolverConfig& cfg_) : cfg(cfg_) {
+    for (int d = 0; d < 3; ++d) {
+      gm.global_vert_dims[d] = dims_global[d];
+      gm.BCs_global[d][0] = bcs[d][0]; gm.BCs_global[d][1] = bcs[d][1];
+      bool p0 = bcs[d][0] == BC_PERIODIC, p1 = bcs[d][1] == BC_PERIODIC;
+      if (p0 != p1) fail("BCs are incompatible");
+      gm.periodic_BC[d] = p0 && p1;
+      gm.global_cell_dims[d] = gm.periodic_BC[d] ? dims_global[d] : dims_global[d] - 1;
+      gm.nproc_dir[d] = nproc_dir[d];
+      gm.L[d] = L[d];
+      gm.d[d] = L[d] / gm.global_cell_dims[d];
+    }
+    P = gm.nproc = nproc_dir[0] * nproc_dir[1] * nproc_dir[2];
+    rm.resize(P);
+    auto rank_of = [&](int px, int py, int pz) { return px + nproc_dir[0] * (py + nproc_dir[1] * pz); };
+    for (int pz = 0; pz < nproc_dir[2]; ++pz)
+      for (int py = 0; py < nproc_dir[1]; ++py)
+        for (int px = 0; px < nproc_dir[0]; ++px) {
+          RankMesh& m = rm[rank_of(px, py, pz)];
+          m.nrank = rank_of(px, py, pz);
+          int pos[3] = {px, py, pz};
+          for (int d = 0; d < 3; ++d) {
+            m.nrank_dir[d] = pos[d];
+            m.vert_dims[d] = gm.global_vert_dims[d] / nproc_dir[d];
+            int np = nproc_dir[d];
+            int prev[3] = {px, py, pz}, next[3] = {px, py, pz};
+            prev[d] = ((pos[d] - 1) % np + np) % np;
+            next[d] = (pos[d] + 1) % np;
+            m.pprev[d] = rank_of(prev[0], prev[1], prev[2]);
+            m.pnext[d] = rank_of(next[0], next[1], next[2]);
+            bool last = pos[d] + 1 == np, first = pos[d] == 0;
+            m.cell_dims[d] = (last && !gm.periodic_BC[d]) ? m.vert_dims[d] - 1 : m.vert_dims[d];
+            m.n_offset[d] = m.vert_dims[d] * pos[d];
+            if (first && last) { m.BCs[d][0] = bcs[d][0]; m.BCs[d][1] = bcs[d][1]; }
+            else if (first) { m.BCs[d][0] = bcs[d][0]; m.BCs[d][1] = BC_HALO; }
+            else if (last) { m.BCs[d][0] = BC_HALO; m.BCs[d][1] = bcs[d][1]; }
+            else { m.BCs[d][0] = BC_HALO; m.BCs[d][1] = BC_HALO; }
+            m.geo.L[d] = gm.L[d];
+            m.geo.d[d] = gm.d[d];
+          }
+        }
+    alloc.init(rm[0].vert_dims, SZ);
+  }
+
+  void set_stretching(const std::string st[3], const double beta[3]) {
+    for (auto& m : rm)
+      for (int d = 0; d < 3; ++d) { m.geo.stretching[d] = st[d]; m.geo.beta[d] = beta[d]; }
+  }
+
+  // finish init once stretching is known: coordinates, buffers, tdsops, time integrator, poisson
+  void init_solver() {
+    for (auto& m : rm) obtain_coordinates(m.geo, m.vert_dims, m.cell_dims, m.n_offset);
+    int ng = std::max(alloc.n_groups(DIR_X), std::max(alloc.n_groups(DIR_Y), alloc.n_groups(DIR_Z)));
+    bufs.resize(P);
+    for (auto& b : bufs) {
+      for (Halo* h : {&b.u_recv_s, &b.u_recv_e, &b.u_send_s, &b.u_send_e, &b.v_recv_s, &b.v_recv_e,
+                      &b.v_send_s, &b.v_send_e, &b.w_recv_s, &b.w_recv_e, &b.w_send_s, &b.w_send_e})
+        h->resize(4, ng);
+      for (Halo* h : {&b.du_send_s, &b.du_send_e, &b.du_recv_s, &b.du_recv_e, &b.dud_send_s, &b.dud_send_e,
+                      &b.dud_recv_s, &b.dud_recv_e, &b.d2u_send_s, &b.d2u_send_e, &b.d2u_recv_s, &b.d2u_recv_e})
+        h->resize(1, ng);
+    }
+    nu = 1.0 / cfg.Re;
+    dt = cfg.dt;
+    ngrid_global = (long long)gm.global_vert_dims[0] * gm.global_vert_dims[1] * gm.global_vert_dims[2];
+    u = get_block(DIR_X); v = get_block(DIR_X); w = get_block(DIR_X);
+    init_time_integrator();
+    xdirps.resize(P); ydirps.resize(P); zdirps.resize(P);
+    for (int r = 0; r < P; ++r) {
+      xdirps[r].dir = DIR_X; ydirps[r].dir = DIR_Y; zdirps[r].dir = DIR_Z;
+      allocate_tdsops(xdirps[r], rm[r]);
+      allocate_tdsops(ydirps[r], rm[r]);
+      allocate_tdsops(zdirps[r], rm[r]);
+    }
+    init_poisson();
+  }
+
+  // ---------------------------------------------------------------- allocator pool
+  WField* get_block(int dir, int data_loc = NULL_LOC) {
+    WField* f;
+    if (pool.empty()) {
+      owned.emplace_back(new WField);
+      f = owned.back().get();
+      f->r.assign(P, std::vector<double>(alloc.ngrid, 0.0));
+    } else {
+      f = pool.back();
+      pool.pop_back();
+    }
+    f->dir = dir;
+    f->data_loc = data_loc;
+    return f;
+  }
+  void release_block(WField* f) { pool.push_back(f); }
+
+  // ---------------------------------------------------------------- solver.f90:214-289
+  void allocate_tdsops(Dirps& dp, const RankMesh& m) {
+    int dir = dp.dir;
+    double d = m.geo.d[dir - 1];
+    int bc_start = m.BCs[dir - 1][0], bc_end = m.BCs[dir - 1][1];
+    int bc_mp_start = bc_start == BC_DIRICHLET ? BC_NEUMANN : bc_start;
+    int bc_mp_end = bc_end == BC_DIRICHLET ? BC_NEUMANN : bc_end;
+    int n_vert = get_n_dir(m, dir, VERT), n_cell = get_n_dir(m, dir, CELL);
+    const Geo& g = m.geo;
+    const double* vds = g.vert_ds[dir - 1].data();
+    const double* vds2 = g.vert_ds2[dir - 1].data();
+    const double* vd2s = g.vert_d2s[dir - 1].data();
+    const double* mds = g.midp_ds[dir - 1].data();
+    dp.der1st = tdsops_init(n_vert, d, "first-deriv", cfg.der1st, bc_start, bc_end, vds);
+    dp.der1st_sym = tdsops_init(n_vert, d, "first-deriv", cfg.der1st, bc_start, bc_end, vds, nullptr, 4, "", true);
+    dp.der2nd = tdsops_init(n_vert, d, "second-deriv", cfg.der2nd, bc_start, bc_end, vds2, vd2s);
+    dp.der2nd_sym = tdsops_init(n_vert, d, "second-deriv", cfg.der2nd, bc_start, bc_end, vds2, vd2s, 4, "", true);
+    dp.stagder_v2p = tdsops_init(n_cell, d, "stag-deriv", cfg.stagder, bc_mp_start, bc_mp_end, mds, nullptr, 4, "v2p");
+    dp.stagder_p2v = tdsops_init(n_vert, d, "stag-deriv", cfg.stagder, bc_mp_start, bc_mp_end, vds, nullptr, 4, "p2v");
+    dp.interpl_v2p = tdsops_init(n_cell, d, "interpolate", cfg.interpl, bc_mp_start, bc_mp_end, nullptr, nullptr, 4, "v2p");
+    dp.interpl_p2v = tdsops_init(n_vert, d, "interpolate", cfg.interpl, bc_mp_start, bc_mp_end, nullptr, nullptr, 4, "p2v");
+  }
+
+  // ---------------------------------------------------------------- halo exchange helpers
+  int n_groups(int dir) const { return alloc.n_groups(dir); }
+  int n_pad(int dir) const { return alloc.padded(dir)[1]; }
+
+  using HaloMember = Halo RankBufs::*;
+  void exchange(int dir, HaloMember recv_s, HaloMember recv_e, HaloMember send_s, HaloMember send_e) {
+    // omp/sendrecv.f90:10-36. Copies are staged so that a rank that is its own neighbour (nproc_dir == 1)
+    // sees f_recv_s = f_send_e, f_recv_e = f_send_s.
+    for (int r = 0; r < P; ++r) {
+      (bufs[r].*recv_s).d = (bufs[rm[r].pprev[dir - 1]].*send_e).d;
+      (bufs[r].*recv_e).d = (bufs[rm[r].pnext[dir - 1]].*send_s).d;
+    }
+  }
+
+  // ---------------------------------------------------------------- omp/backend.f90:340-391 + exec_dist.f90:16-65
+  void tds_solve(WField& du, const WField& uu, const std::vector<const Tdsops*>& ops) {
+    if (uu.dir != du.dir) fail("DIR mismatch between fields in tds_solve.");
+    if (uu.data_loc != NULL_LOC) du.data_loc = move_data_loc(uu.data_loc, uu.dir, ops[0]->move);
+    const int dir = uu.dir, ng = n_groups(dir), npad = n_pad(dir);
+    for (int r = 0; r < P; ++r)
+      copy_into_buffers(bufs[r].u_send_s, bufs[r].u_send_e, uu.r[r].data(), npad, ops[r]->n_tds, ng);
+    exchange(dir, &RankBufs::u_recv_s, &RankBufs::u_recv_e,
+             &RankBufs::u_send_s, &RankBufs::u_send_e);
+    for (int r = 0; r < P; ++r) {
+      const Tdsops& t = *ops[r];
+      RankBufs& b = bufs[r];
+#pragma omp parallel for
+      for (int k = 1; k <= ng; ++k) {
+        size_t off = (size_t)SZ * npad * (k - 1);
+        der_univ_dist(du.r[r].data() + off, b.du_send_s.grp(k), b.du_send_e.grp(k), uu.r[r].data() + off,
+                      b.u_recv_s.grp(k), b.u_recv_e.grp(k), t.n_tds, t.n_rhs, t.coeffs_s, t.coeffs_e, t.coeffs,
+                      t.dist_fw.data(), t.dist_bw.data(), t.dist_af.data());
+      }
+    }
+    exchange(dir, &RankBufs::du_recv_s, &RankBufs::du_recv_e,
+             &RankBufs::du_send_s, &RankBufs::du_send_e);
+    for (int r = 0; r < P; ++r) {
+      const Tdsops& t = *ops[r];
+      RankBufs& b = bufs[r];
+#pragma omp parallel for
+      for (int k = 1; k <= ng; ++k) {
+        size_t off = (size_t)SZ * npad * (k - 1);
+        der_univ_subs(du.r[r].data() + off, b.du_recv_s.grp(k), b.du_recv_e.grp(k), t.n_tds, t.dist_sa.data(),
+                      t.dist_sc.data(), t.stretch.data());
+      }
+    }
+  }
+
+  // pick one operator of a per-rank dirps list
+  template <class M>
+  std::vector<const Tdsops*> op(const std::vector<Dirps>& dps, M member) const {
+    std::vector<const Tdsops*> o(P);
+    for (int r = 0; r < P; ++r) o[r] = &(dps[r].*member);
+    return o;
+  }
+
+  // ---------------------------------------------------------------- omp/backend.f90:299-338 + exec_dist.f90:67-186
+  enum Which { HU, HV, HW };
+  Halo& hrecv_s(RankBufs& b, Which h) { return h == HU ? b.u_recv_s : (h == HV ? b.v_recv_s : b.w_recv_s); }
+  Halo& hrecv_e(RankBufs& b, Which h) { return h == HU ? b.u_recv_e : (h == HV ? b.v_recv_e : b.w_recv_e); }
+
+  void transeq_dist_component(WField& rhs_du, const WField& uu, const WField& conv, double nu_, Which uh,
+                              Which convh, const std::vector<const Tdsops*>& t_du,
+                              const std::vector<const Tdsops*>& t_dud, const std::vector<const Tdsops*>& t_d2u,
+                              int dir) {
+    WField* dud = get_block(dir);
+    WField* d2u = get_block(dir);
+    const int ng = n_groups(dir), npad = n_pad(dir);
+    for (int r = 0; r < P; ++r) {
+      RankBufs& b = bufs[r];
+      const Tdsops &a = *t_du[r], &bb = *t_dud[r], &c = *t_d2u[r];
+      Halo &urs = hrecv_s(b, uh), &ure = hrecv_e(b, uh), &vrs = hrecv_s(b, convh), &vre = hrecv_e(b, convh);
+#pragma omp parallel
+      {
+        std::vector<double> ud((size_t)SZ * std::max(bb.n_tds, bb.n_rhs)), ud_s(SZ * 4), ud_e(SZ * 4);
+#pragma omp for
+        for (int k = 1; k <= ng; ++k) {
+          size_t off = (size_t)SZ * npad * (k - 1);
+          const double* ug = uu.r[r].data() + off;
+          const double* vg = conv.r[r].data() + off;
+          der_univ_dist(rhs_du.r[r].data() + off, b.du_send_s.grp(k), b.du_send_e.grp(k), ug, urs.grp(k),
+                        ure.grp(k), a.n_tds, a.n_rhs, a.coeffs_s, a.coeffs_e, a.coeffs, a.dist_fw.data(),
+                        a.dist_bw.data(), a.dist_af.data());
+          der_univ_dist(d2u->r[r].data() + off, b.d2u_send_s.grp(k), b.d2u_send_e.grp(k), ug, urs.grp(k),
+                        ure.grp(k), c.n_tds, c.n_rhs, c.coeffs_s, c.coeffs_e, c.coeffs, c.dist_fw.data(),
+                        c.dist_bw.data(), c.dist_af.data());
+          for (int j = 1; j <= bb.n_tds; ++j)
+            for (int i = 0; i < SZ; ++i) ORC_AT(ud.data(), i, j) = ORC_AT(ug, i, j) * ORC_AT(vg, i, j);
+          for (int j = 1; j <= 4; ++j)
+            for (int i = 0; i < SZ; ++i) {
+              ORC_AT(ud_s.data(), i, j) = ORC_AT(urs.grp(k), i, j) * ORC_AT(vrs.grp(k), i, j);
+              ORC_AT(ud_e.data(), i, j) = ORC_AT(ure.grp(k), i, j) * ORC_AT(vre.grp(k), i, j);
+            }
+          der_univ_dist(dud->r[r].data() + off, b.dud_send_s.grp(k), b.dud_send_e.grp(k), ud.data(), ud_s.data(),
+                        ud_e.data(), bb.n_tds, bb.n_rhs, bb.coeffs_s, bb.coeffs_e, bb.coeffs, bb.dist_fw.data(),
+                        bb.dist_bw.data(), bb.dist_af.data());
+        }
+      }
+    }
+    exchange(dir, &RankBufs::du_recv_s, &RankBufs::du_recv_e,
+             &RankBufs::du_send_s, &RankBufs::du_send_e);
+    exchange(dir, &RankBufs::dud_recv_s, &RankBufs::dud_recv_e,
+             &RankBufs::dud_send_s, &RankBufs::dud_send_e);
+    exchange(dir, &RankBufs::d2u_recv_s, &RankBufs::d2u_recv_e,
+             &RankBufs::d2u_send_s, &RankBufs::d2u_send_e);
+    for (int r = 0; r < P; ++r) {
+      RankBufs& b = bufs[r];
+      const Tdsops &a = *t_du[r], &bb = *t_dud[r], &c = *t_d2u[r];
+#pragma omp parallel for
+      for (int k = 1; k <= ng; ++k) {
+        size_t off = (size_t)SZ * npad * (k - 1);
+        der_univ_fused_subs(rhs_du.r[r].data() + off, dud->r[r].data() + off, d2u->r[r].data() + off,
+                            conv.r[r].data() + off, b.du_recv_s.grp(k), b.du_recv_e.grp(k), b.dud_recv_s.grp(k),
+                            b.dud_recv_e.grp(k), b.d2u_recv_s.grp(k), b.d2u_recv_e.grp(k), nu_, a.n_tds,
+                            a.dist_sa.data(), a.dist_sc.data(), a.stretch.data(), bb.dist_sa.data(),
+                            bb.dist_sc.data(), bb.stretch.data(), c.dist_sa.data(), c.dist_sc.data(),
+                            c.stretch.data(), c.stretch_correct.data());
+      }
+    }
+    rhs_du.data_loc = uu.data_loc;
+    release_block(dud);
+    release_block(d2u);
+  }
+
+  // omp/backend.f90:235-297
+  void transeq_omp_dist(WField& du, WField& dv, WField& dw, const WField& uu, const WField& vv, const WField& ww,
+                        double nu_, const std::vector<Dirps>& dps) {
+    const int dir = dps[0].dir, ng = n_groups(dir), npad = n_pad(dir);
+    for (int r = 0; r < P; ++r) {
+      int n = get_n_dir(rm[r], uu.dir, uu.data_loc == NULL_LOC ? VERT : uu.data_loc);
+      copy_into_buffers(bufs[r].u_send_s, bufs[r].u_send_e, uu.r[r].data(), npad, n, ng);
+      copy_into_buffers(bufs[r].v_send_s, bufs[r].v_send_e, vv.r[r].data(), npad, n, ng);
+      copy_into_buffers(bufs[r].w_send_s, bufs[r].w_send_e, ww.r[r].data(), npad, n, ng);
+    }
+    exchange(dir, &RankBufs::u_recv_s, &RankBufs::u_recv_e,
+             &RankBufs::u_send_s, &RankBufs::u_send_e);
+    exchange(dir, &RankBufs::v_recv_s, &RankBufs::v_recv_e,
+             &RankBufs::v_send_s, &RankBufs::v_send_e);
+    exchange(dir, &RankBufs::w_recv_s, &RankBufs::w_recv_e,
+             &RankBufs::w_send_s, &RankBufs::w_send_e);
+    transeq_dist_component(du, uu, uu, nu_, HU, HU, op(dps, &Dirps::der1st), op(dps, &Dirps::der1st_sym),
+                           op(dps, &Dirps::der2nd), dir);
+    transeq_dist_component(dv, vv, uu, nu_, HV, HU, op(dps, &Dirps::der1st_sym), op(dps, &Dirps::der1st),
+                           op(dps, &Dirps::der2nd_sym), dir);
+    transeq_dist_component(dw, ww, uu, nu_, HW, HU, op(dps, &Dirps::der1st_sym), op(dps, &Dirps::der1st),
+                           op(dps, &Dirps::der2nd_sym), dir);
+  }
+  // omp/backend.f90:145-184
+  void transeq_x(WField& du, WField& dv, WField& dw, const WField& uu, const WField& vv, const WField& ww, double nu_) {
+    transeq_omp_dist(du, dv, dw, uu, vv, ww, nu_, xdirps);
+  }
+  void transeq_y(WField& du, WField& dv, WField& dw, const WField& uu, const WField& vv, const WField& ww, double nu_) {
+    transeq_omp_dist(dv, du, dw, vv, uu, ww, nu_, ydirps);
+  }
+  void transeq_z(WField& du, WField& dv, WField& dw, const WField& uu, const WField& vv, const WField& ww, double nu_) {
+    transeq_omp_dist(dw, du, dv, ww, uu, vv, nu_, zdirps);
+  }
+
+  // ---------------------------------------------------------------- omp/backend.f90:393-452
+  void reorder(WField& u_, const WField& uu, int direction) {
+    int dir_from, dir_to;
+    get_dirs_from_rdr(dir_from, dir_to, direction);
+    const int* dims = alloc.padded(uu.dir);
+    const int* cart = alloc.padded(DIR_C);
+    const int* od = alloc.padded(dir_to);
+    for (int r = 0; r < P; ++r) {
+      const double* src = uu.r[r].data();
+      double* dst = u_.r[r].data();
+#pragma omp parallel for collapse(2)
+      for (int k = 1; k <= dims[2]; ++k)
+        for (int j = 1; j <= dims[1]; ++j)
+          for (int i = 1; i <= dims[0]; ++i) {
+            int oi, oj, ok;
+            get_index_reordering(oi, oj, ok, i, j, k, dir_from, dir_to, SZ, cart);
+            dst[(oi - 1) + (size_t)od[0] * ((oj - 1) + (size_t)od[1] * (ok - 1))] =
+                src[(i - 1) + (size_t)dims[0] * ((j - 1) + (size_t)dims[1] * (k - 1))];
+          }
+    }
+    u_.data_loc = uu.data_loc;
+  }
+
+  // omp/backend.f90:454-527
+  void sum_intox(WField& uu, const WField& u_, int dir_to) {
+    const int* dims = alloc.padded(uu.dir);
+    const int* cart = alloc.padded(DIR_C);
+    const int* od = alloc.padded(dir_to);
+    for (int r = 0; r < P; ++r) {
+      double* a = uu.r[r].data();
+      const double* b = u_.r[r].data();
+#pragma omp parallel for collapse(2)
+      for (int k = 1; k <= dims[2]; ++k)
+        for (int j = 1; j <= dims[1]; ++j)
+          for (int i = 1; i <= dims[0]; ++i) {
+            int ii, jj, kk;
+            get_index_reordering(ii, jj, kk, i, j, k, DIR_X, dir_to, SZ, cart);
+            size_t ia = (i - 1) + (size_t)dims[0] * ((j - 1) + (size_t)dims[1] * (k - 1));
+            a[ia] = a[ia] + b[(ii - 1) + (size_t)od[0] * ((jj - 1) + (size_t)od[1] * (kk - 1))];
+          }
+    }
+  }
+  void sum_yintox(WField& uu, const WField& u_) { sum_intox(uu, u_, DIR_Y); }
+  void sum_zintox(WField& uu, const WField& u_) { sum_intox(uu, u_, DIR_Z); }
+
+  // omp/backend.f90:529-585
+  void veccopy(WField& dst, const WField& src) {
+    if (src.dir != dst.dir) fail("Called vector copy with incompatible fields");
+    if (dst.dir == DIR_C) fail("veccopy does not support DIR_C fields");
+    for (int r = 0; r < P; ++r) {
+      const double* s = src.r[r].data();
+      double* d = dst.r[r].data();
+      const long long n = (long long)alloc.ngrid;
+#pragma omp parallel for simd
+      for (long long i = 0; i < n; ++i) d[i] = s[i];
+    }
+  }
+  void vecadd(double a, const WField& x, double b, WField& y) {
+    if (x.dir != y.dir) fail("Called vector add with incompatible fields");
+    if (y.dir == DIR_C) fail("vecadd does not support DIR_C fields");
+    for (int r = 0; r < P; ++r) {
+      const double* xs = x.r[r].data();
+      double* ys = y.r[r].data();
+      const long long n = (long long)alloc.ngrid;
+#pragma omp parallel for simd
+      for (long long i = 0; i < n; ++i) ys[i] = a * xs[i] + b * ys[i];
+    }
+  }
+
+  // backend.f90:402-432 (get_field_data into DIR_C) then omp/backend.f90:651-712
+  double scalar_product(const WField& x, const WField& y) {
+    if (x.data_loc == NULL_LOC || y.data_loc == NULL_LOC) fail("You must set the data_loc before calling scalar product");
+    if (x.data_loc != y.data_loc) fail("Called scalar product with incompatible fields");
+    WField* x_ = get_block(DIR_C, x.data_loc);
+    WField* y_ = get_block(DIR_C, y.data_loc);
+    int rx = get_rdr_from_dirs(x.dir, DIR_C), ry = get_rdr_from_dirs(y.dir, DIR_C);
+    if (rx) reorder(*x_, x, rx); else x_->r = x.r;
+    if (ry) reorder(*y_, y, ry); else y_->r = y.r;
+    const int* cp = alloc.padded(DIR_C);
+    double s = 0.0;
+    for (int r = 0; r < P; ++r) {
+      int dims[3];
+      get_dims_dataloc(dims, x.data_loc, rm[r].vert_dims, rm[r].cell_dims);
+      std::vector<double> part(dims[2], 0.0);
+#pragma omp parallel for
+      for (int k = 0; k < dims[2]; ++k) {
+        double acc = 0.0;
+        for (int j = 0; j < dims[1]; ++j) {
+          const double* xr = x_->r[r].data() + (size_t)cp[0] * (j + (size_t)cp[1] * k);
+          const double* yr = y_->r[r].data() + (size_t)cp[0] * (j + (size_t)cp[1] * k);
+          for (int i = 0; i < dims[0]; ++i) acc += xr[i] * yr[i];
+        }
+        part[k] = acc;
+      }
+      for (double p : part) s += p;  // MPI_Allreduce SUM (:708)
+    }
+    release_block(x_);
+    release_block(y_);
+    return s;
+  }
+
+  // omp/backend.f90:739-810
+  void field_max_mean(double& max_val, double& mean_val, const WField& f, int enforced_data_loc = -999) {
+    if (f.data_loc == NULL_LOC && enforced_data_loc == -999) fail("field_max_mean: invalid data_loc");
+    int data_loc = enforced_data_loc != -999 ? enforced_data_loc : f.data_loc;
+    const int* dp_ = alloc.padded(DIR_C);
+    (void)dp_;
+    max_val = 0;
+    mean_val = 0;
+    int gdims[3];
+    get_dims_dataloc(gdims, data_loc, gm.global_vert_dims, gm.global_cell_dims);
+    for (int r = 0; r < P; ++r) {
+      int dims[3];
+      get_dims_dataloc(dims, data_loc, rm[r].vert_dims, rm[r].cell_dims);
+      int n, n_j, n_i;
+      if (f.dir == DIR_X) { n = dims[0]; n_j = dims[1]; n_i = dims[2]; }
+      else if (f.dir == DIR_Y) { n = dims[1]; n_j = dims[0]; n_i = dims[2]; }
+      else if (f.dir == DIR_Z) { n = dims[2]; n_j = dims[0]; n_i = dims[1]; }
+      else fail("field_max_mean does not support DIR_C fields!");
+      const int npad = n_pad(f.dir);
+      const int nkj = (n_j - 1) / SZ + 1;
+      double sum_p = 0, max_p = 0;
+      for (int k_j = 1; k_j <= nkj; ++k_j)
+        for (int k_i = 1; k_i <= n_i; ++k_i) {
+          int k = k_j + (k_i - 1) * nkj;
+          const double* g = f.r[r].data() + (size_t)SZ * npad * (k - 1);
+          double sum_pncl = 0, max_pncl = 0;
+          for (int j = 1; j <= n; ++j)
+            for (int i = 0; i < std::min(SZ, n_j - (k_j - 1) * SZ); ++i) {
+              double val = std::fabs(ORC_AT(g, i, j));
+              sum_pncl = sum_pncl + val;
+              max_pncl = std::max(max_pncl, val);
+            }
+          sum_p = sum_p + sum_pncl;
+          max_p = std::max(max_p, max_pncl);
+        }
+      max_val = std::max(max_val, max_p);
+      mean_val += sum_p / ((double)gdims[0] * gdims[1] * gdims[2]);
+    }
+  }
+
+  // ---------------------------------------------------------------- set/get through DIR_C (backend.f90:402-466)
+  // global Cartesian array g(nx_g, ny_g, nz_g) of the data_loc extents (x fastest, unpadded)
+  void set_field_from_global(WField& f, const double* g, int data_loc) {
+    int gd[3];
+    get_dims_dataloc(gd, data_loc, gm.global_vert_dims, gm.global_cell_dims);
+    WField* c = get_block(DIR_C, data_loc);
+    const int* cp = alloc.padded(DIR_C);
+    for (int r = 0; r < P; ++r) {
+      std::fill(c->r[r].begin(), c->r[r].end(), 0.0);
+      int dims[3];
+      get_dims_dataloc(dims, data_loc, rm[r].vert_dims, rm[r].cell_dims);
+      for (int k = 0; k < dims[2]; ++k)
+        for (int j = 0; j < dims[1]; ++j)
+          for (int i = 0; i < dims[0]; ++i)
+            c->r[r][i + (size_t)cp[0] * (j + (size_t)cp[1] * k)] =
+                g[(i + rm[r].n_offset[0]) + (size_t)gd[0] * ((j + rm[r].n_offset[1]) + (size_t)gd[1] * (k + rm[r].n_offset[2]))];
+    }
+    f.data_loc = data_loc;
+    int rdr = get_rdr_from_dirs(DIR_C, f.dir);
+    if (rdr) reorder(f, *c, rdr); else f.r = c->r;
+    f.data_loc = data_loc;
+    release_block(c);
+  }
+  void get_field_to_global(double* g, const WField& f, int data_loc) {
+    int gd[3];
+    get_dims_dataloc(gd, data_loc, gm.global_vert_dims, gm.global_cell_dims);
+    WField* c = get_block(DIR_C, data_loc);
+    int rdr = get_rdr_from_dirs(f.dir, DIR_C);
+    if (rdr) reorder(*c, f, rdr); else c->r = f.r;
+    const int* cp = alloc.padded(DIR_C);
+    for (int r = 0; r < P; ++r) {
+      int dims[3];
+      get_dims_dataloc(dims, data_loc, rm[r].vert_dims, rm[r].cell_dims);
+      for (int k = 0; k < dims[2]; ++k)
+        for (int j = 0; j < dims[1]; ++j)
+          for (int i = 0; i < dims[0]; ++i)
+            g[(i + rm[r].n_offset[0]) + (size_t)gd[0] * ((j + rm[r].n_offset[1]) + (size_t)gd[1] * (k + rm[r].n_offset[2]))] =
+                c->r[r][i + (size_t)cp[0] * (j + (size_t)cp[1] * k)];
+    }
+    release_block(c);
+  }
+
+  // ---------------------------------------------------------------- solver.f90:291-389
+  void transeq_default(WField& du, WField& dv, WField& dw, const WField& uu, const WField& vv, const WField& ww) {
+    transeq_x(du, dv, dw, uu, vv, ww, nu);
+    WField *u_y = get_block(DIR_Y), *v_y = get_block(DIR_Y), *w_y = get_block(DIR_Y), *du_y = get_block(DIR_Y),
+           *dv_y = get_block(DIR_Y), *dw_y = get_block(DIR_Y);
+    reorder(*u_y, uu, RDR_X2Y); reorder(*v_y, vv, RDR_X2Y); reorder(*w_y, ww, RDR_X2Y);
+    transeq_y(*du_y, *dv_y, *dw_y, *u_y, *v_y, *w_y, nu);
+    release_block(u_y); release_block(v_y); release_block(w_y);
+    sum_yintox(du, *du_y); sum_yintox(dv, *dv_y); sum_yintox(dw, *dw_y);
+    release_block(du_y); release_block(dv_y); release_block(dw_y);
+    WField *u_z = get_block(DIR_Z), *v_z = get_block(DIR_Z), *w_z = get_block(DIR_Z), *du_z = get_block(DIR_Z),
+           *dv_z = get_block(DIR_Z), *dw_z = get_block(DIR_Z);
+    reorder(*u_z, uu, RDR_X2Z); reorder(*v_z, vv, RDR_X2Z); reorder(*w_z, ww, RDR_X2Z);
+    transeq_z(*du_z, *dv_z, *dw_z, *u_z, *v_z, *w_z, nu);
+    release_block(u_z); release_block(v_z); release_block(w_z);
+    sum_zintox(du, *du_z); sum_zintox(dv, *dv_z); sum_zintox(dw, *dw_z);
+    release_block(du_z); release_block(dv_z); release_block(dw_z);
+  }
+
+  // ---------------------------------------------------------------- vector_calculus.f90:142-246
+  void divergence_v2c(WField& div_u, const WField& uu, const WField& vv, const WField& ww) {
+    if (div_u.dir != DIR_Z || uu.dir != DIR_X || vv.dir != DIR_X || ww.dir != DIR_X) fail("divergence_v2c dirs");
+    WField *du_x = get_block(DIR_X), *dv_x = get_block(DIR_X), *dw_x = get_block(DIR_X);
+    tds_solve(*du_x, uu, op(xdirps, &Dirps::stagder_v2p));
+    tds_solve(*dv_x, vv, op(xdirps, &Dirps::interpl_v2p));
+    tds_solve(*dw_x, ww, op(xdirps, &Dirps::interpl_v2p));
+    WField *u_y = get_block(DIR_Y), *v_y = get_block(DIR_Y), *w_y = get_block(DIR_Y);
+    reorder(*u_y, *du_x, RDR_X2Y); reorder(*v_y, *dv_x, RDR_X2Y); reorder(*w_y, *dw_x, RDR_X2Y);
+    release_block(du_x); release_block(dv_x); release_block(dw_x);
+    WField *du_y = get_block(DIR_Y), *dv_y = get_block(DIR_Y), *dw_y = get_block(DIR_Y);
+    tds_solve(*du_y, *u_y, op(ydirps, &Dirps::interpl_v2p));
+    tds_solve(*dv_y, *v_y, op(ydirps, &Dirps::stagder_v2p));
+    tds_solve(*dw_y, *w_y, op(ydirps, &Dirps::interpl_v2p));
+    release_block(u_y); release_block(v_y); release_block(w_y);
+    WField *u_z = get_block(DIR_Z), *w_z = get_block(DIR_Z);
+    vecadd(1.0, *dv_y, 1.0, *du_y);
+    reorder(*u_z, *du_y, RDR_Y2Z); reorder(*w_z, *dw_y, RDR_Y2Z);
+    release_block(du_y); release_block(dv_y); release_block(dw_y);
+    WField* dw_z = get_block(DIR_Z);
+    tds_solve(div_u, *u_z, op(zdirps, &Dirps::interpl_v2p));
+    tds_solve(*dw_z, *w_z, op(zdirps, &Dirps::stagder_v2p));
+    vecadd(1.0, *dw_z, 1.0, div_u);
+    release_block(u_z); release_block(w_z); release_block(dw_z);
+  }
+
+  // vector_calculus.f90:248-332
+  void gradient_c2v(WField& dpdx, WField& dpdy, WField& dpdz, const WField& p) {
+    if (dpdx.dir != DIR_X || dpdy.dir != DIR_X || dpdz.dir != DIR_X || p.dir != DIR_Z) fail("gradient_c2v dirs");
+    WField *p_sxy_z = get_block(DIR_Z), *dpdz_sxy_z = get_block(DIR_Z);
+    tds_solve(*p_sxy_z, p, op(zdirps, &Dirps::interpl_p2v));
+    tds_solve(*dpdz_sxy_z, p, op(zdirps, &Dirps::stagder_p2v));
+    WField *p_sxy_y = get_block(DIR_Y), *dpdz_sxy_y = get_block(DIR_Y);
+    reorder(*p_sxy_y, *p_sxy_z, RDR_Z2Y); reorder(*dpdz_sxy_y, *dpdz_sxy_z, RDR_Z2Y);
+    release_block(p_sxy_z); release_block(dpdz_sxy_z);
+    WField *p_sx_y = get_block(DIR_Y), *dpdy_sx_y = get_block(DIR_Y);
+    tds_solve(*p_sx_y, *p_sxy_y, op(ydirps, &Dirps::interpl_p2v));
+    tds_solve(*dpdy_sx_y, *p_sxy_y, op(ydirps, &Dirps::stagder_p2v));
+    release_block(p_sxy_y);
+    WField* dpdz_sx_y = get_block(DIR_Y);
+    tds_solve(*dpdz_sx_y, *dpdz_sxy_y, op(ydirps, &Dirps::interpl_p2v));
+    release_block(dpdz_sxy_y);
+    WField* p_sx_x = get_block(DIR_X);
+    reorder(*p_sx_x, *p_sx_y, RDR_Y2X); release_block(p_sx_y);
+    WField* dpdy_sx_x = get_block(DIR_X);
+    reorder(*dpdy_sx_x, *dpdy_sx_y, RDR_Y2X); release_block(dpdy_sx_y);
+    WField* dpdz_sx_x = get_block(DIR_X);
+    reorder(*dpdz_sx_x, *dpdz_sx_y, RDR_Y2X); release_block(dpdz_sx_y);
+    tds_solve(dpdx, *p_sx_x, op(xdirps, &Dirps::stagder_p2v));
+    tds_solve(dpdy, *dpdy_sx_x, op(xdirps, &Dirps::interpl_p2v));
+    tds_solve(dpdz, *dpdz_sx_x, op(xdirps, &Dirps::interpl_p2v));
+    release_block(p_sx_x); release_block(dpdy_sx_x); release_block(dpdz_sx_x);
+  }
+
+  // vector_calculus.f90:40-140
+  void curl(WField& o_i, WField& o_j, WField& o_k, const WField& uu, const WField& vv, const WField& ww) {
+    auto xd = op(xdirps, &Dirps::der1st), yd = op(ydirps, &Dirps::der1st), zd = op(zdirps, &Dirps::der1st);
+    WField *w_y = get_block(DIR_Y), *dwdy_y = get_block(DIR_Y);
+    reorder(*w_y, ww, RDR_X2Y); tds_solve(*dwdy_y, *w_y, yd);
+    reorder(o_i, *dwdy_y, RDR_Y2X);
+    release_block(w_y); release_block(dwdy_y);
+    WField *v_z = get_block(DIR_Z), *dvdz_z = get_block(DIR_Z);
+    reorder(*v_z, vv, RDR_X2Z); tds_solve(*dvdz_z, *v_z, zd);
+    WField* dvdz_x = get_block(DIR_X);
+    reorder(*dvdz_x, *dvdz_z, RDR_Z2X);
+    release_block(v_z); release_block(dvdz_z);
+    vecadd(-1.0, *dvdz_x, 1.0, o_i);
+    release_block(dvdz_x);
+    WField *u_z = get_block(DIR_Z), *dudz_z = get_block(DIR_Z);
+    reorder(*u_z, uu, RDR_X2Z); tds_solve(*dudz_z, *u_z, zd);
+    WField* dudz_x = get_block(DIR_X);
+    reorder(*dudz_x, *dudz_z, RDR_Z2X);
+    release_block(u_z); release_block(dudz_z);
+    tds_solve(o_j, ww, xd);
+    vecadd(1.0, *dudz_x, -1.0, o_j);
+    release_block(dudz_x);
+    tds_solve(o_k, vv, xd);
+    WField *u_y = get_block(DIR_Y), *dudy_y = get_block(DIR_Y);
+    reorder(*u_y, uu, RDR_X2Y); tds_solve(*dudy_y, *u_y, yd);
+    WField* dudy_x = get_block(DIR_X);
+    reorder(*dudy_x, *dudy_y, RDR_Y2X);
+    release_block(u_y); release_block(dudy_y);
+    vecadd(-1.0, *dudy_x, 1.0, o_k);
+    release_block(dudy_x);
+  }
+
+  // ---------------------------------------------------------------- poisson_fft.f90:833-882
+  static void wave_numbers(std::vector<double>& a, std::vector<double>& b, std::vector<cplx>& k, std::vector<cplx>& e,
+                           std::vector<cplx>& k2, int n, double L, double d, bool periodic, double c_a, double c_b,
+                           double c_alpha) {
+    a.assign(n + 1, 0); b.assign(n + 1, 0);
+    k.assign(n + 1, 0); e.assign(n + 1, 0); k2.assign(n + 1, 0);
+    for (int i = 1; i <= n; ++i) {
+      if (periodic) { a[i] = std::sin((i - 1) * pi / n); b[i] = std::cos((i - 1) * pi / n); }
+      else { a[i] = std::sin((i - 1) * pi / 2 / n); b[i] = std::cos((i - 1) * pi / 2 / n); }
+    }
+    auto one = [&](int i, double w) {
+      double wp = c_a * 2 * d * std::sin(0.5 * w) + c_b * 2 * d * std::sin(1.5 * w);
+      wp = wp / (1.0 + 2 * c_alpha * std::cos(w));
+      k[i] = cplx(1.0, 1.0) * (n * wp / L);
+      e[i] = cplx(1.0, 1.0) * (n * w / L);
+      double q = n * wp / L;
+      k2[i] = cplx(1.0, 1.0) * (q * q);
+    };
+    if (periodic) {
+      for (int i = 1; i <= n / 2 + 1; ++i) one(i, 2 * pi * (i - 1) / n);
+      for (int i = n / 2 + 2; i <= n; ++i) { k[i] = k[n - i + 2]; e[i] = e[n - i + 2]; k2[i] = k2[n - i + 2]; }
+    } else {
+      for (int i = 1; i <= n; ++i) one(i, pi * (i - 1) / n);
+    }
+  }
+
+  // poisson_fft.f90:120-204 (000 only) + waves_set :654-831 (periodic-z branch :777-819).
+  // The emulation keeps the whole spectral pencil (nx/2+1, ny, nz) in one array (sp_st = 0): 2DECOMP's
+  // distributed transform of the gathered field equals the global transform.
+  void init_poisson() {
+    if (!(gm.periodic_BC[0] && gm.periodic_BC[1] && gm.periodic_BC[2])) return;  // 010 etc: not in the OMP oracle
+    int nx = gm.global_cell_dims[0], ny = gm.global_cell_dims[1], nz = gm.global_cell_dims[2];
+    nx_spec = nx / 2 + 1; ny_spec = ny; nz_spec = nz;
+    const Tdsops &sx = xdirps[0].stagder_v2p, &sy = ydirps[0].stagder_v2p, &sz_ = zdirps[0].stagder_v2p;
+    const Tdsops &ix = xdirps[0].interpl_v2p, &iy = ydirps[0].interpl_v2p, &iz = zdirps[0].interpl_v2p;
+    wave_numbers(ax, bx, kx, exs, k2x, nx, gm.L[0], gm.d[0], gm.periodic_BC[0], sx.a, sx.b, sx.alpha);
+    wave_numbers(ay, by, ky, eys, k2y, ny, gm.L[1], gm.d[1], gm.periodic_BC[1], sy.a, sy.b, sy.alpha);
+    wave_numbers(az, bz, kz, ezs, k2z, nz, gm.L[2], gm.d[2], gm.periodic_BC[2], sz_.a, sz_.b, sz_.alpha);
+    waves.assign((size_t)nx_spec * ny_spec * nz_spec, 0);
+    c_x.assign(waves.size(), 0);
+    for (int k = 1; k <= nz_spec; ++k)
+      for (int j = 1; j <= ny_spec; ++j)
+        for (int i = 1; i <= nx_spec; ++i) {
+          double rlexs = exs[i].real() * gm.d[0], rleys = eys[j].real() * gm.d[1], rlezs = ezs[k].real() * gm.d[2];
+          double xtt = 2 * (ix.a * std::cos(rlexs * 0.5) + ix.b * std::cos(rlexs * 1.5) + ix.c * std::cos(rlexs * 2.5) + ix.d * std::cos(rlexs * 3.5));
+          double ytt = 2 * (iy.a * std::cos(rleys * 0.5) + iy.b * std::cos(rleys * 1.5) + iy.c * std::cos(rleys * 2.5) + iy.d * std::cos(rleys * 3.5));
+          double ztt = 2 * (iz.a * std::cos(rlezs * 0.5) + iz.b * std::cos(rlezs * 1.5) + iz.c * std::cos(rlezs * 2.5) + iz.d * std::cos(rlezs * 3.5));
+          double xt1 = 1.0 + 2 * ix.alpha * std::cos(rlexs);
+          double yt1 = 1.0 + 2 * iy.alpha * std::cos(rleys);
+          double zt1 = 1.0 + 2 * iz.alpha * std::cos(rlezs);
+          double fx = (ytt / yt1) * (ztt / zt1), fy = (xtt / xt1) * (ztt / zt1), fz = (xtt / xt1) * (ytt / yt1);
+          cplx xt2 = k2x[i] * (fx * fx), yt2 = k2y[j] * (fy * fy), zt2 = k2z[k] * (fz * fz);
+          waves[(i - 1) + (size_t)nx_spec * ((j - 1) + (size_t)ny_spec * (k - 1))] = xt2 + yt2 + zt2;
+        }
+  }
+
+  // omp/kernels/spectral_processing.f90:7-106
+  void process_spectral_000() {
+    const int nx = gm.global_cell_dims[0], ny = gm.global_cell_dims[1], nz = gm.global_cell_dims[2];
+#pragma omp parallel for collapse(2)
+    for (int k = 1; k <= nz_spec; ++k)
+      for (int j = 1; j <= ny_spec; ++j)
+        for (int i = 1; i <= nx_spec; ++i) {
+          size_t idx = (i - 1) + (size_t)nx_spec * ((j - 1) + (size_t)ny_spec * (k - 1));
+          double div_r = c_x[idx].real() / nx / ny / nz;
+          double div_c = c_x[idx].imag() / nx / ny / nz;
+          int ix = i, iy = j, iz = k;
+          double tmp_r = div_r, tmp_c = div_c;
+          div_r = tmp_r * bz[iz] + tmp_c * az[iz];
+          div_c = tmp_c * bz[iz] - tmp_r * az[iz];
+          if (iz > nz / 2 + 1) div_r = -div_r;
+          if (iz > nz / 2 + 1) div_c = -div_c;
+          tmp_r = div_r; tmp_c = div_c;
+          div_r = tmp_r * by[iy] + tmp_c * ay[iy];
+          div_c = tmp_c * by[iy] - tmp_r * ay[iy];
+          if (iy > ny / 2 + 1) div_r = -div_r;
+          if (iy > ny / 2 + 1) div_c = -div_c;
+          tmp_r = div_r; tmp_c = div_c;
+          div_r = tmp_r * bx[ix] + tmp_c * ax[ix];
+          div_c = tmp_c * bx[ix] - tmp_r * ax[ix];
+          tmp_r = waves[idx].real(); tmp_c = waves[idx].imag();
+          if ((tmp_r < 1.e-16) || (tmp_c < 1.e-16)) { div_r = 0.0; div_c = 0.0; }
+          else { div_r = -div_r / tmp_r; div_c = -div_c / tmp_c; }
+          tmp_r = div_r; tmp_c = div_c;
+          div_r = tmp_r * bz[iz] - tmp_c * az[iz];
+          div_c = -tmp_c * bz[iz] - tmp_r * az[iz];
+          if (iz > nz / 2 + 1) div_r = -div_r;
+          if (iz > nz / 2 + 1) div_c = -div_c;
+          tmp_r = div_r; tmp_c = div_c;
+          div_r = tmp_r * by[iy] + tmp_c * ay[iy];
+          div_c = tmp_c * by[iy] - tmp_r * ay[iy];
+          if (iy > ny / 2 + 1) div_r = -div_r;
+          if (iy > ny / 2 + 1) div_c = -div_c;
+          tmp_r = div_r; tmp_c = div_c;
+          div_r = tmp_r * bx[ix] + tmp_c * ax[ix];
+          div_c = -tmp_c * bx[ix] + tmp_r * ax[ix];
+          c_x[idx] = cplx(div_r, div_c);
+        }
+  }
+
+  // gather a DIR_C WField (CELL extents) into a global array and back
+  void gather_c(std::vector<double>& g, const WField& c) {
+    int nx = gm.global_cell_dims[0], ny = gm.global_cell_dims[1], nz = gm.global_cell_dims[2];
+    g.assign((size_t)nx * ny * nz, 0.0);
+    const int* cp = alloc.padded(DIR_C);
+    for (int r = 0; r < P; ++r)
+      for (int k = 0; k < rm[r].cell_dims[2]; ++k)
+        for (int j = 0; j < rm[r].cell_dims[1]; ++j)
+          for (int i = 0; i < rm[r].cell_dims[0]; ++i)
+            g[(i + rm[r].n_offset[0]) + (size_t)nx * ((j + rm[r].n_offset[1]) + (size_t)ny * (k + rm[r].n_offset[2]))] =
+                c.r[r][i + (size_t)cp[0] * (j + (size_t)cp[1] * k)];
+  }
+  void scatter_c(WField& c, const std::vector<double>& g) {
+    int nx = gm.global_cell_dims[0], ny = gm.global_cell_dims[1];
+    const int* cp = alloc.padded(DIR_C);
+    for (int r = 0; r < P; ++r)
+      for (int k = 0; k < rm[r].cell_dims[2]; ++k)
+        for (int j = 0; j < rm[r].cell_dims[1]; ++j)
+          for (int i = 0; i < rm[r].cell_dims[0]; ++i)
+            c.r[r][i + (size_t)cp[0] * (j + (size_t)cp[1] * k)] =
+                g[(i + rm[r].n_offset[0]) + (size_t)nx * ((j + rm[r].n_offset[1]) + (size_t)ny * (k + rm[r].n_offset[2]))];
+  }
+
+  // omp/poisson_fft.f90:89-97 / :129-137 on the gathered field
+  void fft_forward(const WField& f_c) {
+    std::vector<double> g;
+    gather_c(g, f_c);
+    int nx = gm.global_cell_dims[0], ny = gm.global_cell_dims[1], nz = gm.global_cell_dims[2];
+    fft3d_forward(g.data(), nx, ny, nx, ny, nz, c_x.data());
+  }
+  void fft_backward(WField& f_c) {
+    int nx = gm.global_cell_dims[0], ny = gm.global_cell_dims[1], nz = gm.global_cell_dims[2];
+    std::vector<double> g((size_t)nx * ny * nz);
+    fft3d_backward(c_x.data(), nx, ny, nz, g.data(), nx, ny);
+    scatter_c(f_c, g);
+  }
+
+  // solver.f90:653-678 + poisson_fft.f90:216-226
+  void poisson_fft(WField& pressure, const WField& div_u) {
+    WField* p_temp = get_block(DIR_C);
+    reorder(*p_temp, div_u, RDR_Z2C);
+    WField* temp = get_block(DIR_C);
+    fft_forward(*p_temp);
+    process_spectral_000();
+    fft_backward(*p_temp);
+    release_block(temp);
+    reorder(pressure, *p_temp, RDR_C2Z);
+    release_block(p_temp);
+  }
+
+  // solver.f90:693-739
+  void pressure_correction(WField& uu, WField& vv, WField& ww) {
+    WField* div_u = get_block(DIR_Z);
+    divergence_v2c(*div_u, uu, vv, ww);
+    WField* p = get_block(DIR_Z);
+    poisson_fft(*p, *div_u);
+    release_block(div_u);
+    WField *dpdx = get_block(DIR_X), *dpdy = get_block(DIR_X), *dpdz = get_block(DIR_X);
+    gradient_c2v(*dpdx, *dpdy, *dpdz, *p);
+    release_block(p);
+    vecadd(-1.0, *dpdx, 1.0, uu);
+    vecadd(-1.0, *dpdy, 1.0, vv);
+    vecadd(-1.0, *dpdz, 1.0, ww);
+    release_block(dpdx); release_block(dpdy); release_block(dpdz);
+  }
+
+  // ---------------------------------------------------------------- time_integrator.f90:70-164
+  void init_time_integrator() {
+    std::memset(ti_coeffs, 0, sizeof ti_coeffs);
+    std::memset(ti_rk_b, 0, sizeof ti_rk_b);
+    std::memset(ti_rk_a, 0, sizeof ti_rk_a);
+    // rk_a(i, j, order), rk_b(i, order), coeffs(i, order) — 1-based
+    ti_rk_b[1][1] = 1.0;
+    ti_rk_a[1][1][2] = 0.5; ti_rk_b[2][2] = 1.0;
+    ti_rk_a[1][1][3] = 0.5; ti_rk_a[2][2][3] = 3.0 / 4.0;
+    ti_rk_b[1][3] = 2.0 / 9.0; ti_rk_b[2][3] = 1.0 / 3.0; ti_rk_b[3][3] = 4.0 / 9.0;
+    ti_rk_a[1][1][4] = 0.5; ti_rk_a[2][2][4] = 0.5; ti_rk_a[3][3][4] = 1.0;
+    ti_rk_b[1][4] = 1.0 / 6.0; ti_rk_b[2][4] = 1.0 / 3.0; ti_rk_b[3][4] = 1.0 / 3.0; ti_rk_b[4][4] = 1.0 / 6.0;
+    ti_coeffs[1][1] = 1.0;
+    ti_coeffs[1][2] = 1.5; ti_coeffs[2][2] = -0.5;
+    ti_coeffs[1][3] = 23.0 / 12.0; ti_coeffs[2][3] = -4.0 / 3.0; ti_coeffs[3][3] = 5.0 / 12.0;
+    ti_coeffs[1][4] = 55.0 / 24.0; ti_coeffs[2][4] = -59.0 / 24.0; ti_coeffs[3][4] = 37.0 / 24.0; ti_coeffs[4][4] = -3.0 / 8.0;
+    const std::string& m = cfg.time_intg;
+    ti_order = m[2] - '0';
+    if (ti_order < 1 || ti_order > 4) fail("Integration order >4 is not supported");
+    if (m.substr(0, 2) == "AB") { ti_is_ab = true; ti_nstep = ti_order; ti_nstage = 1; ti_nolds = ti_nstep - 1; }
+    else if (m.substr(0, 2) == "RK") { ti_is_ab = false; ti_nstep = 1; ti_nstage = ti_order; ti_nolds = ti_nstage; }
+    else fail("Integration method is not defined");
+    ti_istep = 1; ti_istage = 1;
+    olds.assign(3, std::vector<WField*>(ti_nolds + 1, nullptr));
+    for (int i = 0; i < 3; ++i)
+      for (int j = 1; j <= ti_nolds; ++j) olds[i][j] = get_block(DIR_X);
+  }
+
+  // time_integrator.f90:166-231
+  void runge_kutta(WField* curr[3], WField* deriv[3], double dt_) {
+    if (ti_istage == ti_nstage) {
+      for (int i = 0; i < 3; ++i) {
+        if (ti_nstage > 1) veccopy(*curr[i], *olds[i][1]);
+        for (int j = 1; j <= ti_nstage - 1; ++j) vecadd(ti_rk_b[j][ti_nstage] * dt_, *olds[i][j + 1], 1.0, *curr[i]);
+        vecadd(ti_rk_b[ti_nstage][ti_nstage] * dt_, *deriv[i], 1.0, *curr[i]);
+      }
+      ti_istage = 1;
+    } else {
+      for (int i = 0; i < 3; ++i) {
+        if (ti_istage == 1) veccopy(*olds[i][1], *curr[i]);
+        veccopy(*olds[i][ti_istage + 1], *deriv[i]);
+        if (ti_istage > 1) veccopy(*curr[i], *olds[i][1]);
+        for (int j = 1; j <= ti_istage; ++j)
+          vecadd(ti_rk_a[j][ti_istage][ti_nstage] * dt_, *olds[i][j + 1], 1.0, *curr[i]);
+      }
+      ti_istage = ti_istage + 1;
+    }
+  }
+  // time_integrator.f90:233-300
+  void adams_bashforth(WField* curr[3], WField* deriv[3], double dt_) {
+    int nstep = std::min(ti_istep, ti_nstep);
+    for (int i = 0; i < 3; ++i) {
+      vecadd(ti_coeffs[1][nstep] * dt_, *deriv[i], 1.0, *curr[i]);
+      for (int j = 2; j <= nstep; ++j) vecadd(ti_coeffs[j][nstep] * dt_, *olds[i][j - 1], 1.0, *curr[i]);
+      auto rotate = [&](int n) {
+        WField* ptr = olds[i][n];
+        for (int q = n; q >= 2; --q) olds[i][q] = olds[i][q - 1];
+        olds[i][1] = ptr;
+      };
+      if (nstep < ti_nstep) { if (ti_istep > 1) rotate(nstep); }
+      else { if (ti_nstep > 2) rotate(nstep - 1); }
+      if (ti_nstep > 1) veccopy(*olds[i][1], *deriv[i]);
+    }
+    ti_istep = ti_istep + 1;
+  }
+
+  // case/base_case.f90:246-289, one full time step (all sub-stages)
+  void step() {
+    WField* curr[3] = {u, v, w};
+    for (int sub = 1; sub <= ti_nstage; ++sub) {
+      WField* deriv[3] = {get_block(DIR_X), get_block(DIR_X), get_block(DIR_X)};
+      transeq_default(*deriv[0], *deriv[1], *deriv[2], *u, *v, *w);
+      if (ti_is_ab) adams_bashforth(curr, deriv, dt); else runge_kutta(curr, deriv, dt);
+      for (int i = 0; i < 3; ++i) release_block(deriv[i]);
+      pressure_correction(*u, *v, *w);
+    }
+  }
+
+  // case/tgv.f90:41-72 via base_case.f90:set_init (:139-179)
+  void init_tgv() {
+    int nx = gm.global_vert_dims[0], ny = gm.global_vert_dims[1], nz = gm.global_vert_dims[2];
+    std::vector<double> gu((size_t)nx * ny * nz), gv(gu.size());
+    for (int r = 0; r < P; ++r) {
+      const RankMesh& m = rm[r];
+      for (int k = 0; k < m.vert_dims[2]; ++k)
+        for (int j = 0; j < m.vert_dims[1]; ++j)
+          for (int i = 0; i < m.vert_dims[0]; ++i) {
+            double x = m.geo.vert_coords[0][i], y = m.geo.vert_coords[1][j], z = m.geo.vert_coords[2][k];
+            size_t gi = (i + m.n_offset[0]) + (size_t)nx * ((j + m.n_offset[1]) + (size_t)ny * (k + m.n_offset[2]));
+            gu[gi] = std::sin(x) * std::cos(y) * std::cos(z);
+            gv[gi] = -std::cos(x) * std::sin(y) * std::cos(z);
+          }
+    }
+    set_field_from_global(*u, gu.data(), VERT);
+    set_field_from_global(*v, gv.data(), VERT);
+    for (auto& rr : w->r) std::fill(rr.begin(), rr.end(), 0.0);
+    u->data_loc = VERT; v->data_loc = VERT; w->data_loc = VERT;
+  }
+
+  // postprocess/monitoring.f90:46-90
+  double enstrophy() {
+    WField *du = get_block(DIR_X, VERT), *dv = get_block(DIR_X, VERT), *dw = get_block(DIR_X, VERT);
+    curl(*du, *dv, *dw, *u, *v, *w);
+    double e = 0.5 * (scalar_product(*du, *du) + scalar_product(*dv, *dv) + scalar_product(*dw, *dw)) / ngrid_global;
+    release_block(du); release_block(dv); release_block(dw);
+    return e;
+  }
+  // KE built with the same normalisation from scalar_product
+  double kinetic_energy() {
+    return 0.5 * (scalar_product(*u, *u) + scalar_product(*v, *v) + scalar_product(*w, *w)) / ngrid_global;
+  }
+  void divergence_max_mean(double& mx, double& mean) {
+    WField* div_u = get_block(DIR_Z);
+    divergence_v2c(*div_u, *u, *v, *w);
+    field_max_mean(mx, mean, *div_u);
+    release_block(div_u);
+  }
+};
+
+}  // namespace orc
