@@ -1,0 +1,182 @@
+/* x3d2c.h — C ABI of the `cuda_c` backend: a B200 (sm_100a) implementation of x3d2's per-timestep
+ * right-hand-side + pressure hot path, behind the reference's own operator API.
+ *
+ * Every entry point replaces one deferred procedure of the reference's abstract backend
+ *   type, abstract :: base_backend_t      /root/reference/src/backend/backend.f90:13-62
+ *   type, abstract :: poisson_fft_t       /root/reference/src/poisson_fft.f90:9-70
+ * and is what a Fortran `iso_c_binding` shim (`cuda_c_backend_t`) binds to.
+ *
+ * Conventions
+ *  - All functions return an int status (X3D2C_OK == 0). The reference aborts (`error stop`) on misuse;
+ *    the shim turns a non-zero status into `error stop x3d2c_last_error()`.
+ *  - Plain pointers and sizes only. `double*` field arguments are DEVICE pointers obtained from
+ *    x3d2c_field_alloc; host arrays are named `host_*`.
+ *  - One CUDA stream per context; every op is enqueued in call order and is asynchronous unless it
+ *    returns a scalar or copies to the host (those synchronise the stream).
+ *  - Layout contract: only DIR_C (Cartesian, Fortran order (nx_pad, ny_pad, nz), x fastest) is defined
+ *    externally (src/allocator.f90:91). The DIR_X/Y/Z pencil-group layouts are private to the backend
+ *    (SURVEY.md F2): nothing outside a backend indexes directional data.
+ *  - Padding follows src/allocator.f90:72-76 with sz = X3D2C_SZ.
+ */
+#ifndef X3D2C_H
+#define X3D2C_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define X3D2C_SZ 32 /* pencil-group width, role of src/backend/cuda/common.f90:4 */
+
+/* status codes */
+#define X3D2C_OK 0
+#define X3D2C_EINVAL 1
+#define X3D2C_ECUDA 2
+#define X3D2C_ENCCL 3
+#define X3D2C_EUNSUPPORTED 4
+#define X3D2C_ENOMEM 5
+
+/* src/common.f90:23-39 */
+#define X3D2C_DIR_X 1
+#define X3D2C_DIR_Y 2
+#define X3D2C_DIR_Z 3
+#define X3D2C_DIR_C 4
+#define X3D2C_RDR_X2Y 12
+#define X3D2C_RDR_X2Z 13
+#define X3D2C_RDR_Y2X 21
+#define X3D2C_RDR_Y2Z 23
+#define X3D2C_RDR_Z2X 31
+#define X3D2C_RDR_Z2Y 32
+#define X3D2C_RDR_C2X 41
+#define X3D2C_RDR_C2Y 42
+#define X3D2C_RDR_C2Z 43
+#define X3D2C_RDR_X2C 14
+#define X3D2C_RDR_Y2C 24
+#define X3D2C_RDR_Z2C 34
+#define X3D2C_VERT 0
+#define X3D2C_CELL 1110
+#define X3D2C_X_FACE 1100
+#define X3D2C_Y_FACE 1010
+#define X3D2C_Z_FACE 110
+#define X3D2C_X_EDGE 10
+#define X3D2C_Y_EDGE 100
+#define X3D2C_Z_EDGE 1000
+
+/* context flags */
+#define X3D2C_FLAG_STRICT 1 /* reference-order arithmetic, no FMA contraction: bit-exact vs the OMP backend */
+
+typedef struct x3d2c_ctx x3d2c_ctx;
+typedef struct x3d2c_tdsops x3d2c_tdsops;
+typedef struct x3d2c_poisson x3d2c_poisson;
+
+/* What cuda_backend_t%init receives through mesh_t + allocator_t
+ * (src/backend/cuda/backend.f90:95-152, src/mesh.f90:37-158, src/mesh_content.f90:28-59). */
+typedef struct {
+  int dims_vert[3];        /* mesh%get_dims(VERT): local vertex counts            */
+  int dims_cell[3];        /* mesh%get_dims(CELL)                                  */
+  int dims_vert_global[3]; /* mesh%get_global_dims(VERT)                           */
+  int dims_cell_global[3]; /* mesh%get_global_dims(CELL)                           */
+  int nproc_dir[3];        /* mesh%par%nproc_dir                                   */
+  int nrank_dir[3];        /* mesh%par%nrank_dir                                   */
+  int n_offset[3];         /* mesh%par%n_offset                                    */
+  int pprev[3], pnext[3];  /* mesh%par%pprev / pnext (ranks of the communicator)   */
+  int periodic[3];         /* mesh%grid%periodic_BC                                */
+  int sz;                  /* must be X3D2C_SZ; the Fortran allocator pads with it */
+  int rank, nproc;         /* mesh%par%nrank / nproc                               */
+  int device;              /* CUDA device ordinal; -1 keeps the current device     */
+  int flags;               /* X3D2C_FLAG_*                                         */
+  const void* nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks; NULL when nproc == 1 */
+} x3d2c_config;
+
+const char* x3d2c_last_error(void);
+int x3d2c_version(void);
+
+/* ---- backend object: cuda_backend_t%init / finaliser (src/backend/cuda/backend.f90:95-152) */
+int x3d2c_create(const x3d2c_config* cfg, x3d2c_ctx** out);
+int x3d2c_destroy(x3d2c_ctx* ctx);
+int x3d2c_sync(x3d2c_ctx* ctx);
+/* padded Cartesian dims, ngrid = product (src/allocator.f90:64-93); n_groups per DIR_X/Y/Z */
+int x3d2c_get_padded_dims(const x3d2c_ctx* ctx, int dims_padded[3], int n_groups[3], long long* ngrid);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+long long x3d2c_launch_count(const x3d2c_ctx* ctx);
+/* the context's cudaStream_t as an opaque pointer (for event timing on the launching stream) */
+void* x3d2c_stream(const x3d2c_ctx* ctx);
+
+/* ---- field storage: cuda_allocator_t%create_block / cuda_field_t%fill
+ *      (src/backend/cuda/allocator.f90:44-90). Pool semantics (get_block/release_block) stay with the caller. */
+int x3d2c_field_alloc(x3d2c_ctx* ctx, double** dev);
+int x3d2c_field_free(x3d2c_ctx* ctx, double* dev);
+int x3d2c_field_fill(x3d2c_ctx* ctx, double* dev, double c);
+/* copy_data_to_f / copy_f_to_data (src/backend/backend.f90:327-349): whole padded block, ngrid doubles */
+int x3d2c_copy_data_to_f(x3d2c_ctx* ctx, double* dev, const double* host_data);
+int x3d2c_copy_f_to_data(x3d2c_ctx* ctx, double* host_data, const double* dev);
+
+/* ---- alloc_tdsops (src/backend/backend.f90:351-372; upload pattern of src/backend/cuda/tdsops.f90:31-90).
+ * The host computes the tables with tdsops_init (src/tdsops.f90:63-203) and passes them in:
+ *   coeffs[9]; coeffs_s / coeffs_e as [row 0..3][tap 0..8] (= Fortran coeffs_s(tap, row));
+ *   dist_fw/bw/sa/sc/af with n_rhs entries; stretch / stretch_correct with n_tds entries. */
+int x3d2c_tdsops_create(x3d2c_ctx* ctx, int n_tds, int n_rhs, int move, int periodic, const double* coeffs,
+                        const double* coeffs_s, const double* coeffs_e, const double* dist_fw,
+                        const double* dist_bw, const double* dist_sa, const double* dist_sc,
+                        const double* dist_af, const double* stretch, const double* stretch_correct,
+                        x3d2c_tdsops** out);
+int x3d2c_tdsops_destroy(x3d2c_ctx* ctx, x3d2c_tdsops* ops);
+
+/* ---- transeq_x / transeq_y / transeq_z (src/backend/backend.f90:64-86, cuda/backend.f90:244-319).
+ * du, dv, dw, u, v, w are the caller's fields in natural order; `dir` selects which of them is the
+ * line-aligned velocity (the permutation of src/backend/omp/backend.f90:154,168,182 is done here). */
+int x3d2c_transeq(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, const double* u, const double* v,
+                  const double* w, double nu, const x3d2c_tdsops* der1st, const x3d2c_tdsops* der1st_sym,
+                  const x3d2c_tdsops* der2nd, const x3d2c_tdsops* der2nd_sym);
+
+/* ---- tds_solve (src/backend/backend.f90:108-126, cuda/backend.f90:449-521). data_loc bookkeeping
+ * (move_data_loc) stays on the caller's field_t. */
+int x3d2c_tds_solve(x3d2c_ctx* ctx, int dir, double* du, const double* u, const x3d2c_tdsops* ops);
+
+/* ---- reorder (src/backend/backend.f90:128-144), rdr is one of X3D2C_RDR_* */
+int x3d2c_reorder(x3d2c_ctx* ctx, int rdr, double* dst, const double* src);
+/* ---- sum_yintox / sum_zintox (src/backend/backend.f90:146-159): u (DIR_X) += reorder(u_) */
+int x3d2c_sum_yintox(x3d2c_ctx* ctx, double* u, const double* u_y);
+int x3d2c_sum_zintox(x3d2c_ctx* ctx, double* u, const double* u_z);
+
+/* ---- veccopy / vecadd / vecmult (src/backend/backend.f90:161-201): whole padded block */
+int x3d2c_veccopy(x3d2c_ctx* ctx, double* dst, const double* src);
+int x3d2c_vecadd(x3d2c_ctx* ctx, double a, const double* x, double b, double* y);
+int x3d2c_vecmult(x3d2c_ctx* ctx, double* y, const double* x);
+/* ---- field_scale / field_shift (src/backend/backend.f90:255-266) */
+int x3d2c_field_scale(x3d2c_ctx* ctx, double* f, double a);
+int x3d2c_field_shift(x3d2c_ctx* ctx, double* f, double a);
+
+/* ---- scalar_product (src/backend/backend.f90:203-216): global (all-reduced) sum over the un-padded
+ * entries of mesh%get_dims(data_loc); x and y share `dir`. Synchronous. */
+int x3d2c_scalar_product(x3d2c_ctx* ctx, int dir, int data_loc, const double* x, const double* y, double* s);
+/* ---- field_max_mean (src/backend/backend.f90:218-236): max|f| and sum|f| / N_global. Synchronous. */
+int x3d2c_field_max_mean(x3d2c_ctx* ctx, int dir, int data_loc, const double* f, double* max_val, double* mean_val);
+/* ---- field_volume_integral (src/backend/backend.f90:268-279): DIR_X only. Synchronous. */
+int x3d2c_field_volume_integral(x3d2c_ctx* ctx, int data_loc, const double* f, double* s);
+
+/* ---- init_poisson_fft (src/backend/backend.f90:374-391) and the poisson_fft_t hooks
+ * (src/poisson_fft.f90:45-62,72-116). The spectral buffer is hidden state of the handle between
+ * fft_forward / fft_postprocess / fft_backward; both transforms are unnormalised
+ * (tests/verification/test_fft.f90:162-166). */
+/* spectral pencil owned by this rank: extents and offsets passed to poisson_fft_t%base_init */
+int x3d2c_poisson_spec_layout(const x3d2c_ctx* ctx, int n_spec[3], int n_sp_st[3]);
+/* waves: complex(dp) waves(nx_spec, ny_spec, nz_spec) as interleaved re/im (src/poisson_fft.f90:23,163);
+ * ax..bz: the global wave-number tables of src/poisson_fft.f90:148-150 (nx_glob / ny_glob / nz_glob entries) */
+int x3d2c_poisson_create(x3d2c_ctx* ctx, const double* waves, const double* ax, const double* bx,
+                         const double* ay, const double* by, const double* az, const double* bz,
+                         x3d2c_poisson** out);
+int x3d2c_poisson_destroy(x3d2c_ctx* ctx, x3d2c_poisson* p);
+int x3d2c_fft_forward(x3d2c_ctx* ctx, x3d2c_poisson* p, const double* f_c);  /* f_c: DIR_C block */
+int x3d2c_fft_postprocess_000(x3d2c_ctx* ctx, x3d2c_poisson* p);
+int x3d2c_fft_backward(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_c);
+/* debugging / tests: copy the spectral buffer (reference index order (i, j, k), interleaved re/im) to the host */
+int x3d2c_poisson_get_spectrum(x3d2c_ctx* ctx, x3d2c_poisson* p, double* host_spec);
+
+/* ---- not on the hot path of any BASELINE.json config: reported as unsupported
+ * transeq_species (src/backend/backend.f90:88-106) */
+int x3d2c_transeq_species(x3d2c_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* X3D2C_H */

@@ -1,0 +1,56 @@
+"""Per-operator device timing (CUDA events on the backend's stream) against the algorithmic bytes of SURVEY.md §8d.
+
+usage: python tools/opbench.py [N] [--strict]
+"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import x3d2_b200 as X
+
+BYTES_PER_PT = {"transeq_x": 48, "transeq_y": 48, "transeq_z": 48, "tds_solve_x": 16, "tds_solve_y": 16, "tds_solve_z": 16,
+                "reorder_x2y": 16, "reorder_x2z": 16, "reorder_y2x": 16, "reorder_y2z": 16, "reorder_z2y": 16,
+                "reorder_z2c": 16, "reorder_c2z": 16, "reorder_z2x": 16, "sum_yintox": 24, "sum_zintox": 24, "vecadd": 24,
+                "veccopy": 16, "poisson": 152, "pressure_correction": 256 + 152 + 208 + 72, "transeq": 384}
+
+
+def time_op(sim, op, reps, stream):
+    sim.bench_op(op, 2)
+    sim.sync()
+    with torch.cuda.stream(stream):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        sim.bench_op(op, reps)
+        e1.record(stream)
+    e1.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 256
+    strict = "--strict" in sys.argv
+    peak = 6541.8
+    try:
+        peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    sim = X.Sim((n, n, n), strict=strict)
+    sim.init_tgv()
+    stream = torch.cuda.ExternalStream(sim.stream())
+    npts = n ** 3
+    rows = []
+    for op, b in BYTES_PER_PT.items():
+        ms = time_op(sim, op, 5, stream)
+        gbs = b * npts / ms / 1e6
+        rows.append((op, ms, gbs, gbs / peak))
+        print(f"{op:22s} {ms:9.3f} ms  {gbs:9.1f} GB/s  {100 * gbs / peak:6.1f}% of measured {peak:.0f} GB/s", flush=True)
+    t0 = time_op(sim, "transeq", 3, stream) + time_op(sim, "pressure_correction", 3, stream)
+    print(f"N={n} strict={strict}")
+    sim.close()
+
+
+if __name__ == "__main__":
+    main()

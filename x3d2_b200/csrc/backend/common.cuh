@@ -1,0 +1,126 @@
+// Internal declarations of the cuda_c backend (libx3d2c.so). Not part of the ABI.
+//
+// Private directional layouts (SURVEY.md F2 lets a backend choose; SZ = 32 lanes):
+//   DIR_X (i_l, j, g): y = yb*SZ + i_l, x = j, g = yb + nyb*z      idx = i_l + SZ*(x + nx_pad*(yb + nyb*z))
+//   DIR_Y (i_l, j, g): x = xb*SZ + i_l, y = j, g = xb + nxb*z      idx = i_l + SZ*(y + ny_pad*(xb + nxb*z))
+//   DIR_Z (i_l, j, g): x = xb*SZ + i_l, z = j, g = xb + nxb*y      idx = i_l + SZ*(z + nz*(xb + nxb*y))
+//   DIR_C            : idx = x + nx_pad*(y + ny_pad*z)             (the only externally defined layout)
+// Y, Z and C keep x fastest, so Y<->Z<->C are 256-byte granule permutations; anything involving X is a
+// 32x32 tile transpose.
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../../include/x3d2c.h"
+
+#define SZ X3D2C_SZ
+
+namespace x3d2c {
+
+void set_error(const std::string& msg);
+
+#define X3D2C_CHECK_CUDA(expr)                                                                      \
+  do {                                                                                              \
+    cudaError_t e__ = (expr);                                                                       \
+    if (e__ != cudaSuccess) {                                                                       \
+      x3d2c::set_error(std::string(#expr) + ": " + cudaGetErrorString(e__) + " at " + __FILE__ + ":" + \
+                       std::to_string(__LINE__));                                                   \
+      return X3D2C_ECUDA;                                                                           \
+    }                                                                                               \
+  } while (0)
+
+#define X3D2C_CHECK_CUFFT(expr)                                                                     \
+  do {                                                                                              \
+    cufftResult r__ = (expr);                                                                       \
+    if (r__ != CUFFT_SUCCESS) {                                                                     \
+      x3d2c::set_error(std::string(#expr) + ": cufft error " + std::to_string((int)r__) + " at " +  \
+                       __FILE__ + ":" + std::to_string(__LINE__));                                  \
+      return X3D2C_ECUDA;                                                                           \
+    }                                                                                               \
+  } while (0)
+
+#define X3D2C_REQUIRE(cond, msg)       \
+  do {                                 \
+    if (!(cond)) {                     \
+      x3d2c::set_error(msg);           \
+      return X3D2C_EINVAL;             \
+    }                                  \
+  } while (0)
+
+#define X3D2C_CHECK_LAUNCH(ctx)                      \
+  do {                                               \
+    (ctx)->launches++;                               \
+    X3D2C_CHECK_CUDA(cudaGetLastError());            \
+  } while (0)
+
+struct NcclApi;  // dlopen'ed entry points (nccl.cu)
+
+}  // namespace x3d2c
+
+// Device-side view of one tdsops_t (passed by value to kernels)
+struct TdsDev {
+  int n_tds, n_rhs;
+  double coeffs[9];
+  double coeffs_s[4][9];
+  double coeffs_e[4][9];
+  const double *fw, *bw, *sa, *sc, *af, *stretch, *stretch_correct;  // device arrays, 0-based
+};
+
+struct x3d2c_tdsops {
+  int n_tds, n_rhs, move, periodic;
+  TdsDev dev;
+  double* d_block = nullptr;  // one allocation holding all seven arrays
+  std::vector<double> h_fw, h_bw, h_sa, h_sc, h_af, h_stretch, h_stretch_correct;
+  // fast-path tables (m3): generic first-order recurrences z_j = A_j z_{j-1} + B_j r_j, y_j = C_j y_{j+1} + E_j z_j
+  double* d_m3 = nullptr;
+  int has_stretch = 0, has_stretch_correct = 0;
+  unsigned tap_mask = 0x1ff;  // non-zero bulk taps
+};
+
+struct x3d2c_ctx {
+  x3d2c_config cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int strict = 0;
+  int nx_pad = 0, ny_pad = 0, nz_pad = 0;
+  int n_groups[4] = {0, 0, 0, 0};  // [dir]
+  long long ngrid = 0;
+  long long launches = 0;
+  // scratch
+  double* scratch[2] = {nullptr, nullptr};  // dud / d2u blocks of transeq (omp/backend.f90:319-320)
+  double* halo = nullptr;                   // packed halo / reduced-row exchange buffers
+  size_t halo_doubles = 0;
+  double* red = nullptr;       // device reduction scratch
+  double* red_host = nullptr;  // pinned
+  int red_blocks = 0;
+  // multi-rank
+  void* nccl_comm = nullptr;
+  x3d2c::NcclApi* nccl = nullptr;
+
+  int n_pad(int dir) const { return dir == X3D2C_DIR_X ? nx_pad : (dir == X3D2C_DIR_Y ? ny_pad : nz_pad); }
+};
+
+struct x3d2c_poisson {
+  int nx, ny, nz;          // global cell dims
+  int nxh;                 // nx/2 + 1
+  int nz_loc, ny_loc;      // slab extents (physical z-slab, spectral y-slab)
+  cufftHandle plan_r2c = 0, plan_c2r = 0, plan_y = 0, plan_z = 0;
+  bool have_plans = false;
+  cufftDoubleComplex *A = nullptr, *B = nullptr;  // A(nxh, ny, nz_loc) ; B(ny, nxh, nz) working layout
+  double* waves = nullptr;                        // interleaved re/im in B's layout
+  double *ax = nullptr, *bx = nullptr, *ay = nullptr, *by = nullptr, *az = nullptr, *bz = nullptr;
+  double* compact = nullptr;  // un-padded real buffer when the DIR_C block is padded
+};
+
+// internal launch helpers implemented across the .cu files
+namespace x3d2c {
+int launch_reorder(x3d2c_ctx* ctx, int dir_from, int dir_to, double* dst, const double* src, bool accumulate);
+int ensure_scratch(x3d2c_ctx* ctx);
+int get_dims_dataloc(const x3d2c_ctx* ctx, int data_loc, int dims[3], bool global);
+}  // namespace x3d2c

@@ -1,0 +1,262 @@
+// Elementwise field operations and reductions of the cuda_c backend.
+// Replaces veccopy/vecadd/vecmult/field_scale/field_shift (src/backend/omp/backend.f90:529-614,883-901),
+// scalar_product (:651-712), field_max_mean (:739-810), field_volume_integral (:1023-1066) and the
+// CUDA-Fortran kernels of src/backend/cuda/kernels/fieldops.f90.
+// Streaming ops move 128-bit vectors with a grid of 148 SMs x 8 CTAs; reductions are a deterministic
+// two-stage tree (per-CTA partials in a fixed order, then one CTA), not per-thread atomics.
+#include "common.cuh"
+
+namespace x3d2c {
+int allreduce(x3d2c_ctx* ctx, double* dev, size_t count, int op);  // nccl.cu
+}
+
+namespace {
+
+constexpr int kBlocks = 148 * 8;
+constexpr int kThreads = 256;
+
+enum { OP_COPY, OP_AXPBY, OP_MULT, OP_SCALE, OP_SHIFT, OP_FILL };
+
+template <int OP>
+__global__ void __launch_bounds__(kThreads)
+stream_kernel(double* __restrict__ y, const double* __restrict__ x, const double a, const double b,
+              const long long n2) {  // n2 = number of double2 elements
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  double2* y2 = reinterpret_cast<double2*>(y);
+  const double2* x2 = reinterpret_cast<const double2*>(x);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+    double2 r;
+    if (OP == OP_COPY) {
+      r = x2[i];
+    } else if (OP == OP_AXPBY) {
+      const double2 xv = x2[i], yv = y2[i];
+      r.x = a * xv.x + b * yv.x;
+      r.y = a * xv.y + b * yv.y;
+    } else if (OP == OP_MULT) {
+      const double2 xv = x2[i], yv = y2[i];
+      r.x = yv.x * xv.x;
+      r.y = yv.y * xv.y;
+    } else if (OP == OP_SCALE) {
+      const double2 yv = y2[i];
+      r.x = a * yv.x;
+      r.y = a * yv.y;
+    } else if (OP == OP_SHIFT) {
+      const double2 yv = y2[i];
+      r.x = yv.x + a;
+      r.y = yv.y + a;
+    } else {
+      r.x = a;
+      r.y = a;
+    }
+    y2[i] = r;
+  }
+}
+
+// strict variant of axpby: a*x + b*y with separately rounded products (omp/backend.f90:578)
+__global__ void __launch_bounds__(kThreads)
+axpby_strict_kernel(double* __restrict__ y, const double* __restrict__ x, const double a, const double b,
+                    const long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    y[i] = __dadd_rn(__dmul_rn(a, x[i]), __dmul_rn(b, y[i]));
+}
+
+struct RedGeom {
+  int dir;
+  int n_pad;        // padded line length
+  int n_groups;     // groups of 32 lines
+  int nblk;         // groups per plane index (nyb for X, nxb for Y and Z)
+  int n_line;       // valid points along the line
+  int n_lane_dim;   // valid extent of the dimension mapped on (lane, block)
+  int n_plane_dim;  // valid extent of the remaining dimension
+};
+
+enum { RED_DOT, RED_ABS, RED_SUM };
+
+// one warp per (j, g) row of 32 lanes; rows are dealt to warps in a fixed grid-stride order
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+reduce_stage1(const double* __restrict__ x, const double* __restrict__ y, const RedGeom q,
+              double* __restrict__ part_sum, double* __restrict__ part_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long n_rows = (long long)q.n_pad * q.n_groups;
+  const long long warps_total = (long long)gridDim.x * (kThreads / 32);
+  double s = 0.0, m = 0.0;
+  for (long long row = (long long)blockIdx.x * (kThreads / 32) + warp; row < n_rows; row += warps_total) {
+    const int g = (int)(row / q.n_pad);
+    const int j = (int)(row - (long long)g * q.n_pad);
+    const int blk = g % q.nblk, pl = g / q.nblk;
+    const bool ok = j < q.n_line && (blk * SZ + lane) < q.n_lane_dim && pl < q.n_plane_dim;
+    if (ok) {
+      const double xv = x[row * SZ + lane];
+      if (MODE == RED_DOT) {
+        s += xv * y[row * SZ + lane];
+      } else if (MODE == RED_ABS) {
+        const double av = fabs(xv);
+        s += av;
+        m = fmax(m, av);
+      } else {
+        s += xv;
+      }
+    }
+  }
+  __shared__ double sh_s[kThreads / 32], sh_m[kThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  }
+  if (lane == 0) { sh_s[warp] = s; sh_m[warp] = m; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tm = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) { ts += sh_s[w]; tm = fmax(tm, sh_m[w]); }
+    part_sum[blockIdx.x] = ts;
+    part_max[blockIdx.x] = tm;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+reduce_stage2(const double* __restrict__ part_sum, const double* __restrict__ part_max, const int n,
+              double* __restrict__ out) {
+  __shared__ double sh_s[256], sh_m[256];
+  double s = 0.0, m = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) { s += part_sum[i]; m = fmax(m, part_max[i]); }
+  sh_s[threadIdx.x] = s; sh_m[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sh_s[threadIdx.x] += sh_s[threadIdx.x + o];
+      sh_m[threadIdx.x] = fmax(sh_m[threadIdx.x], sh_m[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = sh_s[0]; out[1] = sh_m[0]; }
+}
+
+int red_geom(const x3d2c_ctx* ctx, int dir, int data_loc, RedGeom* q) {
+  int dims[3];
+  int rc = x3d2c::get_dims_dataloc(ctx, data_loc, dims, false);
+  if (rc) return rc;
+  q->dir = dir;
+  q->n_pad = ctx->n_pad(dir);
+  q->n_groups = ctx->n_groups[dir];
+  if (dir == X3D2C_DIR_X) { q->nblk = ctx->ny_pad / SZ; q->n_line = dims[0]; q->n_lane_dim = dims[1]; q->n_plane_dim = dims[2]; }
+  else if (dir == X3D2C_DIR_Y) { q->nblk = ctx->nx_pad / SZ; q->n_line = dims[1]; q->n_lane_dim = dims[0]; q->n_plane_dim = dims[2]; }
+  else if (dir == X3D2C_DIR_Z) { q->nblk = ctx->nx_pad / SZ; q->n_line = dims[2]; q->n_lane_dim = dims[0]; q->n_plane_dim = dims[1]; }
+  else { x3d2c::set_error("reductions support DIR_X/Y/Z fields only"); return X3D2C_EINVAL; }
+  return X3D2C_OK;
+}
+
+template <int MODE>
+int run_reduce(x3d2c_ctx* ctx, const double* x, const double* y, const RedGeom& q) {
+  double* ps = ctx->red;
+  double* pm = ctx->red + ctx->red_blocks;
+  double* out = ctx->red + 2 * ctx->red_blocks;
+  reduce_stage1<MODE><<<ctx->red_blocks, kThreads, 0, ctx->stream>>>(x, y, q, ps, pm);
+  X3D2C_CHECK_LAUNCH(ctx);
+  reduce_stage2<<<1, 256, 0, ctx->stream>>>(ps, pm, ctx->red_blocks, out);
+  X3D2C_CHECK_LAUNCH(ctx);
+  return X3D2C_OK;
+}
+
+int fetch2(x3d2c_ctx* ctx, double* s, double* m) {
+  double* out = ctx->red + 2 * ctx->red_blocks;
+  X3D2C_CHECK_CUDA(cudaMemcpyAsync(ctx->red_host, out, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  X3D2C_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (s) *s = ctx->red_host[0];
+  if (m) *m = ctx->red_host[1];
+  return X3D2C_OK;
+}
+
+template <int OP>
+int run_stream(x3d2c_ctx* ctx, double* y, const double* x, double a, double b) {
+  stream_kernel<OP><<<kBlocks, kThreads, 0, ctx->stream>>>(y, x, a, b, ctx->ngrid / 2);
+  X3D2C_CHECK_LAUNCH(ctx);
+  return X3D2C_OK;
+}
+
+}  // namespace
+
+using namespace x3d2c;
+
+extern "C" {
+
+int x3d2c_field_fill(x3d2c_ctx* ctx, double* dev, double c) {
+  X3D2C_REQUIRE(ctx && dev, "x3d2c_field_fill: null argument");
+  return run_stream<OP_FILL>(ctx, dev, nullptr, c, 0.0);
+}
+int x3d2c_veccopy(x3d2c_ctx* ctx, double* dst, const double* src) {
+  X3D2C_REQUIRE(ctx && dst && src, "x3d2c_veccopy: null argument");
+  return run_stream<OP_COPY>(ctx, dst, src, 0.0, 0.0);
+}
+int x3d2c_vecadd(x3d2c_ctx* ctx, double a, const double* x, double b, double* y) {
+  X3D2C_REQUIRE(ctx && x && y, "x3d2c_vecadd: null argument");
+  if (ctx->strict) {
+    axpby_strict_kernel<<<kBlocks, kThreads, 0, ctx->stream>>>(y, x, a, b, ctx->ngrid);
+    X3D2C_CHECK_LAUNCH(ctx);
+    return X3D2C_OK;
+  }
+  return run_stream<OP_AXPBY>(ctx, y, x, a, b);
+}
+int x3d2c_vecmult(x3d2c_ctx* ctx, double* y, const double* x) {
+  X3D2C_REQUIRE(ctx && x && y, "x3d2c_vecmult: null argument");
+  return run_stream<OP_MULT>(ctx, y, x, 0.0, 0.0);
+}
+int x3d2c_field_scale(x3d2c_ctx* ctx, double* f, double a) {
+  X3D2C_REQUIRE(ctx && f, "x3d2c_field_scale: null argument");
+  return run_stream<OP_SCALE>(ctx, f, nullptr, a, 0.0);
+}
+int x3d2c_field_shift(x3d2c_ctx* ctx, double* f, double a) {
+  X3D2C_REQUIRE(ctx && f, "x3d2c_field_shift: null argument");
+  return run_stream<OP_SHIFT>(ctx, f, nullptr, a, 0.0);
+}
+
+int x3d2c_scalar_product(x3d2c_ctx* ctx, int dir, int data_loc, const double* x, const double* y, double* s) {
+  X3D2C_REQUIRE(ctx && x && y && s, "x3d2c_scalar_product: null argument");
+  RedGeom q;
+  int rc = red_geom(ctx, dir, data_loc, &q);
+  if (rc) return rc;
+  rc = run_reduce<RED_DOT>(ctx, x, y, q);
+  if (rc) return rc;
+  rc = allreduce(ctx, ctx->red + 2 * ctx->red_blocks, 1, 0);  // MPI_Allreduce SUM (omp/backend.f90:708)
+  if (rc) return rc;
+  return fetch2(ctx, s, nullptr);
+}
+
+int x3d2c_field_max_mean(x3d2c_ctx* ctx, int dir, int data_loc, const double* f, double* max_val, double* mean_val) {
+  X3D2C_REQUIRE(ctx && f && max_val && mean_val, "x3d2c_field_max_mean: null argument");
+  RedGeom q;
+  int rc = red_geom(ctx, dir, data_loc, &q);
+  if (rc) return rc;
+  rc = run_reduce<RED_ABS>(ctx, f, nullptr, q);
+  if (rc) return rc;
+  double* out = ctx->red + 2 * ctx->red_blocks;
+  rc = allreduce(ctx, out, 1, 0);
+  if (rc) return rc;
+  rc = allreduce(ctx, out + 1, 1, 1);
+  if (rc) return rc;
+  double s = 0, m = 0;
+  rc = fetch2(ctx, &s, &m);
+  if (rc) return rc;
+  int g[3];
+  rc = get_dims_dataloc(ctx, data_loc, g, true);
+  if (rc) return rc;
+  *max_val = m;
+  *mean_val = s / ((double)g[0] * g[1] * g[2]);  // omp/backend.f90:802
+  return X3D2C_OK;
+}
+
+int x3d2c_field_volume_integral(x3d2c_ctx* ctx, int data_loc, const double* f, double* s) {
+  X3D2C_REQUIRE(ctx && f && s, "x3d2c_field_volume_integral: null argument");
+  RedGeom q;
+  int rc = red_geom(ctx, X3D2C_DIR_X, data_loc, &q);
+  if (rc) return rc;
+  rc = run_reduce<RED_SUM>(ctx, f, nullptr, q);
+  if (rc) return rc;
+  rc = allreduce(ctx, ctx->red + 2 * ctx->red_blocks, 1, 0);
+  if (rc) return rc;
+  return fetch2(ctx, s, nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,340 @@
+// FFT Poisson solver (periodic 000 case) of the cuda_c backend.
+// Replaces omp_poisson_fft_t / cuda_poisson_fft_t: fft_forward, fft_postprocess_000, fft_backward
+//   src/backend/omp/poisson_fft.f90:49-97,129-137,169-181
+//   src/backend/omp/kernels/spectral_processing.f90:7-106   (process_spectral_000)
+//   src/backend/cuda/poisson_fft.f90:97-260,640-720         (prior art: cuFFT 3-D plans / cuFFTMp)
+//
+// cuFFT is used for batched 1-D transforms only; everything else is hand written:
+//   forward : [strip padding] -> D2Z along x (batch ny*nz_loc) -> A(nxh, ny, nz_loc)
+//             -> tile transpose A -> B(ny, nxh, nz_loc) -> Z2Z along y (contiguous, batch nxh*nz_loc)
+//             -> [P > 1: pack + NCCL all-to-all: z-slabs -> y-slabs] -> C(ny_loc, nxh, nz)
+//             -> Z2Z along z (stride ny_loc*nxh, dist 1, batch ny_loc*nxh)
+//   spectral: one fused kernel on C: normalise, three half-cell phase rotations, division by the modified
+//             wavenumber, three inverse rotations (arithmetic order of spectral_processing.f90:36-100)
+//   backward: the mirror image, ending with Z2D along x into the DIR_C block.
+// The spectrum is therefore stored as C(j_loc, i, k) (y fastest); the reference's waves(i, j, k) table is
+// permuted to that order once at creation.
+#include "common.cuh"
+
+namespace x3d2c {
+int alltoall(x3d2c_ctx* ctx, double* recv, const double* send, size_t block_doubles);  // nccl.cu
+}
+
+namespace {
+
+// A(i, j, k) [nxh, ny, nz] <-> B(j, i, k) [ny, nxh, nz]; one 32x32 tile of complex numbers per CTA
+__global__ void __launch_bounds__(256)
+cplx_transpose_kernel(double2* __restrict__ dst, const double2* __restrict__ src, const int n0, const int n1) {
+  // src has fastest extent n0 and second extent n1; dst has fastest extent n1 and second extent n0
+  __shared__ double2 tile[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const size_t plane = (size_t)n0 * n1 * blockIdx.z;
+  const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + tx, j = j0 + ty + 8 * r;
+    if (i < n0 && j < n1) tile[ty + 8 * r][tx] = src[plane + (size_t)j * n0 + i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int j = j0 + tx, i = i0 + ty + 8 * r;
+    if (i < n0 && j < n1) dst[plane + (size_t)i * n1 + j] = tile[tx][ty + 8 * r];
+  }
+}
+
+// strip / restore the allocator padding of a DIR_C block (role of memcpy3D, cuda/kernels/spectral_processing.f90:10-60)
+template <bool TO_COMPACT>
+__global__ void __launch_bounds__(256)
+pad_copy_kernel(double* __restrict__ compact, double* __restrict__ padded, const int nx, const int ny, const int nz,
+                const int nx_pad, const int ny_pad) {
+  const size_t n = (size_t)nx * ny * nz;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t % nx);
+    const size_t r = t / nx;
+    const int j = (int)(r % ny), k = (int)(r / ny);
+    const size_t p = i + (size_t)nx_pad * (j + (size_t)ny_pad * k);
+    if (TO_COMPACT) compact[t] = padded[p];
+    else padded[p] = compact[t];
+  }
+}
+
+// z-slab -> y-slab packing: B(ny, nxh, nz_loc) -> send[r][k_loc][i][j_loc]  (and its inverse)
+template <bool PACK>
+__global__ void __launch_bounds__(256)
+slab_pack_kernel(double2* __restrict__ packed, double2* __restrict__ b, const int ny, const int ny_loc,
+                 const int nxh, const int nz_loc) {
+  const size_t n = (size_t)ny * nxh * nz_loc;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(t % ny);
+    const size_t q = t / ny;  // i + nxh * k_loc
+    const int r = j / ny_loc, jl = j - r * ny_loc;
+    const size_t p = ((size_t)r * nz_loc * nxh + q) * ny_loc + jl;
+    if (PACK) packed[p] = b[t];
+    else b[t] = packed[p];
+  }
+}
+
+struct SpecParams {
+  int ny_loc, nxh, nz;  // extents of C(j_loc, i, k)
+  int nx_g, ny_g, nz_g; // global cell dims
+  int y_off;            // sp_st(2)
+  int pow2;             // nx*ny*nz is a power of two => the normalisation is an exact scaling
+  double inv_n;
+};
+
+// spectral_processing.f90:36-100, one thread per mode of C(j_loc, i, k)
+template <bool STRICT>
+__global__ void __launch_bounds__(256)
+process_spectral_000_kernel(double2* __restrict__ c, const double2* __restrict__ waves,
+                            const double* __restrict__ ax, const double* __restrict__ bx,
+                            const double* __restrict__ ay, const double* __restrict__ by,
+                            const double* __restrict__ az, const double* __restrict__ bz, const SpecParams p) {
+  const int jl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (jl >= p.ny_loc) return;
+  const int i = blockIdx.y, k = blockIdx.z;
+  const size_t idx = jl + (size_t)p.ny_loc * (i + (size_t)p.nxh * k);
+  const int ix = i, iy = jl + p.y_off, iz = k;  // 0-based
+  double2 v = c[idx];
+  double div_r, div_c;
+  if (p.pow2) {
+    div_r = v.x * p.inv_n;
+    div_c = v.y * p.inv_n;
+  } else {
+    div_r = v.x / p.nx_g / p.ny_g / p.nz_g;
+    div_c = v.y / p.nx_g / p.ny_g / p.nz_g;
+  }
+  const double axv = ax[ix], bxv = bx[ix], ayv = ay[iy], byv = by[iy], azv = az[iz], bzv = bz[iz];
+  const bool fz = (iz + 1) > p.nz_g / 2 + 1, fy = (iy + 1) > p.ny_g / 2 + 1;
+  double tr, tc;
+#define ROT(A, B, SGN_R, SGN_C)                                  \
+  tr = div_r; tc = div_c;                                        \
+  if (STRICT) {                                                  \
+    div_r = __dadd_rn(__dmul_rn(tr, B), SGN_R __dmul_rn(tc, A)); \
+    div_c = __dadd_rn(SGN_C __dmul_rn(tc, B), -__dmul_rn(tr, A)); \
+  } else {                                                       \
+    div_r = tr * B SGN_R tc * A;                                 \
+    div_c = SGN_C tc * B - tr * A;                               \
+  }
+  // forward: z, y, x
+  ROT(azv, bzv, +, +)
+  if (fz) { div_r = -div_r; div_c = -div_c; }
+  ROT(ayv, byv, +, +)
+  if (fy) { div_r = -div_r; div_c = -div_c; }
+  ROT(axv, bxv, +, +)
+  // solve
+  const double2 w = waves[idx];
+  if ((w.x < 1.e-16) || (w.y < 1.e-16)) {
+    div_r = 0.0; div_c = 0.0;
+  } else {
+    div_r = -div_r / w.x;
+    div_c = -div_c / w.y;
+  }
+  // backward: z (r*b - c*a, -c*b - r*a), y, x (r*b + c*a, -c*b + r*a)
+  ROT(azv, bzv, -, -)
+  if (fz) { div_r = -div_r; div_c = -div_c; }
+  ROT(ayv, byv, +, +)
+  if (fy) { div_r = -div_r; div_c = -div_c; }
+  tr = div_r; tc = div_c;
+  if (STRICT) {
+    div_r = __dadd_rn(__dmul_rn(tr, bxv), __dmul_rn(tc, axv));
+    div_c = __dadd_rn(-__dmul_rn(tc, bxv), __dmul_rn(tr, axv));
+  } else {
+    div_r = tr * bxv + tc * axv;
+    div_c = -tc * bxv + tr * axv;
+  }
+#undef ROT
+  c[idx] = make_double2(div_r, div_c);
+}
+
+int upload(double** dst, const double* src, size_t n, cudaStream_t s) {
+  X3D2C_CHECK_CUDA(cudaMalloc(dst, sizeof(double) * n));
+  X3D2C_CHECK_CUDA(cudaMemcpyAsync(*dst, src, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+  return X3D2C_OK;
+}
+
+bool slab_z(const x3d2c_ctx* ctx) { return ctx->cfg.nproc_dir[0] == 1 && ctx->cfg.nproc_dir[1] == 1; }
+
+}  // namespace
+
+using namespace x3d2c;
+
+extern "C" {
+
+int x3d2c_poisson_spec_layout(const x3d2c_ctx* ctx, int n_spec[3], int n_sp_st[3]) {
+  X3D2C_REQUIRE(ctx && n_spec && n_sp_st, "x3d2c_poisson_spec_layout: null argument");
+  X3D2C_REQUIRE(slab_z(ctx), "the cuda_c FFT Poisson solver needs nproc_dir = (1, 1, P)");
+  const int P = ctx->cfg.nproc, ny = ctx->cfg.dims_cell_global[1];
+  X3D2C_REQUIRE(ny % P == 0, "ny must be divisible by the number of ranks");
+  n_spec[0] = ctx->cfg.dims_cell_global[0] / 2 + 1;
+  n_spec[1] = ny / P;
+  n_spec[2] = ctx->cfg.dims_cell_global[2];
+  n_sp_st[0] = 0; n_sp_st[1] = (ny / P) * ctx->cfg.rank; n_sp_st[2] = 0;
+  return X3D2C_OK;
+}
+
+int x3d2c_poisson_create(x3d2c_ctx* ctx, const double* waves, const double* ax, const double* bx,
+                         const double* ay, const double* by, const double* az, const double* bz,
+                         x3d2c_poisson** out) {
+  X3D2C_REQUIRE(ctx && waves && ax && bx && ay && by && az && bz && out, "x3d2c_poisson_create: null argument");
+  X3D2C_REQUIRE(ctx->cfg.periodic[0] && ctx->cfg.periodic[1] && ctx->cfg.periodic[2],
+                "x3d2c_poisson_create: only the fully periodic (000) solver is implemented");
+  X3D2C_REQUIRE(slab_z(ctx), "x3d2c_poisson_create: needs nproc_dir = (1, 1, P)");
+  auto* p = new x3d2c_poisson;
+  const int P = ctx->cfg.nproc;
+  p->nx = ctx->cfg.dims_cell_global[0]; p->ny = ctx->cfg.dims_cell_global[1]; p->nz = ctx->cfg.dims_cell_global[2];
+  p->nxh = p->nx / 2 + 1;
+  p->nz_loc = ctx->cfg.dims_cell[2];
+  X3D2C_REQUIRE(p->ny % P == 0 && p->nz_loc * P == p->nz, "x3d2c_poisson_create: ny, nz must divide by nproc");
+  p->ny_loc = p->ny / P;
+  X3D2C_REQUIRE(p->nz <= 65535 && p->nxh <= 65535, "x3d2c_poisson_create: grid limit exceeded");
+  const size_t n_spec = (size_t)p->nxh * p->ny_loc * p->nz;  // == nxh * ny * nz_loc
+  X3D2C_CHECK_CUDA(cudaMalloc(&p->A, sizeof(cufftDoubleComplex) * n_spec));
+  X3D2C_CHECK_CUDA(cudaMalloc(&p->B, sizeof(cufftDoubleComplex) * n_spec));
+  // waves(i, j, k) -> C order (j, i, k)
+  std::vector<double> wc(2 * n_spec);
+  for (int k = 0; k < p->nz; ++k)
+    for (int j = 0; j < p->ny_loc; ++j)
+      for (int i = 0; i < p->nxh; ++i) {
+        const size_t s = i + (size_t)p->nxh * (j + (size_t)p->ny_loc * k);
+        const size_t d = j + (size_t)p->ny_loc * (i + (size_t)p->nxh * k);
+        wc[2 * d] = waves[2 * s];
+        wc[2 * d + 1] = waves[2 * s + 1];
+      }
+  int rc;
+  if ((rc = upload(&p->waves, wc.data(), wc.size(), ctx->stream))) return rc;
+  if ((rc = upload(&p->ax, ax, p->nx, ctx->stream))) return rc;
+  if ((rc = upload(&p->bx, bx, p->nx, ctx->stream))) return rc;
+  if ((rc = upload(&p->ay, ay, p->ny, ctx->stream))) return rc;
+  if ((rc = upload(&p->by, by, p->ny, ctx->stream))) return rc;
+  if ((rc = upload(&p->az, az, p->nz, ctx->stream))) return rc;
+  if ((rc = upload(&p->bz, bz, p->nz, ctx->stream))) return rc;
+  X3D2C_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  const bool padded = ctx->nx_pad != p->nx || ctx->ny_pad != p->ny;
+  if (padded) X3D2C_CHECK_CUDA(cudaMalloc(&p->compact, sizeof(double) * (size_t)p->nx * p->ny * p->nz_loc));
+  // batched 1-D plans
+  int n_x[1] = {p->nx}, n_y[1] = {p->ny}, n_z[1] = {p->nz};
+  X3D2C_CHECK_CUFFT(cufftPlanMany(&p->plan_r2c, 1, n_x, n_x, 1, p->nx, n_x, 1, p->nxh, CUFFT_D2Z, p->ny * p->nz_loc));
+  X3D2C_CHECK_CUFFT(cufftPlanMany(&p->plan_c2r, 1, n_x, n_x, 1, p->nxh, n_x, 1, p->nx, CUFFT_Z2D, p->ny * p->nz_loc));
+  X3D2C_CHECK_CUFFT(cufftPlanMany(&p->plan_y, 1, n_y, n_y, 1, p->ny, n_y, 1, p->ny, CUFFT_Z2Z, p->nxh * p->nz_loc));
+  const int zs = p->ny_loc * p->nxh;
+  X3D2C_CHECK_CUFFT(cufftPlanMany(&p->plan_z, 1, n_z, n_z, zs, 1, n_z, zs, 1, CUFFT_Z2Z, zs));
+  X3D2C_CHECK_CUFFT(cufftSetStream(p->plan_r2c, ctx->stream));
+  X3D2C_CHECK_CUFFT(cufftSetStream(p->plan_c2r, ctx->stream));
+  X3D2C_CHECK_CUFFT(cufftSetStream(p->plan_y, ctx->stream));
+  X3D2C_CHECK_CUFFT(cufftSetStream(p->plan_z, ctx->stream));
+  p->have_plans = true;
+  *out = p;
+  return X3D2C_OK;
+}
+
+int x3d2c_poisson_destroy(x3d2c_ctx* ctx, x3d2c_poisson* p) {
+  if (!p) return X3D2C_OK;
+  cudaStreamSynchronize(ctx->stream);
+  if (p->have_plans) { cufftDestroy(p->plan_r2c); cufftDestroy(p->plan_c2r); cufftDestroy(p->plan_y); cufftDestroy(p->plan_z); }
+  for (void* q : {(void*)p->A, (void*)p->B, (void*)p->waves, (void*)p->ax, (void*)p->bx, (void*)p->ay, (void*)p->by,
+                  (void*)p->az, (void*)p->bz, (void*)p->compact})
+    if (q) cudaFree(q);
+  delete p;
+  return X3D2C_OK;
+}
+
+// the spectrum C(j_loc, i, k) always lives in p->B
+static cufftDoubleComplex* spec_buf(const x3d2c_ctx*, x3d2c_poisson* p) { return p->B; }
+
+int x3d2c_fft_forward(x3d2c_ctx* ctx, x3d2c_poisson* p, const double* f_c) {
+  X3D2C_REQUIRE(ctx && p && f_c, "x3d2c_fft_forward: null argument");
+  const double* in = f_c;
+  if (p->compact) {
+    pad_copy_kernel<true><<<1184, 256, 0, ctx->stream>>>(p->compact, const_cast<double*>(f_c), p->nx, p->ny,
+                                                         p->nz_loc, ctx->nx_pad, ctx->ny_pad);
+    X3D2C_CHECK_LAUNCH(ctx);
+    in = p->compact;
+  }
+  X3D2C_CHECK_CUFFT(cufftExecD2Z(p->plan_r2c, const_cast<double*>(in), p->A));
+  ctx->launches++;
+  const dim3 grid((p->nxh + 31) / 32, (p->ny + 31) / 32, p->nz_loc), block(32, 8);
+  cplx_transpose_kernel<<<grid, block, 0, ctx->stream>>>((double2*)p->B, (const double2*)p->A, p->nxh, p->ny);
+  X3D2C_CHECK_LAUNCH(ctx);
+  X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_y, p->B, p->B, CUFFT_FORWARD));
+  ctx->launches++;
+  cufftDoubleComplex* c = p->B;
+  if (ctx->cfg.nproc > 1) {
+    slab_pack_kernel<true><<<1184, 256, 0, ctx->stream>>>((double2*)p->A, (double2*)p->B, p->ny, p->ny_loc, p->nxh, p->nz_loc);
+    X3D2C_CHECK_LAUNCH(ctx);
+    int rc = alltoall(ctx, (double*)p->B, (const double*)p->A, 2 * (size_t)p->ny_loc * p->nxh * p->nz_loc);
+    if (rc) return rc;
+    // received blocks [s][k_loc][i][j_loc] are exactly C(j_loc, i, k = s*nz_loc + k_loc)
+  }
+  X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_z, c, c, CUFFT_FORWARD));
+  ctx->launches++;
+  return X3D2C_OK;
+}
+
+int x3d2c_fft_postprocess_000(x3d2c_ctx* ctx, x3d2c_poisson* p) {
+  X3D2C_REQUIRE(ctx && p, "x3d2c_fft_postprocess_000: null argument");
+  SpecParams sp;
+  sp.ny_loc = p->ny_loc; sp.nxh = p->nxh; sp.nz = p->nz;
+  sp.nx_g = p->nx; sp.ny_g = p->ny; sp.nz_g = p->nz;
+  sp.y_off = p->ny_loc * ctx->cfg.rank;
+  const long long N = (long long)p->nx * p->ny * p->nz;
+  sp.pow2 = (N & (N - 1)) == 0;
+  sp.inv_n = 1.0 / (double)N;
+  const int bx_ = p->ny_loc >= 256 ? 256 : ((p->ny_loc + 31) / 32) * 32;
+  const dim3 grid((p->ny_loc + bx_ - 1) / bx_, p->nxh, p->nz), block(bx_);
+  cufftDoubleComplex* c = spec_buf(ctx, p);
+  if (ctx->strict)
+    process_spectral_000_kernel<true><<<grid, block, 0, ctx->stream>>>((double2*)c, (const double2*)p->waves, p->ax,
+                                                                      p->bx, p->ay, p->by, p->az, p->bz, sp);
+  else
+    process_spectral_000_kernel<false><<<grid, block, 0, ctx->stream>>>((double2*)c, (const double2*)p->waves, p->ax,
+                                                                       p->bx, p->ay, p->by, p->az, p->bz, sp);
+  X3D2C_CHECK_LAUNCH(ctx);
+  return X3D2C_OK;
+}
+
+int x3d2c_fft_backward(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_c) {
+  X3D2C_REQUIRE(ctx && p && f_c, "x3d2c_fft_backward: null argument");
+  cufftDoubleComplex* c = spec_buf(ctx, p);
+  X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_z, c, c, CUFFT_INVERSE));
+  ctx->launches++;
+  if (ctx->cfg.nproc > 1) {
+    // y-slabs -> z-slabs: block s of C (k range of rank s) goes back to rank s
+    int rc = alltoall(ctx, (double*)p->A, (const double*)p->B, 2 * (size_t)p->ny_loc * p->nxh * p->nz_loc);
+    if (rc) return rc;
+    slab_pack_kernel<false><<<1184, 256, 0, ctx->stream>>>((double2*)p->A, (double2*)p->B, p->ny, p->ny_loc, p->nxh, p->nz_loc);
+    X3D2C_CHECK_LAUNCH(ctx);
+  }
+  X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_y, p->B, p->B, CUFFT_INVERSE));
+  ctx->launches++;
+  const dim3 grid((p->ny + 31) / 32, (p->nxh + 31) / 32, p->nz_loc), block(32, 8);
+  cplx_transpose_kernel<<<grid, block, 0, ctx->stream>>>((double2*)p->A, (const double2*)p->B, p->ny, p->nxh);
+  X3D2C_CHECK_LAUNCH(ctx);
+  double* outp = p->compact ? p->compact : f_c;
+  X3D2C_CHECK_CUFFT(cufftExecZ2D(p->plan_c2r, p->A, outp));
+  ctx->launches++;
+  if (p->compact) {
+    pad_copy_kernel<false><<<1184, 256, 0, ctx->stream>>>(p->compact, f_c, p->nx, p->ny, p->nz_loc, ctx->nx_pad, ctx->ny_pad);
+    X3D2C_CHECK_LAUNCH(ctx);
+  }
+  return X3D2C_OK;
+}
+
+int x3d2c_poisson_get_spectrum(x3d2c_ctx* ctx, x3d2c_poisson* p, double* host_spec) {
+  X3D2C_REQUIRE(ctx && p && host_spec, "x3d2c_poisson_get_spectrum: null argument");
+  const size_t n = (size_t)p->nxh * p->ny_loc * p->nz;
+  std::vector<double> tmp(2 * n);
+  X3D2C_CHECK_CUDA(cudaMemcpyAsync(tmp.data(), spec_buf(ctx, p), sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  X3D2C_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < p->nz; ++k)
+    for (int j = 0; j < p->ny_loc; ++j)
+      for (int i = 0; i < p->nxh; ++i) {
+        const size_t d = i + (size_t)p->nxh * (j + (size_t)p->ny_loc * k);
+        const size_t s = j + (size_t)p->ny_loc * (i + (size_t)p->nxh * k);
+        host_spec[2 * d] = tmp[2 * s];
+        host_spec[2 * d + 1] = tmp[2 * s + 1];
+      }
+  return X3D2C_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+// Pencil reorders and sum_{y,z}intox of the cuda_c backend.
+// Replaces reorder_omp / sum_intox_omp (src/backend/omp/backend.f90:393-527; index maps
+// src/ordering.f90:13-87) and the CUDA-Fortran tile kernels (src/backend/cuda/kernels/reorder.f90:9-314).
+//
+// Every layout of common.cuh is affine in the tile coordinates (x_l, xb, y_l, yb, z) with
+// x = xb*32 + x_l, y = yb*32 + y_l, so ONE kernel serves all twelve RDR_* codes: a CTA moves one
+// 32x32 (x_l, y_l) tile, reading with the source's unit-stride index across lanes and writing with the
+// destination's unit-stride index across lanes (through a padded shared-memory tile when they differ).
+#include "common.cuh"
+
+namespace {
+
+struct Lay {
+  long long sxl, sxb, syl, syb, sz;
+  int fast;  // 0: x_l has unit stride, 1: y_l has unit stride
+};
+
+Lay layout_of(const x3d2c_ctx* ctx, int dir) {
+  const long long nxp = ctx->nx_pad, nyp = ctx->ny_pad, nz = ctx->nz_pad;
+  const long long nxb = nxp / SZ, nyb = nyp / SZ;
+  Lay l{};
+  switch (dir) {
+    case X3D2C_DIR_X: l = {SZ, (long long)SZ * SZ, 1, SZ * nxp, SZ * nxp * nyb, 1}; break;
+    case X3D2C_DIR_Y: l = {1, SZ * nyp, SZ, (long long)SZ * SZ, SZ * nyp * nxb, 0}; break;
+    case X3D2C_DIR_Z: l = {1, SZ * nz, SZ * nz * nxb, SZ * SZ * nz * nxb, SZ, 0}; break;
+    default: l = {1, SZ, nxp, SZ * nxp, nxp * nyp, 0}; break;
+  }
+  return l;
+}
+
+template <bool ACC>
+__global__ void __launch_bounds__(256)
+reorder_tile_kernel(double* __restrict__ dst, const double* __restrict__ src, const Lay ls, const Lay ld) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const long long bs = blockIdx.x * ls.sxb + blockIdx.y * ls.syb + blockIdx.z * ls.sz;
+  const long long bd = blockIdx.x * ld.sxb + blockIdx.y * ld.syb + blockIdx.z * ld.sz;
+  const long long s_fast = ls.fast ? ls.syl : ls.sxl, s_other = ls.fast ? ls.sxl : ls.syl;
+  const long long d_fast = ld.fast ? ld.syl : ld.sxl, d_other = ld.fast ? ld.sxl : ld.syl;
+  double v[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) v[r] = src[bs + tx * s_fast + (ty + 8 * r) * s_other];
+  if (ls.fast == ld.fast) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      double* p = dst + bd + tx * d_fast + (ty + 8 * r) * d_other;
+      *p = ACC ? *p + v[r] : v[r];
+    }
+    return;
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) tile[ty + 8 * r][tx] = v[r];
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    double* p = dst + bd + tx * d_fast + (ty + 8 * r) * d_other;
+    const double t = tile[tx][ty + 8 * r];
+    *p = ACC ? *p + t : t;
+  }
+}
+
+}  // namespace
+
+namespace x3d2c {
+int launch_reorder(x3d2c_ctx* ctx, int dir_from, int dir_to, double* dst, const double* src, bool accumulate) {
+  const Lay ls = layout_of(ctx, dir_from), ld = layout_of(ctx, dir_to);
+  const dim3 grid(ctx->nx_pad / SZ, ctx->ny_pad / SZ, ctx->nz_pad), block(32, 8);
+  if (accumulate)
+    reorder_tile_kernel<true><<<grid, block, 0, ctx->stream>>>(dst, src, ls, ld);
+  else
+    reorder_tile_kernel<false><<<grid, block, 0, ctx->stream>>>(dst, src, ls, ld);
+  X3D2C_CHECK_LAUNCH(ctx);
+  return X3D2C_OK;
+}
+}  // namespace x3d2c
+
+using namespace x3d2c;
+
+extern "C" {
+
+int x3d2c_reorder(x3d2c_ctx* ctx, int rdr, double* dst, const double* src) {
+  X3D2C_REQUIRE(ctx && dst && src, "x3d2c_reorder: null argument");
+  X3D2C_REQUIRE(dst != src, "x3d2c_reorder: in-place reorder is not supported");
+  const int from = rdr / 10, to = rdr % 10;  // src/common.f90:23-26,44-53
+  X3D2C_REQUIRE(from >= 1 && from <= 4 && to >= 1 && to <= 4 && from != to, "x3d2c_reorder: unknown RDR code");
+  X3D2C_REQUIRE(ctx->nz_pad <= 65535, "x3d2c_reorder: nz exceeds the grid limit");
+  return launch_reorder(ctx, from, to, dst, src, false);
+}
+
+int x3d2c_sum_yintox(x3d2c_ctx* ctx, double* u, const double* u_y) {
+  X3D2C_REQUIRE(ctx && u && u_y, "x3d2c_sum_yintox: null argument");
+  return launch_reorder(ctx, X3D2C_DIR_Y, X3D2C_DIR_X, u, u_y, true);
+}
+
+int x3d2c_sum_zintox(x3d2c_ctx* ctx, double* u, const double* u_z) {
+  X3D2C_REQUIRE(ctx && u && u_z, "x3d2c_sum_zintox: null argument");
+  return launch_reorder(ctx, X3D2C_DIR_Z, X3D2C_DIR_X, u, u_z, true);
+}
+
+}  // extern "C"

@@ -1,0 +1,730 @@
+// Host layer of the cuda_c backend: the reference's solver-side modules, restated in C++ on top of the
+// C ABI of include/x3d2c.h (the Fortran toolchain is absent in this image; with one, these classes are
+// the reference's own Fortran modules and only cuda_c_backend_t below becomes an iso_c_binding shim).
+//
+//   mesh_t / par_t / geo_t       src/mesh.f90:37-306, src/mesh_content.f90:6-253
+//   allocator_t / field_t        src/allocator.f90:9-162, src/field.f90:5-83
+//   cuda_c_backend_t             a new `extends(base_backend_t)` (src/backend/backend.f90:13-62),
+//                                modelled on cuda_backend_t (src/backend/cuda/backend.f90:42-81)
+//   poisson_fft_t (000)          src/poisson_fft.f90:120-226,654-882
+//   vector_calculus_t            src/vector_calculus.f90:40-332
+//   time_intg_t                  src/time_integrator.f90:70-300
+//   solver_t                     src/solver.f90:111-389,603-739
+//   base_case_t%run / case_tgv_t src/case/base_case.f90:139-289, src/case/tgv.f90:41-72
+//   monitoring_t                 src/postprocess/monitoring.f90:46-90
+#pragma once
+#include <array>
+#include <complex>
+
+#include "../../../include/x3d2c.h"
+#include "tdsops.hpp"
+
+namespace x3d2h {
+
+using cplx = std::complex<double>;
+
+struct Config {
+  int dims_global[3];
+  int nproc_dir[3];
+  double L_global[3];
+  int bc[3][2];
+  double Re = 1600, dt = 1e-3;
+  std::string time_intg = "RK3", der1st = "compact6", der2nd = "compact6", interpl = "classic",
+              stagder = "compact6";
+  int rank = 0, nproc = 1, device = -1, flags = 0;
+  const void* nccl_unique_id = nullptr;
+};
+
+// ------------------------------------------------------------------------------------ mesh
+struct Mesh {
+  // grid_t
+  int global_vert_dims[3], global_cell_dims[3], vert_dims[3], cell_dims[3];
+  bool periodic_BC[3];
+  int BCs_global[3][2], BCs[3][2];
+  // par_t
+  int nrank = 0, nproc = 1, nrank_dir[3], nproc_dir[3], n_offset[3], pprev[3], pnext[3];
+  // geo_t (uniform meshes; the stretched channel is a later row of SURVEY.md §8f)
+  double d[3], L[3];
+  std::vector<double> vert_coords[3], midp_coords[3];
+
+  // mesh.f90:37-158 with the generic decomposition of :160-194
+  void init(const Config& c) {
+    nrank = c.rank;
+    nproc = c.nproc;
+    for (int dir = 0; dir < 3; ++dir) {
+      BCs_global[dir][0] = c.bc[dir][0]; BCs_global[dir][1] = c.bc[dir][1];
+      bool p0 = c.bc[dir][0] == BC_PERIODIC, p1 = c.bc[dir][1] == BC_PERIODIC;
+      if (p0 != p1) fail("BCs are incompatible: in a direction make sure to have either both sides periodic or none.");
+      periodic_BC[dir] = p0 && p1;
+      global_vert_dims[dir] = c.dims_global[dir];
+      global_cell_dims[dir] = periodic_BC[dir] ? c.dims_global[dir] : c.dims_global[dir] - 1;
+      nproc_dir[dir] = c.nproc_dir[dir];
+      L[dir] = c.L_global[dir];
+      d[dir] = L[dir] / global_cell_dims[dir];
+    }
+    if (nproc_dir[0] * nproc_dir[1] * nproc_dir[2] != nproc) {  // xcompact.f90:69-74
+      nproc_dir[0] = 1; nproc_dir[1] = 1; nproc_dir[2] = nproc;
+    }
+    // global_ranks = reshape([0..nproc-1], [px, py, pz]) (x fastest), mesh.f90:186-187
+    auto rank_of = [&](int px, int py, int pz) { return px + nproc_dir[0] * (py + nproc_dir[1] * pz); };
+    int pos[3] = {nrank % nproc_dir[0], (nrank / nproc_dir[0]) % nproc_dir[1], nrank / (nproc_dir[0] * nproc_dir[1])};
+    for (int dir = 0; dir < 3; ++dir) {
+      nrank_dir[dir] = pos[dir];
+      if (global_vert_dims[dir] % nproc_dir[dir]) fail("dims_global must be divisible by nproc_dir");
+      vert_dims[dir] = global_vert_dims[dir] / nproc_dir[dir];
+      const int np = nproc_dir[dir];
+      int prev[3] = {pos[0], pos[1], pos[2]}, next[3] = {pos[0], pos[1], pos[2]};
+      prev[dir] = ((pos[dir] - 1) % np + np) % np;  // mesh_content.f90:87-100
+      next[dir] = (pos[dir] + 1) % np;
+      pprev[dir] = rank_of(prev[0], prev[1], prev[2]);
+      pnext[dir] = rank_of(next[0], next[1], next[2]);
+      const bool first = pos[dir] == 0, last = pos[dir] + 1 == np;
+      cell_dims[dir] = (last && !periodic_BC[dir]) ? vert_dims[dir] - 1 : vert_dims[dir];  // :104-121
+      n_offset[dir] = vert_dims[dir] * pos[dir];
+      if (first && last) { BCs[dir][0] = BCs_global[dir][0]; BCs[dir][1] = BCs_global[dir][1]; }  // mesh.f90:119-136
+      else if (first) { BCs[dir][0] = BCs_global[dir][0]; BCs[dir][1] = BC_HALO; }
+      else if (last) { BCs[dir][0] = BC_HALO; BCs[dir][1] = BCs_global[dir][1]; }
+      else { BCs[dir][0] = BC_HALO; BCs[dir][1] = BC_HALO; }
+      // mesh_content.f90:163-176 (uniform)
+      vert_coords[dir].resize(vert_dims[dir]);
+      midp_coords[dir].resize(cell_dims[dir]);
+      for (int i = 1; i <= vert_dims[dir]; ++i) vert_coords[dir][i - 1] = (n_offset[dir] + i - 1) * d[dir];
+      for (int i = 1; i <= cell_dims[dir]; ++i) midp_coords[dir][i - 1] = (n_offset[dir] + i - 0.5) * d[dir];
+    }
+  }
+
+  void get_dims(int dims[3], int data_loc, bool global = false) const {  // mesh.f90:196-261
+    const int* v = global ? global_vert_dims : vert_dims;
+    const int* c = global ? global_cell_dims : cell_dims;
+    switch (data_loc) {
+      case VERT: dims[0] = v[0]; dims[1] = v[1]; dims[2] = v[2]; break;
+      case CELL: dims[0] = c[0]; dims[1] = c[1]; dims[2] = c[2]; break;
+      case X_FACE: dims[0] = v[0]; dims[1] = c[1]; dims[2] = c[2]; break;
+      case Y_FACE: dims[0] = c[0]; dims[1] = v[1]; dims[2] = c[2]; break;
+      case Z_FACE: dims[0] = c[0]; dims[1] = c[1]; dims[2] = v[2]; break;
+      case X_EDGE: dims[0] = c[0]; dims[1] = v[1]; dims[2] = v[2]; break;
+      case Y_EDGE: dims[0] = v[0]; dims[1] = c[1]; dims[2] = v[2]; break;
+      case Z_EDGE: dims[0] = v[0]; dims[1] = v[1]; dims[2] = c[2]; break;
+      default: fail("Unknown location in get_dims_dataloc");
+    }
+  }
+  int get_n(int dir, int data_loc) const {  // mesh.f90:263-306
+    int n_cell = cell_dims[dir - 1], n_vert = vert_dims[dir - 1], n = n_vert;
+    switch (data_loc) {
+      case CELL: n = n_cell; break;
+      case VERT: n = n_vert; break;
+      case X_FACE: if (dir != DIR_X) n = n_cell; break;
+      case Y_FACE: if (dir != DIR_Y) n = n_cell; break;
+      case Z_FACE: if (dir != DIR_Z) n = n_cell; break;
+      case X_EDGE: if (dir == DIR_X) n = n_cell; break;
+      case Y_EDGE: if (dir == DIR_Y) n = n_cell; break;
+      case Z_EDGE: if (dir == DIR_Z) n = n_cell; break;
+      default: fail("Unknown direction in get_n_dir");
+    }
+    return n;
+  }
+};
+
+// ------------------------------------------------------------------------------------ field / allocator
+struct Field {  // field.f90:5-23 with the device pointer of cuda_field_t (cuda/allocator.f90:9-29)
+  double* dev = nullptr;
+  int dir = DIR_X, data_loc = NULL_LOC, id = 0;
+  Field* next = nullptr;
+};
+
+[[noreturn]] inline void fail_c(const char* what) { fail(std::string(what) + ": " + x3d2c_last_error()); }
+#define X3D2H_CALL(expr)            \
+  do {                              \
+    if ((expr) != X3D2C_OK) fail_c(#expr); \
+  } while (0)
+
+class Allocator {  // allocator.f90:9-162; storage comes from x3d2c_field_alloc (create_block override)
+ public:
+  x3d2c_ctx* ctx = nullptr;
+  int next_id = 0;
+  Field* first = nullptr;
+  std::vector<std::unique_ptr<Field>> all;
+  int dims_padded[3] = {0, 0, 0}, n_groups_dir[3] = {0, 0, 0};
+  long long ngrid = 0;
+
+  void init(x3d2c_ctx* c) {
+    ctx = c;
+    X3D2H_CALL(x3d2c_get_padded_dims(ctx, dims_padded, n_groups_dir, &ngrid));
+  }
+  Field* get_block(int dir, int data_loc = NULL_LOC) {
+    if (!first) {
+      all.emplace_back(new Field);
+      Field* f = all.back().get();
+      f->id = ++next_id;
+      X3D2H_CALL(x3d2c_field_alloc(ctx, &f->dev));
+      f->next = first;
+      first = f;
+    }
+    Field* h = first;
+    first = first->next;
+    h->next = nullptr;
+    h->dir = dir;
+    h->data_loc = data_loc;
+    return h;
+  }
+  void release_block(Field* h) {
+    h->next = first;
+    first = h;
+  }
+  void destroy() {
+    for (auto& f : all)
+      if (f->dev) x3d2c_field_free(ctx, f->dev);
+    all.clear();
+    first = nullptr;
+  }
+};
+
+struct DevTdsops {  // cuda_tdsops_t role (cuda/tdsops.f90:9-23): host tables + device handle
+  Tdsops t;
+  x3d2c_tdsops* h = nullptr;
+};
+struct DevDirps {
+  DevTdsops der1st, der1st_sym, der2nd, der2nd_sym, stagder_v2p, stagder_p2v, interpl_v2p, interpl_p2v;
+  int dir = 0;
+};
+
+// ------------------------------------------------------------------------------------ backend
+class Backend {  // cuda_c_backend_t: every method is one deferred procedure of base_backend_t
+ public:
+  x3d2c_ctx* ctx = nullptr;
+  x3d2c_poisson* poisson = nullptr;
+  Mesh* mesh = nullptr;
+  Allocator* allocator = nullptr;
+
+  void alloc_tdsops(DevTdsops& o, int n_tds, double delta, const std::string& operation, const std::string& scheme,
+                    int bc_start, int bc_end, const double* stretch = nullptr, const double* stretch_correct = nullptr,
+                    int n_halo = 4, const std::string& from_to = "", bool sym = false) {
+    o.t = tdsops_init(n_tds, delta, operation, scheme, bc_start, bc_end, stretch, stretch_correct, n_halo, from_to, sym);
+    const Tdsops& t = o.t;
+    double cs[36], ce[36];
+    for (int i = 1; i <= 4; ++i)
+      for (int k = 1; k <= 9; ++k) { cs[(i - 1) * 9 + k - 1] = t.coeffs_s[i][k]; ce[(i - 1) * 9 + k - 1] = t.coeffs_e[i][k]; }
+    X3D2H_CALL(x3d2c_tdsops_create(ctx, t.n_tds, t.n_rhs, t.move, t.periodic, &t.coeffs[1], cs, ce, &t.dist_fw[1],
+                                   &t.dist_bw[1], &t.dist_sa[1], &t.dist_sc[1], &t.dist_af[1], &t.stretch[1],
+                                   &t.stretch_correct[1], &o.h));
+  }
+  void transeq(int dir, Field& du, Field& dv, Field& dw, const Field& u, const Field& v, const Field& w, double nu,
+               const DevDirps& dp) {
+    X3D2H_CALL(x3d2c_transeq(ctx, dir, du.dev, dv.dev, dw.dev, u.dev, v.dev, w.dev, nu, dp.der1st.h, dp.der1st_sym.h,
+                             dp.der2nd.h, dp.der2nd_sym.h));
+    du.data_loc = u.data_loc; dv.data_loc = v.data_loc; dw.data_loc = w.data_loc;  // omp/backend.f90:333
+  }
+  void transeq_x(Field& du, Field& dv, Field& dw, const Field& u, const Field& v, const Field& w, double nu, const DevDirps& dp) { transeq(DIR_X, du, dv, dw, u, v, w, nu, dp); }
+  void transeq_y(Field& du, Field& dv, Field& dw, const Field& u, const Field& v, const Field& w, double nu, const DevDirps& dp) { transeq(DIR_Y, du, dv, dw, u, v, w, nu, dp); }
+  void transeq_z(Field& du, Field& dv, Field& dw, const Field& u, const Field& v, const Field& w, double nu, const DevDirps& dp) { transeq(DIR_Z, du, dv, dw, u, v, w, nu, dp); }
+  void tds_solve(Field& du, const Field& u, const DevTdsops& ops) {  // cuda/backend.f90:449-470
+    if (u.dir != du.dir) fail("DIR mismatch between fields in tds_solve.");
+    if (u.data_loc != NULL_LOC) du.data_loc = move_data_loc(u.data_loc, u.dir, ops.t.move);
+    X3D2H_CALL(x3d2c_tds_solve(ctx, u.dir, du.dev, u.dev, ops.h));
+  }
+  void reorder(Field& u_, const Field& u, int direction) {
+    X3D2H_CALL(x3d2c_reorder(ctx, direction, u_.dev, u.dev));
+    u_.data_loc = u.data_loc;
+  }
+  void sum_yintox(Field& u, const Field& u_) { X3D2H_CALL(x3d2c_sum_yintox(ctx, u.dev, u_.dev)); }
+  void sum_zintox(Field& u, const Field& u_) { X3D2H_CALL(x3d2c_sum_zintox(ctx, u.dev, u_.dev)); }
+  void veccopy(Field& dst, const Field& src) {
+    if (src.dir != dst.dir) fail("Called vector copy with incompatible fields");
+    if (dst.dir == DIR_C) fail("veccopy does not support DIR_C fields");
+    X3D2H_CALL(x3d2c_veccopy(ctx, dst.dev, src.dev));
+  }
+  void vecadd(double a, const Field& x, double b, Field& y) {
+    if (x.dir != y.dir) fail("Called vector add with incompatible fields");
+    if (y.dir == DIR_C) fail("vecadd does not support DIR_C fields");
+    X3D2H_CALL(x3d2c_vecadd(ctx, a, x.dev, b, y.dev));
+  }
+  double scalar_product(const Field& x, const Field& y) {
+    if (x.data_loc == NULL_LOC || y.data_loc == NULL_LOC) fail("You must set the data_loc before calling scalar product");
+    if (x.data_loc != y.data_loc) fail("Called scalar product with incompatible fields");
+    if (x.dir != y.dir) fail("Called scalar product with incompatible fields");
+    double s = 0;
+    X3D2H_CALL(x3d2c_scalar_product(ctx, x.dir, x.data_loc, x.dev, y.dev, &s));
+    return s;
+  }
+  void field_max_mean(double& mx, double& mean, const Field& f, int enforced_data_loc = -999) {
+    if (f.data_loc == NULL_LOC && enforced_data_loc == -999) fail("field_max_mean: the field has no valid data_loc");
+    X3D2H_CALL(x3d2c_field_max_mean(ctx, f.dir, enforced_data_loc != -999 ? enforced_data_loc : f.data_loc, f.dev, &mx, &mean));
+  }
+  // backend.f90:402-466 (get_field_data / set_field_data through a DIR_C block); `data` is the full padded block
+  void set_field_data(Field& f, const double* data_padded_c) {
+    int rdr = get_rdr_from_dirs(DIR_C, f.dir);
+    if (rdr) {
+      Field* tmp = allocator->get_block(DIR_C, f.data_loc);
+      X3D2H_CALL(x3d2c_copy_data_to_f(ctx, tmp->dev, data_padded_c));
+      int loc = f.data_loc;
+      reorder(f, *tmp, rdr);
+      f.data_loc = loc;
+      allocator->release_block(tmp);
+    } else {
+      X3D2H_CALL(x3d2c_copy_data_to_f(ctx, f.dev, data_padded_c));
+    }
+  }
+  void get_field_data(double* data_padded_c, const Field& f) {
+    int rdr = get_rdr_from_dirs(f.dir, DIR_C);
+    if (rdr) {
+      Field* tmp = allocator->get_block(DIR_C);
+      reorder(*tmp, f, rdr);
+      X3D2H_CALL(x3d2c_copy_f_to_data(ctx, data_padded_c, tmp->dev));
+      allocator->release_block(tmp);
+    } else {
+      X3D2H_CALL(x3d2c_copy_f_to_data(ctx, data_padded_c, f.dev));
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------ poisson_fft_t (000)
+struct PoissonFFT {
+  int nx_glob, ny_glob, nz_glob, nx_spec, ny_spec, nz_spec, sp_st[3];
+  std::vector<double> ax, bx, ay, by, az, bz;  // 1-based
+  std::vector<cplx> kx, ky, kz, exs, eys, ezs, k2x, k2y, k2z;
+  std::vector<cplx> waves;
+
+  // poisson_fft.f90:833-882
+  static void wave_numbers(std::vector<double>& a, std::vector<double>& b, std::vector<cplx>& k, std::vector<cplx>& e,
+                           std::vector<cplx>& k2, int n, double L, double d, bool periodic, double c_a, double c_b,
+                           double c_alpha) {
+    a.assign(n + 1, 0); b.assign(n + 1, 0);
+    k.assign(n + 1, 0); e.assign(n + 1, 0); k2.assign(n + 1, 0);
+    for (int i = 1; i <= n; ++i) {
+      if (periodic) { a[i] = std::sin((i - 1) * pi / n); b[i] = std::cos((i - 1) * pi / n); }
+      else { a[i] = std::sin((i - 1) * pi / 2 / n); b[i] = std::cos((i - 1) * pi / 2 / n); }
+    }
+    auto one = [&](int i, double w) {
+      double wp = c_a * 2 * d * std::sin(0.5 * w) + c_b * 2 * d * std::sin(1.5 * w);
+      wp = wp / (1.0 + 2 * c_alpha * std::cos(w));
+      k[i] = cplx(1.0, 1.0) * (n * wp / L);
+      e[i] = cplx(1.0, 1.0) * (n * w / L);
+      const double q = n * wp / L;
+      k2[i] = cplx(1.0, 1.0) * (q * q);
+    };
+    if (periodic) {
+      for (int i = 1; i <= n / 2 + 1; ++i) one(i, 2 * pi * (i - 1) / n);
+      for (int i = n / 2 + 2; i <= n; ++i) { k[i] = k[n - i + 2]; e[i] = e[n - i + 2]; k2[i] = k2[n - i + 2]; }
+    } else {
+      for (int i = 1; i <= n; ++i) one(i, pi * (i - 1) / n);
+    }
+  }
+
+  // base_init (:120-204) + waves_set, periodic-z branch (:777-819)
+  void base_init(const Mesh& mesh, const DevDirps& xd, const DevDirps& yd, const DevDirps& zd, const int n_spec[3],
+                 const int n_sp_st[3]) {
+    if (mesh.nproc_dir[0] != 1) fail("nproc_dir in x-dir must be 1");
+    nx_glob = mesh.global_cell_dims[0]; ny_glob = mesh.global_cell_dims[1]; nz_glob = mesh.global_cell_dims[2];
+    nx_spec = n_spec[0]; ny_spec = n_spec[1]; nz_spec = n_spec[2];
+    for (int q = 0; q < 3; ++q) sp_st[q] = n_sp_st[q];
+    if (!(mesh.periodic_BC[0] && mesh.periodic_BC[1] && mesh.periodic_BC[2]))
+      fail("Requested BCs are not supported in the cuda_c FFT-based Poisson solver (000 only)");
+    const Tdsops &sx = xd.stagder_v2p.t, &sy = yd.stagder_v2p.t, &sz_ = zd.stagder_v2p.t;
+    const Tdsops &ix = xd.interpl_v2p.t, &iy = yd.interpl_v2p.t, &iz = zd.interpl_v2p.t;
+    wave_numbers(ax, bx, kx, exs, k2x, nx_glob, mesh.L[0], mesh.d[0], mesh.periodic_BC[0], sx.a, sx.b, sx.alpha);
+    wave_numbers(ay, by, ky, eys, k2y, ny_glob, mesh.L[1], mesh.d[1], mesh.periodic_BC[1], sy.a, sy.b, sy.alpha);
+    wave_numbers(az, bz, kz, ezs, k2z, nz_glob, mesh.L[2], mesh.d[2], mesh.periodic_BC[2], sz_.a, sz_.b, sz_.alpha);
+    waves.assign((size_t)nx_spec * ny_spec * nz_spec, 0);
+    for (int k = 1; k <= nz_spec; ++k)
+      for (int j = 1; j <= ny_spec; ++j)
+        for (int i = 1; i <= nx_spec; ++i) {
+          const int ixx = i + sp_st[0], iyy = j + sp_st[1], izz = k + sp_st[2];
+          const double rlexs = exs[ixx].real() * mesh.d[0], rleys = eys[iyy].real() * mesh.d[1], rlezs = ezs[izz].real() * mesh.d[2];
+          const double xtt = 2 * (ix.a * std::cos(rlexs * 0.5) + ix.b * std::cos(rlexs * 1.5) + ix.c * std::cos(rlexs * 2.5) + ix.d * std::cos(rlexs * 3.5));
+          const double ytt = 2 * (iy.a * std::cos(rleys * 0.5) + iy.b * std::cos(rleys * 1.5) + iy.c * std::cos(rleys * 2.5) + iy.d * std::cos(rleys * 3.5));
+          const double ztt = 2 * (iz.a * std::cos(rlezs * 0.5) + iz.b * std::cos(rlezs * 1.5) + iz.c * std::cos(rlezs * 2.5) + iz.d * std::cos(rlezs * 3.5));
+          const double xt1 = 1.0 + 2 * ix.alpha * std::cos(rlexs);
+          const double yt1 = 1.0 + 2 * iy.alpha * std::cos(rleys);
+          const double zt1 = 1.0 + 2 * iz.alpha * std::cos(rlezs);
+          const double fx = (ytt / yt1) * (ztt / zt1), fy = (xtt / xt1) * (ztt / zt1), fz = (xtt / xt1) * (ytt / yt1);
+          const cplx xt2 = k2x[ixx] * (fx * fx), yt2 = k2y[iyy] * (fy * fy), zt2 = k2z[izz] * (fz * fz);
+          waves[(i - 1) + (size_t)nx_spec * ((j - 1) + (size_t)ny_spec * (k - 1))] = xt2 + yt2 + zt2;
+        }
+  }
+};
+
+// ------------------------------------------------------------------------------------ solver + time integrator + case
+class Sim {
+ public:
+  Config cfg;
+  Mesh mesh;
+  x3d2c_ctx* ctx = nullptr;
+  Allocator allocator;
+  Backend backend;
+  DevDirps xdirps, ydirps, zdirps;
+  PoissonFFT pfft;
+  double nu = 0, dt = 0;
+  long long ngrid = 0;
+  Field *u = nullptr, *v = nullptr, *w = nullptr;
+  // time_intg_t (time_integrator.f90:11-26)
+  int ti_istep = 1, ti_istage = 1, ti_order = 3, ti_nstep = 1, ti_nstage = 3, ti_nolds = 3;
+  bool ti_is_ab = false;
+  double ti_coeffs[5][5], ti_rk_b[5][5], ti_rk_a[4][4][5];
+  std::vector<std::vector<Field*>> olds;
+
+  explicit Sim(const Config& c) : cfg(c) {
+    mesh.init(cfg);
+    x3d2c_config bc;
+    std::memset(&bc, 0, sizeof bc);
+    for (int q = 0; q < 3; ++q) {
+      bc.dims_vert[q] = mesh.vert_dims[q]; bc.dims_cell[q] = mesh.cell_dims[q];
+      bc.dims_vert_global[q] = mesh.global_vert_dims[q]; bc.dims_cell_global[q] = mesh.global_cell_dims[q];
+      bc.nproc_dir[q] = mesh.nproc_dir[q]; bc.nrank_dir[q] = mesh.nrank_dir[q]; bc.n_offset[q] = mesh.n_offset[q];
+      bc.pprev[q] = mesh.pprev[q]; bc.pnext[q] = mesh.pnext[q]; bc.periodic[q] = mesh.periodic_BC[q];
+    }
+    bc.sz = SZ; bc.rank = mesh.nrank; bc.nproc = mesh.nproc; bc.device = cfg.device; bc.flags = cfg.flags;
+    bc.nccl_unique_id = cfg.nccl_unique_id;
+    X3D2H_CALL(x3d2c_create(&bc, &ctx));
+    allocator.init(ctx);
+    backend.ctx = ctx; backend.mesh = &mesh; backend.allocator = &allocator;
+    // solver init (solver.f90:111-212)
+    u = allocator.get_block(DIR_X); v = allocator.get_block(DIR_X); w = allocator.get_block(DIR_X);
+    init_time_integrator();
+    dt = cfg.dt;
+    nu = 1.0 / cfg.Re;
+    ngrid = (long long)mesh.global_vert_dims[0] * mesh.global_vert_dims[1] * mesh.global_vert_dims[2];
+    xdirps.dir = DIR_X; ydirps.dir = DIR_Y; zdirps.dir = DIR_Z;
+    allocate_tdsops(xdirps); allocate_tdsops(ydirps); allocate_tdsops(zdirps);
+    init_poisson_fft();
+  }
+  ~Sim() {
+    if (!ctx) return;
+    x3d2c_sync(ctx);
+    if (backend.poisson) x3d2c_poisson_destroy(ctx, backend.poisson);
+    for (DevDirps* d : {&xdirps, &ydirps, &zdirps})
+      for (DevTdsops* o : {&d->der1st, &d->der1st_sym, &d->der2nd, &d->der2nd_sym, &d->stagder_v2p, &d->stagder_p2v,
+                           &d->interpl_v2p, &d->interpl_p2v})
+        if (o->h) x3d2c_tdsops_destroy(ctx, o->h);
+    allocator.destroy();
+    x3d2c_destroy(ctx);
+  }
+
+  // solver.f90:214-289
+  void allocate_tdsops(DevDirps& dp) {
+    const int dir = dp.dir;
+    const double d = mesh.d[dir - 1];
+    const int bc_start = mesh.BCs[dir - 1][0], bc_end = mesh.BCs[dir - 1][1];
+    const int bc_mp_start = bc_start == BC_DIRICHLET ? BC_NEUMANN : bc_start;
+    const int bc_mp_end = bc_end == BC_DIRICHLET ? BC_NEUMANN : bc_end;
+    const int n_vert = mesh.get_n(dir, VERT), n_cell = mesh.get_n(dir, CELL);
+    backend.alloc_tdsops(dp.der1st, n_vert, d, "first-deriv", cfg.der1st, bc_start, bc_end);
+    backend.alloc_tdsops(dp.der1st_sym, n_vert, d, "first-deriv", cfg.der1st, bc_start, bc_end, nullptr, nullptr, 4, "", true);
+    backend.alloc_tdsops(dp.der2nd, n_vert, d, "second-deriv", cfg.der2nd, bc_start, bc_end);
+    backend.alloc_tdsops(dp.der2nd_sym, n_vert, d, "second-deriv", cfg.der2nd, bc_start, bc_end, nullptr, nullptr, 4, "", true);
+    backend.alloc_tdsops(dp.stagder_v2p, n_cell, d, "stag-deriv", cfg.stagder, bc_mp_start, bc_mp_end, nullptr, nullptr, 4, "v2p");
+    backend.alloc_tdsops(dp.stagder_p2v, n_vert, d, "stag-deriv", cfg.stagder, bc_mp_start, bc_mp_end, nullptr, nullptr, 4, "p2v");
+    backend.alloc_tdsops(dp.interpl_v2p, n_cell, d, "interpolate", cfg.interpl, bc_mp_start, bc_mp_end, nullptr, nullptr, 4, "v2p");
+    backend.alloc_tdsops(dp.interpl_p2v, n_vert, d, "interpolate", cfg.interpl, bc_mp_start, bc_mp_end, nullptr, nullptr, 4, "p2v");
+  }
+
+  // init_poisson_fft (cuda/poisson_fft.f90:97-260 pattern): layout from the backend, base_init on the host, upload
+  void init_poisson_fft() {
+    if (!(mesh.periodic_BC[0] && mesh.periodic_BC[1] && mesh.periodic_BC[2])) return;
+    int n_spec[3], n_sp_st[3];
+    X3D2H_CALL(x3d2c_poisson_spec_layout(ctx, n_spec, n_sp_st));
+    pfft.base_init(mesh, xdirps, ydirps, zdirps, n_spec, n_sp_st);
+    X3D2H_CALL(x3d2c_poisson_create(ctx, reinterpret_cast<const double*>(pfft.waves.data()), &pfft.ax[1], &pfft.bx[1],
+                                    &pfft.ay[1], &pfft.by[1], &pfft.az[1], &pfft.bz[1], &backend.poisson));
+  }
+
+  // solver.f90:291-389
+  void transeq_default(Field& du, Field& dv, Field& dw, const Field& uu, const Field& vv, const Field& ww) {
+    Allocator& A = allocator;
+    backend.transeq_x(du, dv, dw, uu, vv, ww, nu, xdirps);
+    Field *u_y = A.get_block(DIR_Y), *v_y = A.get_block(DIR_Y), *w_y = A.get_block(DIR_Y), *du_y = A.get_block(DIR_Y),
+          *dv_y = A.get_block(DIR_Y), *dw_y = A.get_block(DIR_Y);
+    backend.reorder(*u_y, uu, RDR_X2Y); backend.reorder(*v_y, vv, RDR_X2Y); backend.reorder(*w_y, ww, RDR_X2Y);
+    backend.transeq_y(*du_y, *dv_y, *dw_y, *u_y, *v_y, *w_y, nu, ydirps);
+    A.release_block(u_y); A.release_block(v_y); A.release_block(w_y);
+    backend.sum_yintox(du, *du_y); backend.sum_yintox(dv, *dv_y); backend.sum_yintox(dw, *dw_y);
+    A.release_block(du_y); A.release_block(dv_y); A.release_block(dw_y);
+    Field *u_z = A.get_block(DIR_Z), *v_z = A.get_block(DIR_Z), *w_z = A.get_block(DIR_Z), *du_z = A.get_block(DIR_Z),
+          *dv_z = A.get_block(DIR_Z), *dw_z = A.get_block(DIR_Z);
+    backend.reorder(*u_z, uu, RDR_X2Z); backend.reorder(*v_z, vv, RDR_X2Z); backend.reorder(*w_z, ww, RDR_X2Z);
+    backend.transeq_z(*du_z, *dv_z, *dw_z, *u_z, *v_z, *w_z, nu, zdirps);
+    A.release_block(u_z); A.release_block(v_z); A.release_block(w_z);
+    backend.sum_zintox(du, *du_z); backend.sum_zintox(dv, *dv_z); backend.sum_zintox(dw, *dw_z);
+    A.release_block(du_z); A.release_block(dv_z); A.release_block(dw_z);
+  }
+
+  // vector_calculus.f90:142-246
+  void divergence_v2c(Field& div_u, const Field& uu, const Field& vv, const Field& ww) {
+    if (div_u.dir != DIR_Z || uu.dir != DIR_X || vv.dir != DIR_X || ww.dir != DIR_X)
+      fail("Error in divergence_v2c input/output field dirs: output must be in DIR_Z, inputs must be in DIR_X layout.");
+    Allocator& A = allocator;
+    Field *du_x = A.get_block(DIR_X), *dv_x = A.get_block(DIR_X), *dw_x = A.get_block(DIR_X);
+    backend.tds_solve(*du_x, uu, xdirps.stagder_v2p);
+    backend.tds_solve(*dv_x, vv, xdirps.interpl_v2p);
+    backend.tds_solve(*dw_x, ww, xdirps.interpl_v2p);
+    Field *u_y = A.get_block(DIR_Y), *v_y = A.get_block(DIR_Y), *w_y = A.get_block(DIR_Y);
+    backend.reorder(*u_y, *du_x, RDR_X2Y); backend.reorder(*v_y, *dv_x, RDR_X2Y); backend.reorder(*w_y, *dw_x, RDR_X2Y);
+    A.release_block(du_x); A.release_block(dv_x); A.release_block(dw_x);
+    Field *du_y = A.get_block(DIR_Y), *dv_y = A.get_block(DIR_Y), *dw_y = A.get_block(DIR_Y);
+    backend.tds_solve(*du_y, *u_y, ydirps.interpl_v2p);
+    backend.tds_solve(*dv_y, *v_y, ydirps.stagder_v2p);
+    backend.tds_solve(*dw_y, *w_y, ydirps.interpl_v2p);
+    A.release_block(u_y); A.release_block(v_y); A.release_block(w_y);
+    Field *u_z = A.get_block(DIR_Z), *w_z = A.get_block(DIR_Z);
+    backend.vecadd(1.0, *dv_y, 1.0, *du_y);
+    backend.reorder(*u_z, *du_y, RDR_Y2Z); backend.reorder(*w_z, *dw_y, RDR_Y2Z);
+    A.release_block(du_y); A.release_block(dv_y); A.release_block(dw_y);
+    Field* dw_z = A.get_block(DIR_Z);
+    backend.tds_solve(div_u, *u_z, zdirps.interpl_v2p);
+    backend.tds_solve(*dw_z, *w_z, zdirps.stagder_v2p);
+    backend.vecadd(1.0, *dw_z, 1.0, div_u);
+    A.release_block(u_z); A.release_block(w_z); A.release_block(dw_z);
+  }
+
+  // vector_calculus.f90:248-332
+  void gradient_c2v(Field& dpdx, Field& dpdy, Field& dpdz, const Field& p) {
+    if (dpdx.dir != DIR_X || dpdy.dir != DIR_X || dpdz.dir != DIR_X || p.dir != DIR_Z)
+      fail("Error in gradient_c2v input/output field dirs: outputs must be in DIR_X, input must be in DIR_Z layout.");
+    Allocator& A = allocator;
+    Field *p_sxy_z = A.get_block(DIR_Z), *dpdz_sxy_z = A.get_block(DIR_Z);
+    backend.tds_solve(*p_sxy_z, p, zdirps.interpl_p2v);
+    backend.tds_solve(*dpdz_sxy_z, p, zdirps.stagder_p2v);
+    Field *p_sxy_y = A.get_block(DIR_Y), *dpdz_sxy_y = A.get_block(DIR_Y);
+    backend.reorder(*p_sxy_y, *p_sxy_z, RDR_Z2Y); backend.reorder(*dpdz_sxy_y, *dpdz_sxy_z, RDR_Z2Y);
+    A.release_block(p_sxy_z); A.release_block(dpdz_sxy_z);
+    Field *p_sx_y = A.get_block(DIR_Y), *dpdy_sx_y = A.get_block(DIR_Y);
+    backend.tds_solve(*p_sx_y, *p_sxy_y, ydirps.interpl_p2v);
+    backend.tds_solve(*dpdy_sx_y, *p_sxy_y, ydirps.stagder_p2v);
+    A.release_block(p_sxy_y);
+    Field* dpdz_sx_y = A.get_block(DIR_Y);
+    backend.tds_solve(*dpdz_sx_y, *dpdz_sxy_y, ydirps.interpl_p2v);
+    A.release_block(dpdz_sxy_y);
+    Field* p_sx_x = A.get_block(DIR_X);
+    backend.reorder(*p_sx_x, *p_sx_y, RDR_Y2X); A.release_block(p_sx_y);
+    Field* dpdy_sx_x = A.get_block(DIR_X);
+    backend.reorder(*dpdy_sx_x, *dpdy_sx_y, RDR_Y2X); A.release_block(dpdy_sx_y);
+    Field* dpdz_sx_x = A.get_block(DIR_X);
+    backend.reorder(*dpdz_sx_x, *dpdz_sx_y, RDR_Y2X); A.release_block(dpdz_sx_y);
+    backend.tds_solve(dpdx, *p_sx_x, xdirps.stagder_p2v);
+    backend.tds_solve(dpdy, *dpdy_sx_x, xdirps.interpl_p2v);
+    backend.tds_solve(dpdz, *dpdz_sx_x, xdirps.interpl_p2v);
+    A.release_block(p_sx_x); A.release_block(dpdy_sx_x); A.release_block(dpdz_sx_x);
+  }
+
+  // vector_calculus.f90:40-140
+  void curl(Field& o_i, Field& o_j, Field& o_k, const Field& uu, const Field& vv, const Field& ww) {
+    Allocator& A = allocator;
+    Field *w_y = A.get_block(DIR_Y), *dwdy_y = A.get_block(DIR_Y);
+    backend.reorder(*w_y, ww, RDR_X2Y); backend.tds_solve(*dwdy_y, *w_y, ydirps.der1st);
+    backend.reorder(o_i, *dwdy_y, RDR_Y2X);
+    A.release_block(w_y); A.release_block(dwdy_y);
+    Field *v_z = A.get_block(DIR_Z), *dvdz_z = A.get_block(DIR_Z);
+    backend.reorder(*v_z, vv, RDR_X2Z); backend.tds_solve(*dvdz_z, *v_z, zdirps.der1st);
+    Field* dvdz_x = A.get_block(DIR_X);
+    backend.reorder(*dvdz_x, *dvdz_z, RDR_Z2X);
+    A.release_block(v_z); A.release_block(dvdz_z);
+    backend.vecadd(-1.0, *dvdz_x, 1.0, o_i);
+    A.release_block(dvdz_x);
+    Field *u_z = A.get_block(DIR_Z), *dudz_z = A.get_block(DIR_Z);
+    backend.reorder(*u_z, uu, RDR_X2Z); backend.tds_solve(*dudz_z, *u_z, zdirps.der1st);
+    Field* dudz_x = A.get_block(DIR_X);
+    backend.reorder(*dudz_x, *dudz_z, RDR_Z2X);
+    A.release_block(u_z); A.release_block(dudz_z);
+    backend.tds_solve(o_j, ww, xdirps.der1st);
+    backend.vecadd(1.0, *dudz_x, -1.0, o_j);
+    A.release_block(dudz_x);
+    backend.tds_solve(o_k, vv, xdirps.der1st);
+    Field *u_y = A.get_block(DIR_Y), *dudy_y = A.get_block(DIR_Y);
+    backend.reorder(*u_y, uu, RDR_X2Y); backend.tds_solve(*dudy_y, *u_y, ydirps.der1st);
+    Field* dudy_x = A.get_block(DIR_X);
+    backend.reorder(*dudy_x, *dudy_y, RDR_Y2X);
+    A.release_block(u_y); A.release_block(dudy_y);
+    backend.vecadd(-1.0, *dudy_x, 1.0, o_k);
+    A.release_block(dudy_x);
+  }
+
+  // solver.f90:653-678 + poisson_fft.f90:206-226
+  void poisson_fft(Field& pressure, const Field& div_u) {
+    if (!backend.poisson) fail("FFT Poisson solver is not initialised for these BCs");
+    Field* p_temp = allocator.get_block(DIR_C);
+    backend.reorder(*p_temp, div_u, RDR_Z2C);
+    Field* temp = allocator.get_block(DIR_C);
+    X3D2H_CALL(x3d2c_fft_forward(ctx, backend.poisson, p_temp->dev));
+    X3D2H_CALL(x3d2c_fft_postprocess_000(ctx, backend.poisson));
+    X3D2H_CALL(x3d2c_fft_backward(ctx, backend.poisson, p_temp->dev));
+    allocator.release_block(temp);
+    backend.reorder(pressure, *p_temp, RDR_C2Z);
+    allocator.release_block(p_temp);
+  }
+
+  // solver.f90:693-739
+  void pressure_correction(Field& uu, Field& vv, Field& ww) {
+    Allocator& A = allocator;
+    Field* div_u = A.get_block(DIR_Z);
+    divergence_v2c(*div_u, uu, vv, ww);
+    Field* p = A.get_block(DIR_Z);
+    poisson_fft(*p, *div_u);
+    A.release_block(div_u);
+    Field *dpdx = A.get_block(DIR_X), *dpdy = A.get_block(DIR_X), *dpdz = A.get_block(DIR_X);
+    gradient_c2v(*dpdx, *dpdy, *dpdz, *p);
+    A.release_block(p);
+    backend.vecadd(-1.0, *dpdx, 1.0, uu);
+    backend.vecadd(-1.0, *dpdy, 1.0, vv);
+    backend.vecadd(-1.0, *dpdz, 1.0, ww);
+    A.release_block(dpdx); A.release_block(dpdy); A.release_block(dpdz);
+  }
+
+  // time_integrator.f90:70-164
+  void init_time_integrator() {
+    std::memset(ti_coeffs, 0, sizeof ti_coeffs);
+    std::memset(ti_rk_b, 0, sizeof ti_rk_b);
+    std::memset(ti_rk_a, 0, sizeof ti_rk_a);
+    ti_rk_b[1][1] = 1.0;
+    ti_rk_a[1][1][2] = 0.5; ti_rk_b[2][2] = 1.0;
+    ti_rk_a[1][1][3] = 0.5; ti_rk_a[2][2][3] = 3.0 / 4.0;
+    ti_rk_b[1][3] = 2.0 / 9.0; ti_rk_b[2][3] = 1.0 / 3.0; ti_rk_b[3][3] = 4.0 / 9.0;
+    ti_rk_a[1][1][4] = 0.5; ti_rk_a[2][2][4] = 0.5; ti_rk_a[3][3][4] = 1.0;
+    ti_rk_b[1][4] = 1.0 / 6.0; ti_rk_b[2][4] = 1.0 / 3.0; ti_rk_b[3][4] = 1.0 / 3.0; ti_rk_b[4][4] = 1.0 / 6.0;
+    ti_coeffs[1][1] = 1.0;
+    ti_coeffs[1][2] = 1.5; ti_coeffs[2][2] = -0.5;
+    ti_coeffs[1][3] = 23.0 / 12.0; ti_coeffs[2][3] = -4.0 / 3.0; ti_coeffs[3][3] = 5.0 / 12.0;
+    ti_coeffs[1][4] = 55.0 / 24.0; ti_coeffs[2][4] = -59.0 / 24.0; ti_coeffs[3][4] = 37.0 / 24.0; ti_coeffs[4][4] = -3.0 / 8.0;
+    const std::string& m = cfg.time_intg;
+    if (m.size() != 3) fail("Integration method " + m + " is not defined");
+    ti_order = m[2] - '0';
+    if (ti_order < 1 || ti_order > 4) fail("Integration order >4 is not supported");
+    if (m.substr(0, 2) == "AB") { ti_is_ab = true; ti_nstep = ti_order; ti_nstage = 1; ti_nolds = ti_nstep - 1; }
+    else if (m.substr(0, 2) == "RK") { ti_is_ab = false; ti_nstep = 1; ti_nstage = ti_order; ti_nolds = ti_nstage; }
+    else fail("Integration method " + m + " is not defined");
+    ti_istep = 1; ti_istage = 1;
+    olds.assign(3, std::vector<Field*>(ti_nolds + 1, nullptr));
+    for (int i = 0; i < 3; ++i)
+      for (int j = 1; j <= ti_nolds; ++j) olds[i][j] = allocator.get_block(DIR_X);
+  }
+  // time_integrator.f90:166-231
+  void runge_kutta(Field* curr[3], Field* deriv[3], double dt_) {
+    if (ti_istage == ti_nstage) {
+      for (int i = 0; i < 3; ++i) {
+        if (ti_nstage > 1) backend.veccopy(*curr[i], *olds[i][1]);
+        for (int j = 1; j <= ti_nstage - 1; ++j) backend.vecadd(ti_rk_b[j][ti_nstage] * dt_, *olds[i][j + 1], 1.0, *curr[i]);
+        backend.vecadd(ti_rk_b[ti_nstage][ti_nstage] * dt_, *deriv[i], 1.0, *curr[i]);
+      }
+      ti_istage = 1;
+    } else {
+      for (int i = 0; i < 3; ++i) {
+        if (ti_istage == 1) backend.veccopy(*olds[i][1], *curr[i]);
+        backend.veccopy(*olds[i][ti_istage + 1], *deriv[i]);
+        if (ti_istage > 1) backend.veccopy(*curr[i], *olds[i][1]);
+        for (int j = 1; j <= ti_istage; ++j)
+          backend.vecadd(ti_rk_a[j][ti_istage][ti_nstage] * dt_, *olds[i][j + 1], 1.0, *curr[i]);
+      }
+      ti_istage = ti_istage + 1;
+    }
+  }
+  // time_integrator.f90:233-300
+  void adams_bashforth(Field* curr[3], Field* deriv[3], double dt_) {
+    const int nstep = std::min(ti_istep, ti_nstep);
+    for (int i = 0; i < 3; ++i) {
+      backend.vecadd(ti_coeffs[1][nstep] * dt_, *deriv[i], 1.0, *curr[i]);
+      for (int j = 2; j <= nstep; ++j) backend.vecadd(ti_coeffs[j][nstep] * dt_, *olds[i][j - 1], 1.0, *curr[i]);
+      auto rotate = [&](int n) {
+        Field* ptr = olds[i][n];
+        for (int q = n; q >= 2; --q) olds[i][q] = olds[i][q - 1];
+        olds[i][1] = ptr;
+      };
+      if (nstep < ti_nstep) { if (ti_istep > 1) rotate(nstep); }
+      else { if (ti_nstep > 2) rotate(nstep - 1); }
+      if (ti_nstep > 1) backend.veccopy(*olds[i][1], *deriv[i]);
+    }
+    ti_istep = ti_istep + 1;
+  }
+
+  // base_case.f90:246-289: one time step = nstage x (transeq, time integration, pressure correction)
+  void step() {
+    Field* curr[3] = {u, v, w};
+    for (int sub = 1; sub <= ti_nstage; ++sub) {
+      Field* deriv[3] = {allocator.get_block(DIR_X), allocator.get_block(DIR_X), allocator.get_block(DIR_X)};
+      transeq_default(*deriv[0], *deriv[1], *deriv[2], *u, *v, *w);
+      if (ti_is_ab) adams_bashforth(curr, deriv, dt); else runge_kutta(curr, deriv, dt);
+      for (int i = 0; i < 3; ++i) allocator.release_block(deriv[i]);
+      pressure_correction(*u, *v, *w);
+    }
+  }
+
+  // ---- host <-> field helpers: local Cartesian un-padded arrays of the data_loc extents
+  void pad(std::vector<double>& padded, const double* compact, int data_loc) const {
+    int dims[3];
+    mesh.get_dims(dims, data_loc);
+    const int* p = allocator.dims_padded;
+    padded.assign((size_t)allocator.ngrid, 0.0);
+    for (int k = 0; k < dims[2]; ++k)
+      for (int j = 0; j < dims[1]; ++j)
+        std::memcpy(&padded[(size_t)p[0] * (j + (size_t)p[1] * k)], compact + (size_t)dims[0] * (j + (size_t)dims[1] * k),
+                    sizeof(double) * dims[0]);
+  }
+  void unpad(double* compact, const std::vector<double>& padded, int data_loc) const {
+    int dims[3];
+    mesh.get_dims(dims, data_loc);
+    const int* p = allocator.dims_padded;
+    for (int k = 0; k < dims[2]; ++k)
+      for (int j = 0; j < dims[1]; ++j)
+        std::memcpy(compact + (size_t)dims[0] * (j + (size_t)dims[1] * k), &padded[(size_t)p[0] * (j + (size_t)p[1] * k)],
+                    sizeof(double) * dims[0]);
+  }
+  void set_field(Field& f, const double* compact, int data_loc) {
+    std::vector<double> padded;
+    pad(padded, compact, data_loc);
+    f.data_loc = data_loc;
+    backend.set_field_data(f, padded.data());
+    f.data_loc = data_loc;
+  }
+  void get_field(double* compact, const Field& f, int data_loc) {
+    std::vector<double> padded((size_t)allocator.ngrid);
+    backend.get_field_data(padded.data(), f);
+    unpad(compact, padded, data_loc);
+  }
+
+  // case/tgv.f90:41-72 through base_case.f90:139-179 (set_init)
+  void init_tgv() {
+    const int nx = mesh.vert_dims[0], ny = mesh.vert_dims[1], nz = mesh.vert_dims[2];
+    std::vector<double> hu((size_t)nx * ny * nz), hv(hu.size());
+    for (int k = 0; k < nz; ++k)
+      for (int j = 0; j < ny; ++j)
+        for (int i = 0; i < nx; ++i) {
+          const double x = mesh.vert_coords[0][i], y = mesh.vert_coords[1][j], z = mesh.vert_coords[2][k];
+          hu[i + (size_t)nx * (j + (size_t)ny * k)] = std::sin(x) * std::cos(y) * std::cos(z);
+          hv[i + (size_t)nx * (j + (size_t)ny * k)] = -std::cos(x) * std::sin(y) * std::cos(z);
+        }
+    set_field(*u, hu.data(), VERT);
+    set_field(*v, hv.data(), VERT);
+    X3D2H_CALL(x3d2c_field_fill(ctx, w->dev, 0.0));
+    u->data_loc = VERT; v->data_loc = VERT; w->data_loc = VERT;
+  }
+
+  // monitoring.f90:46-90 (+ kinetic energy with the same normalisation)
+  double enstrophy() {
+    Field *du = allocator.get_block(DIR_X, VERT), *dv = allocator.get_block(DIR_X, VERT), *dw = allocator.get_block(DIR_X, VERT);
+    curl(*du, *dv, *dw, *u, *v, *w);
+    const double e = 0.5 * (backend.scalar_product(*du, *du) + backend.scalar_product(*dv, *dv) + backend.scalar_product(*dw, *dw)) / ngrid;
+    allocator.release_block(du); allocator.release_block(dv); allocator.release_block(dw);
+    return e;
+  }
+  double kinetic_energy() {
+    return 0.5 * (backend.scalar_product(*u, *u) + backend.scalar_product(*v, *v) + backend.scalar_product(*w, *w)) / ngrid;
+  }
+  void divergence_max_mean(double& mx, double& mean) {
+    Field* div_u = allocator.get_block(DIR_Z);
+    divergence_v2c(*div_u, *u, *v, *w);
+    backend.field_max_mean(mx, mean, *div_u);
+    allocator.release_block(div_u);
+  }
+
+  const DevTdsops& pick(int dir, const std::string& name) const {
+    const DevDirps& d = dir == DIR_X ? xdirps : (dir == DIR_Y ? ydirps : zdirps);
+    if (name == "der1st") return d.der1st;
+    if (name == "der1st_sym") return d.der1st_sym;
+    if (name == "der2nd") return d.der2nd;
+    if (name == "der2nd_sym") return d.der2nd_sym;
+    if (name == "stagder_v2p") return d.stagder_v2p;
+    if (name == "stagder_p2v") return d.stagder_p2v;
+    if (name == "interpl_v2p") return d.interpl_v2p;
+    if (name == "interpl_p2v") return d.interpl_p2v;
+    fail("unknown operator name " + name);
+  }
+};
+
+}  // namespace x3d2h
