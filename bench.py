@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the cuda_c backend: Taylor-Green vortex, FP64, RK3.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun by the driver)
+  python bench.py --impl reference --steps K --warmup W    (CPU arm: the oracle port of the reference OMP backend)
+
+A "step" is one full RK3 time step of the reference's time loop (src/case/base_case.f90:246-289): three sub-stages
+of transeq + time integration + pressure correction. Metric: Mpt-steps/s = global grid points * steps / time / 1e6.
+Workload (weak scaling, 512^3 points per GPU): 512^3 (N=1, BASELINE.json configs[2]), 512x512x1024 (N=2),
+512x1024x1024 (N=4), 1024^3 (N=8, configs[3]); slab decomposition nproc_dir = (1, 1, N).
+One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_PT = {"transeq": 48, "tds_solve": 16}  # per transeq_{x,y,z} / tds_solve call
+STEP_BYTES_PER_PT = 3888                                # whole RK3 step
+
+
+def grid_for(n_gpus, base):
+    dims = [base, base, base]
+    k, axis = n_gpus, 2
+    while k > 1:  # double z, then y, then x: 1 -> (b,b,b), 2 -> (b,b,2b), 4 -> (b,2b,2b), 8 -> (2b,2b,2b)
+        dims[axis] *= 2
+        axis -= 1
+        k //= 2
+    return dims
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx = float(p[1])
+            except ValueError:
+                continue
+            for name, val in zip(names, p[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_run(dims, steps, warmup, threads=None):
+    """Times the oracle port (C++/OpenMP restatement of the reference OMP backend) on the host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+    n_threads = threads or os.cpu_count()
+    os.environ.setdefault("OMP_NUM_THREADS", str(n_threads))
+    w = _oracle.World(tuple(dims))
+    w.init_tgv()
+    for _ in range(warmup):
+        w.step(1)
+    t0 = time.perf_counter()
+    w.step(steps)
+    dt = time.perf_counter() - t0
+    pts = dims[0] * dims[1] * dims[2]
+    return pts * steps / dt / 1e6, dt / steps, n_threads
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path. The Fortran/MPI/2DECOMP build is impossible in this image
+    (no gfortran, no MPI), so oracle/_ref does not exist and the oracle port is timed (kind = "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = args.cpu_size
+    if base <= 0:
+        # calibrate on 64^3, then pick the largest grid whose K+W steps fit in ~150 s
+        v, s_per_step, _ = cpu_port_run([64] * 3, 1, 1)
+        per_pt = s_per_step / 64 ** 3
+        base = 64
+        for cand in (96, 128, 192, 256):
+            if per_pt * cand ** 3 * (args.steps + args.warmup) * 1.3 < 150:
+                base = cand
+    dims = [base] * 3
+    value, s_per_step, threads = cpu_port_run(dims, args.steps, args.warmup)
+    sample = (f"TGV {base}^3 FP64 RK3, {args.steps} steps after {args.warmup} warm-up: a bounded sample of the "
+              f"{args.size}^3-per-GPU workload (same per-point work, smaller periodic box)")
+    out = {"impl": "reference", "metric": "Mpt-steps/s", "value": value, "unit": "Mpt-steps/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * s_per_step, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"TGV {args.size}^3 per GPU FP64 RK3 (Re=1600, dt=1e-3, compact6)", "sample": sample},
+           "cpu_baseline": {"value": value, "unit": "Mpt-steps/s", "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "Mpt-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda_c", choices=["cuda_c", "reference"])
+    ap.add_argument("--size", type=int, default=512, help="grid points per direction per GPU (default 512)")
+    ap.add_argument("--cpu-size", type=int, default=0, help="grid of the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strict", action="store_true", help="reference-order (bit-exact) kernels instead of the fast path")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+
+    import x3d2_b200 as X
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    nccl_id = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        c, _ = X.load()
+        buf = [None]
+        if rank == 0:
+            import ctypes
+            raw = ctypes.create_string_buffer(128)
+            assert c.x3d2c_nccl_unique_id(raw) == 0, c.x3d2c_last_error()
+            buf = [raw.raw]
+        dist.broadcast_object_list(buf, src=0)
+        nccl_id = buf[0]
+
+    dims = grid_for(world, args.size)
+    L = tuple(2 * np.pi * d / args.size for d in dims)
+    sim = X.Sim(dims, nproc_dir=(1, 1, world), L=L, rank=rank, nproc=world, device=local_rank, strict=args.strict,
+                nccl_unique_id=nccl_id)
+    sim.init_tgv()
+    stream = torch.cuda.ExternalStream(sim.stream())
+    pts_global = dims[0] * dims[1] * dims[2]
+    pts_local = pts_global // world
+
+    def barrier():
+        sim.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---------------------------------------------------------------- device-resident timing (value)
+    sim.step(args.warmup)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = sim.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sim.step(args.steps)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = sim.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = pts_global / (ms_per_step * 1e-3) / 1e6
+    mon = sim.monitor()
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel (transeq)
+    peak, peak_src = measured_peak()
+    roof = {}
+    for op, key in (("transeq_x", "transeq"), ("tds_solve_x", "tds_solve")):
+        sim.bench_op(op, 2)
+        sim.sync()
+        reps = 5
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        sim.bench_op(op, reps)
+        b.record(stream)
+        b.synchronize()
+        op_ms = a.elapsed_time(b) / reps
+        roof[key] = {"ms": op_ms, "gbs": ALGO_BYTES_PER_PT[key] * pts_local / op_ms / 1e6}
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("transeq_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "transeq_x (fused DistD2-TDS transeq, one call = 3 velocity components)",
+                "achieved": roof["transeq"]["gbs"], "peak": peak, "unit": "GB/s", "frac": roof["transeq"]["gbs"] / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": 48 * pts_local,
+                "ms_per_launch": roof["transeq"]["ms"],
+                "tds_solve": {"achieved": roof["tds_solve"]["gbs"], "frac": roof["tds_solve"]["gbs"] / peak,
+                              "ms_per_launch": roof["tds_solve"]["ms"], "algorithmic_bytes_per_launch": 16 * pts_local},
+                "whole_step": {"achieved": STEP_BYTES_PER_PT * pts_local / (ms_per_step * 1e-3) / 1e9,
+                               "frac": STEP_BYTES_PER_PT * pts_local / (ms_per_step * 1e-3) / 1e9 / peak,
+                               "algorithmic_bytes_per_step": STEP_BYTES_PER_PT * pts_local}}
+
+    # ---------------------------------------------------------------- end to end: host buffers in, host buffers out
+    nz, ny, nx = sim.shape()
+    host = [torch.empty((nz, ny, nx), dtype=torch.float64).pin_memory() for _ in range(3)]
+    host_np = [h.numpy() for h in host]
+    sim.get_uvw(out=host_np)
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sim.set_uvw(*host_np)          # H2D of the step's inputs (pinned)
+        sim.step(1)
+        sim.get_uvw(out=host_np)       # D2H of the step's result (synchronises)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": pts_global / e2e_s / 1e6, "unit": "Mpt-steps/s", "h2d_bytes_per_step": 3 * 8 * pts_local,
+           "d2h_bytes_per_step": 3 * 8 * pts_local, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s}
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cs = args.cpu_size if args.cpu_size > 0 else 128
+        v, s_per_step, threads = cpu_port_run([cs] * 3, 3, 1)
+        cpu = {"value": v, "unit": "Mpt-steps/s", "cores": threads, "kind": "port",
+               "sample": f"TGV {cs}^3 FP64 RK3, 3 steps after 1 warm-up, oracle port of the reference OMP backend "
+                         f"(C++/OpenMP, strict IEEE), {1e3 * s_per_step:.0f} ms/step"}
+
+    if rank == 0:
+        out = {"metric": "Mpt-steps/s", "value": value, "unit": "Mpt-steps/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": f"Taylor-Green vortex {dims[0]}x{dims[1]}x{dims[2]} FP64 RK3 "
+                                      f"(Re=1600, dt=1e-3, compact6/classic), {args.size}^3 points per GPU, "
+                                      f"nproc_dir=(1,1,{world})",
+                          "mode": "strict (reference-order, bit-exact)" if args.strict else "fast (FMA)",
+                          "l2": "every field block (8 B x points per GPU) exceeds the 126 MB L2; no flush needed",
+                          "monitor_after_run": mon},
+               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(out), flush=True)
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -89,6 +89,8 @@ typedef struct {
 
 const char* x3d2c_last_error(void);
 int x3d2c_version(void);
+/* fills 128 bytes with a fresh ncclUniqueId (rank 0 calls this and broadcasts the bytes to all ranks) */
+int x3d2c_nccl_unique_id(void* out128);
 
 /* ---- backend object: cuda_backend_t%init / finaliser (src/backend/cuda/backend.f90:95-152) */
 int x3d2c_create(const x3d2c_config* cfg, x3d2c_ctx** out);

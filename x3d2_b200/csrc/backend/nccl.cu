@@ -134,3 +134,18 @@ int alltoall(x3d2c_ctx* ctx, double* recv, const double* send, size_t block_doub
 }
 
 }  // namespace x3d2c
+
+extern "C" int x3d2c_nccl_unique_id(void* out128) {
+  using namespace x3d2c;
+  X3D2C_REQUIRE(out128, "x3d2c_nccl_unique_id: null argument");
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { set_error(std::string("cannot dlopen libnccl.so.2: ") + dlerror()); return X3D2C_ENCCL; }
+  int (*get_id)(ncclUniqueId_t*) = nullptr;
+  *(void**)(&get_id) = dlsym(h, "ncclGetUniqueId");
+  if (!get_id) { set_error("missing NCCL symbol ncclGetUniqueId"); return X3D2C_ENCCL; }
+  ncclUniqueId_t id;
+  if (get_id(&id) != 0) { set_error("ncclGetUniqueId failed"); return X3D2C_ENCCL; }
+  std::memcpy(out128, &id, sizeof id);
+  return X3D2C_OK;
+}

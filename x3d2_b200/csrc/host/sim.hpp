@@ -665,14 +665,28 @@ class Sim {
         std::memcpy(compact + (size_t)dims[0] * (j + (size_t)dims[1] * k), &padded[(size_t)p[0] * (j + (size_t)p[1] * k)],
                     sizeof(double) * dims[0]);
   }
+  bool is_unpadded(int data_loc) const {
+    int dims[3];
+    mesh.get_dims(dims, data_loc);
+    const int* p = allocator.dims_padded;
+    return dims[0] == p[0] && dims[1] == p[1] && dims[2] == p[2];
+  }
   void set_field(Field& f, const double* compact, int data_loc) {
-    std::vector<double> padded;
-    pad(padded, compact, data_loc);
     f.data_loc = data_loc;
-    backend.set_field_data(f, padded.data());
+    if (is_unpadded(data_loc)) {  // the caller's array already is the DIR_C block: copy straight from it
+      backend.set_field_data(f, compact);
+    } else {
+      std::vector<double> padded;
+      pad(padded, compact, data_loc);
+      backend.set_field_data(f, padded.data());
+    }
     f.data_loc = data_loc;
   }
   void get_field(double* compact, const Field& f, int data_loc) {
+    if (is_unpadded(data_loc)) {
+      backend.get_field_data(compact, f);
+      return;
+    }
     std::vector<double> padded((size_t)allocator.ngrid);
     backend.get_field_data(padded.data(), f);
     unpad(compact, padded, data_loc);
