@@ -1,0 +1,51 @@
+"""Fast path (segment-parallel register-resident kernels, tds_m3.cu) vs the oracle and vs the strict kernels."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12  # north_star: derivatives and fields within 1e-12 relative in FP64
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def rnd(shape, seed):
+    return np.random.default_rng(seed).standard_normal(shape)
+
+
+@pytest.mark.parametrize("dims", [(64, 64, 64), (128, 96, 80), (256, 64, 128), (512, 64, 64), (64, 1024, 64)])
+def test_fast_vs_oracle_and_strict(oracle, x3d2, dims):
+    fast, strict, ref = x3d2.Sim(dims), x3d2.Sim(dims, strict=True), oracle.World(dims)
+    u, v, w = rnd(fast.shape(), 1), rnd(fast.shape(), 2), rnd(fast.shape(), 3)
+    worst = 0.0
+    for d in (1, 2, 3):
+        for op in ("der1st", "der2nd", "stagder_v2p", "interpl_v2p"):
+            e = ref.tds_solve(d, op, u)
+            assert np.array_equal(strict.tds_solve(d, op, u), e)
+            worst = max(worst, rel(fast.tds_solve(d, op, u), e))
+        for op in ("stagder_p2v", "interpl_p2v"):
+            e = ref.tds_solve(d, op, u, 1110)
+            worst = max(worst, rel(fast.tds_solve(d, op, u, 1110), e))
+        exp = ref.transeq_dir(d, u, v, w)
+        for g, s, e in zip(fast.transeq_dir(d, u, v, w), strict.transeq_dir(d, u, v, w), exp):
+            assert np.array_equal(s, e)
+            worst = max(worst, rel(g, e))
+    print(dims, "worst fast-path rel err", worst)
+    assert worst < TOL
+    fast.close()
+    strict.close()
+
+
+def test_tgv_256_one_step(oracle, x3d2):
+    """BASELINE.json configs[1] size: one RK3 step at 256^3, fields within 1e-12 of the OMP oracle."""
+    n = 256
+    sim, ref = x3d2.Sim((n, n, n)), oracle.World((n, n, n))
+    sim.init_tgv()
+    ref.init_tgv()
+    sim.step(1)
+    ref.step(1)
+    a, b = sim.get_uvw(), ref.get_uvw()
+    scale = max(np.abs(y).max() for y in b)
+    assert max(np.abs(x - y).max() for x, y in zip(a, b)) / scale < TOL
+    sim.close()
