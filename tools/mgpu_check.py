@@ -28,14 +28,14 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     c, _ = X.load()
-    buf = [None]
-    if rank == 0:
-        raw = ctypes.create_string_buffer(128)
-        assert c.x3d2c_nccl_unique_id(raw) == 0, c.x3d2c_last_error()
-        buf = [raw.raw]
-    dist.broadcast_object_list(buf, src=0)
     ok = True
     for strict in (False, True):
+        buf = [None]  # one ncclUniqueId per communicator
+        if rank == 0:
+            raw = ctypes.create_string_buffer(128)
+            assert c.x3d2c_nccl_unique_id(raw) == 0, c.x3d2c_last_error()
+            buf = [raw.raw]
+        dist.broadcast_object_list(buf, src=0)
         sim = X.Sim(dims, nproc_dir=(1, 1, world), rank=rank, nproc=world, device=local, strict=strict,
                     nccl_unique_id=buf[0])
         sim.init_tgv()
