@@ -145,7 +145,7 @@ __device__ __forceinline__ int woff(int t, int bm, int b0, int bp) {
 // One velocity component of one tile, everything addressed by offsets into smem[]. fF: field tile (in/out, in
 // place); fC: conv tile; cur / oth: the two three-field buffers whose pad rows hold the carries (ze in cur,
 // ys in oth).
-template <int L, unsigned M1, unsigned M2>
+template <int L, unsigned M1, unsigned M2, bool SELF>  // SELF: the field is its own conv (aligned velocity)
 __device__ __forceinline__ void component(const int fF, const int fC, const int cur, const int oth, const Params& p,
                                           const int q, const int l, const int bm, const int b0, const int bp) {
   const int nseg = p.g.nseg, fd = p.g.field_doubles;
@@ -156,14 +156,14 @@ __device__ __forceinline__ void component(const int fF, const int fC, const int 
     for (int t = 0; t < 8; ++t) {
       const int o = woff<L>(t, bm, b0, bp);
       wf[t] = smem[fF + o];
-      wp[t] = wf[t] * smem[fC + o];
+      wp[t] = wf[t] * (SELF ? wf[t] : smem[fC + o]);
     }
     double p1 = 0.0, p2 = 0.0, p3 = 0.0;
 #pragma unroll
     for (int k = 0; k < S; ++k) {
       const int o = woff<L>(k + 8, bm, b0, bp);
       wf[8] = smem[fF + o];
-      wp[8] = wf[8] * smem[fC + o];
+      wp[8] = wf[8] * (SELF ? wf[8] : smem[fC + o]);
       p1 = fma(p.o_du.a, p1, sten<M1>(p.o_du.cfw, wf));
       p2 = fma(p.o_dud.a, p2, sten<M1>(p.o_dud.cfw, wp));
       p3 = fma(p.o_d2u.a, p3, sten<M2>(p.o_d2u.cfw, wf));
@@ -238,9 +238,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) transeq_m3_kernel(const __grid
     const int bo = (it & 1) * 3 * fd, oo = ((it & 1) ^ 1) * 3 * fd;
     double* b = smem + bo;
     // components 1 and 2 first: they read the aligned velocity (field 0) as conv; field 0 is overwritten last
-    component<L, M1, M2>(bo + 1 * fd, bo, bo, oo, p, q, l, bm, b0, bp);
-    component<L, M1, M2>(bo + 2 * fd, bo, bo, oo, p, q, l, bm, b0, bp);
-    component<L, M1, M2>(bo, bo, bo, oo, p, q, l, bm, b0, bp);
+    component<L, M1, M2, false>(bo + 1 * fd, bo, bo, oo, p, q, l, bm, b0, bp);
+    component<L, M1, M2, false>(bo + 2 * fd, bo, bo, oo, p, q, l, bm, b0, bp);
+    component<L, M1, M2, true>(bo, bo, bo, oo, p, q, l, bm, b0, bp);
 #pragma unroll
     for (int f = 0; f < 3; ++f) cp.store(p.out[f], b + f * fd, g, tile);
     __syncthreads();
