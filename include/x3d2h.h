@@ -35,6 +35,8 @@ typedef struct {
   int device;                 /* CUDA device ordinal, -1 = current */
   int flags;                  /* X3D2C_FLAG_* */
   const void* nccl_unique_id; /* 128 bytes when nproc > 1 */
+  const char* stretching[3];  /* 'uniform' | 'centred' | 'top-bottom' | 'bottom' per direction; NULL = uniform */
+  double beta[3];             /* stretching parameter (src/config.f90 domain_settings) */
 } x3d2h_config;
 
 const char* x3d2h_last_error(void);
@@ -43,6 +45,8 @@ const char* x3d2h_last_error(void);
 /* mesh_t decomposition (src/mesh.f90:160-194, src/mesh_content.f90:72-121). out: vert_dims[3], cell_dims[3],
  * n_offset[3], nrank_dir[3], pprev[3], pnext[3], BCs[6] = 24 ints */
 int x3d2h_decompose(const x3d2h_config* cfg, int* out24);
+/* geo_t of rank cfg->rank along `dir` (0..2): vert_coords, vert_ds, vert_ds2, vert_d2s (n_vert), midp_coords, midp_ds (n_cell) */
+int x3d2h_geo(const x3d2h_config* cfg, int dir, double* vc, double* vds, double* vds2, double* vd2s, double* mc, double* mds);
 /* tdsops_init (src/tdsops.f90:63-203): fills the tables exactly as they are passed to x3d2c_tdsops_create.
  * info[4] = n_tds, n_rhs, move, periodic; sc[5] = alpha, a, b, c, d; arrays as in x3d2c_tdsops_create. */
 int x3d2h_tdsops_tables(int n_tds, double delta, const char* operation, const char* scheme, int bc_start, int bc_end,
@@ -86,6 +90,10 @@ int x3d2h_sum_intox(x3d2h_sim* sim, int dir_from, const double* a, const double*
 int x3d2h_vecadd(x3d2h_sim* sim, int dir, double a, const double* x, double b, const double* y, double* out);
 int x3d2h_scalar_product(x3d2h_sim* sim, int dir, int data_loc, const double* x, const double* y, double* s);
 int x3d2h_field_max_mean(x3d2h_sim* sim, int dir, int data_loc, const double* x, double* mx, double* mean);
+
+/* remaining elementwise ops / reductions: op = "scale" | "shift" | "vecmult" | "veccopy" | "fill" | "volume_integral" */
+int x3d2h_fieldop(x3d2h_sim* sim, const char* op, int dir, int data_loc, double a, const double* x, const double* y,
+                  double* out, double* s);
 
 /* ---- device-resident benchmark helpers: fields stay in HBM, only the op is enqueued (bench.py) */
 /* op: "transeq_x|y|z", "tds_solve_x|y|z" (der1st), "reorder_x2y|x2z|y2z|z2c|...", "sum_yintox", "vecadd", ... */

@@ -325,3 +325,11 @@ class World:
         o = list(out)
         return dict(vert_dims=o[0:3], cell_dims=o[3:6], padded=o[6:9], n_groups=o[9:12],
                     BCs=[o[12:14], o[14:16], o[16:18]])
+
+    def geo(self, dir):
+        """geo_t of emulated rank 0 along dir (0..2): mesh_content.f90:159-263 as restated in orc_world.hpp."""
+        nv = self.shape()[2 - dir]
+        nc = self.shape(CELL)[2 - dir]
+        a = [np.zeros(nv) for _ in range(4)] + [np.zeros(nc) for _ in range(2)]
+        _chk(lib().orc_world_geo(self.h, dir, *[_p(x) for x in a]))
+        return dict(zip(("vert_coords", "vert_ds", "vert_ds2", "vert_d2s", "midp_coords", "midp_ds"), a))

@@ -108,6 +108,25 @@ def test_waves_match_oracle(x3d2, oracle):
     assert w[0, 0, 0] == 0 and np.all(w.real == w.imag)
 
 
+@pytest.mark.parametrize("stretching,beta,bc", [("uniform", 1.0, (0, 0)), ("uniform", 1.0, (2, 2)),
+                                                ("centred", 0.8, (1, 1)), ("top-bottom", 0.259065151, (2, 2)),
+                                                ("bottom", 1.3, (2, 1)), ("centred", 2.0, (0, 0))])
+def test_geo_matches_oracle(x3d2, oracle, stretching, beta, bc):
+    """Stretched-mesh coordinates and stretching factors of the host mesh (mesh_content.f90:159-263) are the oracle's, bitwise."""
+    n = 64 if bc[0] == 0 else 65
+    for d in range(3):
+        dims, bcs = [32, 32, 32], [(0, 0)] * 3
+        st, be = ["uniform"] * 3, [1.0] * 3
+        dims[d], bcs[d], st[d], be[d] = n, bc, stretching, beta
+        g = x3d2.geo(tuple(dims), d, tuple(bcs), (2.0, 1.0, 3.0), st, be)
+        e = oracle.World(tuple(dims), L=(2.0, 1.0, 3.0), bcs=tuple(bcs), stretching=st, beta=be).geo(d)
+        for k in e:
+            assert np.array_equal(g[k], e[k]), (d, k)
+        if stretching != "uniform":
+            assert np.ptp(g["vert_ds"]) > 0
+            assert np.all(np.diff(g["vert_coords"]) > 0)
+
+
 def test_bench_grid_and_reference_arm():
     import subprocess, sys, json
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

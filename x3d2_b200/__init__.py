@@ -18,7 +18,7 @@ from . import lib as _libmod
 from .lib import (BC_DIRICHLET, BC_HALO, BC_NEUMANN, BC_PERIODIC, CELL, DIR_C, DIR_X, DIR_Y, DIR_Z, FLAG_STRICT, RDR,
                   VERT, X3D2HConfig, build, load)
 
-__all__ = ["Sim", "build", "load", "tdsops_tables", "decompose", "waves_000", "DIR_X", "DIR_Y", "DIR_Z", "DIR_C", "VERT",
+__all__ = ["Sim", "build", "load", "tdsops_tables", "decompose", "geo", "waves_000", "DIR_X", "DIR_Y", "DIR_Z", "DIR_C", "VERT",
            "CELL", "BC_PERIODIC", "BC_NEUMANN", "BC_DIRICHLET", "BC_HALO", "FLAG_STRICT", "RDR"]
 
 _dp = C.POINTER(C.c_double)
@@ -39,7 +39,7 @@ def _chk(rc):
 
 
 def _config(dims, nproc_dir, L, bcs, Re, dt, time_intg, der1st, der2nd, interpl, stagder, rank, nproc, device, flags,
-            nccl_id):
+            nccl_id, stretching=None, beta=None):
     cfg = X3D2HConfig()
     cfg.dims_global = (C.c_int * 3)(*[int(d) for d in dims])
     cfg.nproc_dir = (C.c_int * 3)(*nproc_dir)
@@ -53,6 +53,9 @@ def _config(dims, nproc_dir, L, bcs, Re, dt, time_intg, der1st, der2nd, interpl,
     cfg.stagder_scheme = stagder.encode()
     cfg.rank, cfg.nproc, cfg.device, cfg.flags = rank, nproc, device, flags
     cfg.nccl_unique_id = C.cast(C.c_char_p(nccl_id), C.c_void_p) if nccl_id else None
+    st = stretching or ("uniform",) * 3
+    cfg.stretching = (C.c_char_p * 3)(*[s.encode() for s in st])
+    cfg.beta = (C.c_double * 3)(*(beta or (1.0, 1.0, 1.0)))
     return cfg
 
 
@@ -66,6 +69,17 @@ def decompose(dims, nproc_dir, rank, bcs=((0, 0), (0, 0), (0, 0)), L=(2 * np.pi,
     o = list(out)
     return dict(vert_dims=o[0:3], cell_dims=o[3:6], n_offset=o[6:9], nrank_dir=o[9:12], pprev=o[12:15], pnext=o[15:18],
                 BCs=[o[18:20], o[20:22], o[22:24]])
+
+
+def geo(dims, dir, bcs=((0, 0), (0, 0), (0, 0)), L=(2 * np.pi,) * 3, stretching=None, beta=None):
+    """geo_t of the host layer along `dir` (0..2) on a single rank (no GPU needed)."""
+    cfg = _config(dims, (1, 1, 1), L, bcs, 1600.0, 1e-3, "RK3", "compact6", "compact6", "classic", "compact6", 0, 1, -1, 0,
+                  None, stretching, beta)
+    nv = dims[dir]
+    nc = nv if bcs[dir][0] == BC_PERIODIC else nv - 1
+    a = [np.zeros(nv) for _ in range(4)] + [np.zeros(nc) for _ in range(2)]
+    _chk(load()[1].x3d2h_geo(C.byref(cfg), dir, *[_p(x) for x in a]))
+    return dict(zip(("vert_coords", "vert_ds", "vert_ds2", "vert_d2s", "midp_coords", "midp_ds"), a))
 
 
 def tdsops_tables(n_tds, delta, operation, scheme, bc_start, bc_end, stretch=None, stretch_correct=None, n_halo=4,
@@ -107,13 +121,13 @@ class Sim:
 
     def __init__(self, dims, nproc_dir=(1, 1, 1), L=(2 * np.pi,) * 3, bcs=((0, 0), (0, 0), (0, 0)), Re=1600.0, dt=1e-3,
                  time_intg="RK3", der1st="compact6", der2nd="compact6", interpl="classic", stagder="compact6", rank=0,
-                 nproc=1, device=-1, strict=False, nccl_unique_id=None):
+                 nproc=1, device=-1, strict=False, nccl_unique_id=None, stretching=None, beta=None):
         self._c, self._h = load()
         self.dims = tuple(int(d) for d in dims)
         self.periodic = [pair[0] == BC_PERIODIC for pair in bcs]
         self._nccl_id = nccl_unique_id  # keep the bytes alive
         cfg = _config(dims, nproc_dir, L, bcs, Re, dt, time_intg, der1st, der2nd, interpl, stagder, rank, nproc, device,
-                      FLAG_STRICT if strict else 0, nccl_unique_id)
+                      FLAG_STRICT if strict else 0, nccl_unique_id, stretching, beta)
         self.h = C.c_void_p()
         rc = self._h.x3d2h_create(C.byref(cfg), C.byref(self.h))
         if rc != 0:
@@ -265,3 +279,13 @@ class Sim:
         mx, mean = C.c_double(0), C.c_double(0)
         _chk(self._h.x3d2h_field_max_mean(self.h, dir, loc, _p(x), C.byref(mx), C.byref(mean)))
         return mx.value, mean.value
+
+    def fieldop(self, op, dir, x, y=None, a=0.0, loc=VERT):
+        """field_scale / field_shift / vecmult / veccopy / fill / volume_integral on host data."""
+        x = _f(x)
+        y = _f(y) if y is not None else None
+        out = self._out(loc)
+        s = C.c_double(0)
+        _chk(self._h.x3d2h_fieldop(self.h, op.encode(), dir, loc, float(a), _p(x), _p(y) if y is not None else None,
+                                   _p(out), C.byref(s)))
+        return s.value if op == "volume_integral" else out

@@ -36,6 +36,10 @@ static Config to_config(const x3d2h_config* c) {
   if (c->stagder_scheme) k.stagder = c->stagder_scheme;
   k.rank = c->rank; k.nproc = c->nproc; k.device = c->device; k.flags = c->flags;
   k.nccl_unique_id = c->nccl_unique_id;
+  for (int q = 0; q < 3; ++q) {
+    if (c->stretching[q]) k.stretching[q] = c->stretching[q];
+    k.beta[q] = c->beta[q] > 0 ? c->beta[q] : 1.0;
+  }
   return k;
 }
 
@@ -61,6 +65,17 @@ int x3d2h_decompose(const x3d2h_config* cfg, int* out) {
     out[q] = m.vert_dims[q]; out[3 + q] = m.cell_dims[q]; out[6 + q] = m.n_offset[q]; out[9 + q] = m.nrank_dir[q];
     out[12 + q] = m.pprev[q]; out[15 + q] = m.pnext[q]; out[18 + 2 * q] = m.BCs[q][0]; out[19 + 2 * q] = m.BCs[q][1];
   }
+  H_CATCH
+}
+
+int x3d2h_geo(const x3d2h_config* cfg, int dir, double* vc, double* vds, double* vds2, double* vd2s, double* mc, double* mds) {
+  H_TRY
+  Mesh m;
+  m.init(to_config(cfg));
+  for (size_t i = 0; i < m.vert_coords[dir].size(); ++i) {
+    vc[i] = m.vert_coords[dir][i]; vds[i] = m.vert_ds[dir][i]; vds2[i] = m.vert_ds2[dir][i]; vd2s[i] = m.vert_d2s[dir][i];
+  }
+  for (size_t i = 0; i < m.midp_coords[dir].size(); ++i) { mc[i] = m.midp_coords[dir][i]; mds[i] = m.midp_ds[dir][i]; }
   H_CATCH
 }
 
@@ -356,3 +371,25 @@ int x3d2h_bench_op(x3d2h_sim* sim, const char* op_c, int reps) {
 }
 
 }  // extern "C"
+
+// remaining elementwise ops / reductions of base_backend_t on host data (parity tests):
+// op = "scale" | "shift" | "vecmult" | "veccopy" | "fill" | "volume_integral"
+extern "C" int x3d2h_fieldop(x3d2h_sim* sim, const char* op_c, int dir, int data_loc, double a, const double* x,
+                             const double* y, double* out, double* s) {
+  H_TRY
+  Sim& S = *sim->s;
+  const std::string op = op_c;
+  Tmp t(S.allocator);
+  Field *fx = t.get(dir, data_loc), *fy = t.get(dir, data_loc);
+  S.set_field(*fx, x, data_loc);
+  if (y) S.set_field(*fy, y, data_loc);
+  if (op == "scale") X3D2H_CALL(x3d2c_field_scale(S.ctx, fx->dev, a));
+  else if (op == "shift") X3D2H_CALL(x3d2c_field_shift(S.ctx, fx->dev, a));
+  else if (op == "vecmult") { X3D2H_CALL(x3d2c_vecmult(S.ctx, fy->dev, fx->dev)); fx = fy; }
+  else if (op == "veccopy") { S.backend.veccopy(*fy, *fx); fx = fy; }
+  else if (op == "fill") X3D2H_CALL(x3d2c_field_fill(S.ctx, fx->dev, a));
+  else if (op == "volume_integral") X3D2H_CALL(x3d2c_field_volume_integral(S.ctx, data_loc, fx->dev, s));
+  else fail("x3d2h_fieldop: unknown op " + op);
+  if (out) S.get_field(out, *fx, data_loc);
+  H_CATCH
+}

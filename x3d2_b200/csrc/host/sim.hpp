@@ -33,6 +33,8 @@ struct Config {
               stagder = "compact6";
   int rank = 0, nproc = 1, device = -1, flags = 0;
   const void* nccl_unique_id = nullptr;
+  std::string stretching[3] = {"uniform", "uniform", "uniform"};
+  double beta[3] = {1.0, 1.0, 1.0};
 };
 
 // ------------------------------------------------------------------------------------ mesh
@@ -43,9 +45,12 @@ struct Mesh {
   int BCs_global[3][2], BCs[3][2];
   // par_t
   int nrank = 0, nproc = 1, nrank_dir[3], nproc_dir[3], n_offset[3], pprev[3], pnext[3];
-  // geo_t (uniform meshes; the stretched channel is a later row of SURVEY.md §8f)
-  double d[3], L[3];
-  std::vector<double> vert_coords[3], midp_coords[3];
+  // geo_t (mesh_content.f90:6-27)
+  double d[3], L[3], alpha[3] = {0, 0, 0}, beta[3] = {1, 1, 1};
+  std::string stretching[3];
+  bool stretched[3] = {false, false, false};
+  std::vector<double> vert_coords[3], midp_coords[3], vert_ds[3], vert_ds2[3], vert_d2s[3], midp_ds[3], midp_ds2[3],
+      midp_d2s[3];
 
   // mesh.f90:37-158 with the generic decomposition of :160-194
   void init(const Config& c) {
@@ -85,11 +90,56 @@ struct Mesh {
       else if (first) { BCs[dir][0] = BCs_global[dir][0]; BCs[dir][1] = BC_HALO; }
       else if (last) { BCs[dir][0] = BC_HALO; BCs[dir][1] = BCs_global[dir][1]; }
       else { BCs[dir][0] = BC_HALO; BCs[dir][1] = BC_HALO; }
-      // mesh_content.f90:163-176 (uniform)
-      vert_coords[dir].resize(vert_dims[dir]);
-      midp_coords[dir].resize(cell_dims[dir]);
-      for (int i = 1; i <= vert_dims[dir]; ++i) vert_coords[dir][i - 1] = (n_offset[dir] + i - 1) * d[dir];
-      for (int i = 1; i <= cell_dims[dir]; ++i) midp_coords[dir][i - 1] = (n_offset[dir] + i - 0.5) * d[dir];
+      stretching[dir] = c.stretching[dir];
+      beta[dir] = c.beta[dir];
+      obtain_coordinates(dir);
+    }
+  }
+
+  // geo_t%obtain_coordinates, mesh_content.f90:142-253
+  void obtain_coordinates(int dir) {
+    const int nv = vert_dims[dir], nc = cell_dims[dir];
+    vert_coords[dir].assign(nv, 0); vert_ds[dir].assign(nv, 1); vert_ds2[dir].assign(nv, 1); vert_d2s[dir].assign(nv, 0);
+    midp_coords[dir].assign(nc, 0); midp_ds[dir].assign(nc, 1); midp_ds2[dir].assign(nc, 1); midp_d2s[dir].assign(nc, 0);
+    if (stretching[dir] == "uniform") {
+      stretched[dir] = false;
+      alpha[dir] = 0;
+      for (int i = 1; i <= nv; ++i) vert_coords[dir][i - 1] = (n_offset[dir] + i - 1) * d[dir];
+      for (int i = 1; i <= nc; ++i) midp_coords[dir][i - 1] = (n_offset[dir] + i - 0.5) * d[dir];
+      return;
+    }
+    stretched[dir] = true;
+    const std::string& st = stretching[dir];
+    if (st != "centred" && st != "top-bottom" && st != "bottom") fail("Invalid stretching type");
+    const double L_inf = L[dir] / 2, be = beta[dir];
+    if (be <= 2.220446049250313e-16) fail("Invalid beta in domain_settings");
+    const double al = std::fabs((L_inf - std::sqrt((pi * be) * (pi * be) + L_inf * L_inf)) / (2 * be * L_inf));
+    alpha[dir] = al;
+    const double r = std::sqrt((al * be + 1) / (al * be));
+    const double cst = std::sqrt(be) / (2 * std::sqrt(al) * std::sqrt(al * be + 1));
+    const double s = d[dir] / L[dir];
+    auto eta = [&](double idx) { return st == "centred" ? idx * s : (st == "top-bottom" ? idx * s - 0.5 : idx * s / 2 - 0.5); };
+    auto fill = [&](double y, double& coord, double& ds, double& ds2, double& d2s) {
+      const double sp = std::sin(pi * y), cp = std::cos(pi * y);
+      coord = cst * std::atan2(r * sp, cp) * (2 * al * be - std::cos(2 * pi * y) + 1) / (sp * sp + al * be) + pi * cst;
+      ds = L[dir] * (al / pi + sp * sp / (pi * be));
+      ds2 = ds * ds;
+      d2s = 2 * cp * sp / be;
+    };
+    for (int i = 1; i <= nv; ++i)
+      fill(eta((double)(i + n_offset[dir] - 1)), vert_coords[dir][i - 1], vert_ds[dir][i - 1], vert_ds2[dir][i - 1],
+           vert_d2s[dir][i - 1]);
+    for (int i = 1; i <= nc; ++i)
+      fill(eta(i + n_offset[dir] - 0.5), midp_coords[dir][i - 1], midp_ds[dir][i - 1], midp_ds2[dir][i - 1],
+           midp_d2s[dir][i - 1]);
+    if (st == "centred") {
+      for (auto& x : vert_coords[dir]) x -= L_inf;
+      for (auto& x : midp_coords[dir]) x -= L_inf;
+    } else if (st == "bottom") {
+      for (auto& x : vert_coords[dir]) x = 2 * x;
+      for (auto& x : vert_d2s[dir]) x = x / 2;
+      for (auto& x : midp_coords[dir]) x = 2 * x;
+      for (auto& x : midp_d2s[dir]) x = x / 2;
     }
   }
 
@@ -407,12 +457,16 @@ class Sim {
     const int bc_mp_start = bc_start == BC_DIRICHLET ? BC_NEUMANN : bc_start;
     const int bc_mp_end = bc_end == BC_DIRICHLET ? BC_NEUMANN : bc_end;
     const int n_vert = mesh.get_n(dir, VERT), n_cell = mesh.get_n(dir, CELL);
-    backend.alloc_tdsops(dp.der1st, n_vert, d, "first-deriv", cfg.der1st, bc_start, bc_end);
-    backend.alloc_tdsops(dp.der1st_sym, n_vert, d, "first-deriv", cfg.der1st, bc_start, bc_end, nullptr, nullptr, 4, "", true);
-    backend.alloc_tdsops(dp.der2nd, n_vert, d, "second-deriv", cfg.der2nd, bc_start, bc_end);
-    backend.alloc_tdsops(dp.der2nd_sym, n_vert, d, "second-deriv", cfg.der2nd, bc_start, bc_end, nullptr, nullptr, 4, "", true);
-    backend.alloc_tdsops(dp.stagder_v2p, n_cell, d, "stag-deriv", cfg.stagder, bc_mp_start, bc_mp_end, nullptr, nullptr, 4, "v2p");
-    backend.alloc_tdsops(dp.stagder_p2v, n_vert, d, "stag-deriv", cfg.stagder, bc_mp_start, bc_mp_end, nullptr, nullptr, 4, "p2v");
+    const double* vds = mesh.vert_ds[dir - 1].data();
+    const double* vds2 = mesh.vert_ds2[dir - 1].data();
+    const double* vd2s = mesh.vert_d2s[dir - 1].data();
+    const double* mds = mesh.midp_ds[dir - 1].data();
+    backend.alloc_tdsops(dp.der1st, n_vert, d, "first-deriv", cfg.der1st, bc_start, bc_end, vds);
+    backend.alloc_tdsops(dp.der1st_sym, n_vert, d, "first-deriv", cfg.der1st, bc_start, bc_end, vds, nullptr, 4, "", true);
+    backend.alloc_tdsops(dp.der2nd, n_vert, d, "second-deriv", cfg.der2nd, bc_start, bc_end, vds2, vd2s);
+    backend.alloc_tdsops(dp.der2nd_sym, n_vert, d, "second-deriv", cfg.der2nd, bc_start, bc_end, vds2, vd2s, 4, "", true);
+    backend.alloc_tdsops(dp.stagder_v2p, n_cell, d, "stag-deriv", cfg.stagder, bc_mp_start, bc_mp_end, mds, nullptr, 4, "v2p");
+    backend.alloc_tdsops(dp.stagder_p2v, n_vert, d, "stag-deriv", cfg.stagder, bc_mp_start, bc_mp_end, vds, nullptr, 4, "p2v");
     backend.alloc_tdsops(dp.interpl_v2p, n_cell, d, "interpolate", cfg.interpl, bc_mp_start, bc_mp_end, nullptr, nullptr, 4, "v2p");
     backend.alloc_tdsops(dp.interpl_p2v, n_vert, d, "interpolate", cfg.interpl, bc_mp_start, bc_mp_end, nullptr, nullptr, 4, "p2v");
   }

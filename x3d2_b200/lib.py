@@ -22,7 +22,7 @@ class X3D2HConfig(C.Structure):  # include/x3d2h.h: x3d2h_config
                 ("bc", C.c_int * 6), ("Re", C.c_double), ("dt", C.c_double), ("time_intg", C.c_char_p),
                 ("der1st_scheme", C.c_char_p), ("der2nd_scheme", C.c_char_p), ("interpl_scheme", C.c_char_p),
                 ("stagder_scheme", C.c_char_p), ("rank", C.c_int), ("nproc", C.c_int), ("device", C.c_int),
-                ("flags", C.c_int), ("nccl_unique_id", C.c_void_p)]
+                ("flags", C.c_int), ("nccl_unique_id", C.c_void_p), ("stretching", C.c_char_p * 3), ("beta", C.c_double * 3)]
 
 
 def build(verbose=False):
@@ -60,6 +60,7 @@ def load():
     cfgp = C.POINTER(X3D2HConfig)
     sig = dict(
         x3d2h_decompose=[cfgp, _ip],
+        x3d2h_geo=[cfgp, C.c_int] + [_dp] * 6,
         x3d2h_tdsops_tables=[C.c_int, C.c_double, C.c_char_p, C.c_char_p, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_char_p,
                              C.c_int, _ip] + [_dp] * 11,
         x3d2h_waves_000=[cfgp, _dp],
@@ -87,6 +88,7 @@ def load():
         x3d2h_scalar_product=[C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp],
         x3d2h_field_max_mean=[C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp],
         x3d2h_bench_op=[C.c_void_p, C.c_char_p, C.c_int],
+        x3d2h_fieldop=[C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp],
     )
     for name, args in sig.items():
         fn = getattr(h, name)
