@@ -79,12 +79,16 @@ def test_gloo_world2_exchange_patterns():
 
 
 @pytest.mark.gpu
-def test_two_gpus_vs_oracle():
+@pytest.mark.parametrize("nz,z_path", [(128, "m1 (reference order)"), (256, "m3 (fast path)")])
+def test_two_gpus_vs_oracle(nz, z_path):
+    """z-slabs on 2 GPUs against the oracle's 2-rank emulation: 64 planes per rank use the reference-order
+    DistD2 kernels with the 2x2 reduced systems, 128 planes per rank the distributed fast path (m3_edge.cu)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "mgpu_check.py"), "64", "64", "128", "2"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "mgpu_check.py"), "64", "64", str(nz), "2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, X3D2C_TRACE="1"))
     print(r.stdout[-4000:], r.stderr[-2000:])
     assert r.returncode == 0 and "MGPU_CHECK PASS" in r.stdout
+    assert f"transeq dir=3 ranks=2 -> {z_path}" in r.stderr and f"tds_solve dir=3 ranks=2 -> {z_path}" in r.stderr

@@ -72,7 +72,9 @@ int x3d2c_create(const x3d2c_config* cfg, x3d2c_ctx** out) {
   // 9 quantities x 4 buffers x 1 row, sized for the largest cross-section (omp/backend.f90:84-112)
   int ng = ctx->n_groups[1] > ctx->n_groups[2] ? ctx->n_groups[1] : ctx->n_groups[2];
   if (ctx->n_groups[3] > ng) ng = ctx->n_groups[3];
-  ctx->halo_doubles = (size_t)SZ * ng * (3 * 4 * 4 + 9 * 4 * 1);
+  // multi-rank contexts also hold the exchange buffers of the distributed fast path (m3_common.cuh: DistBufs)
+  const int halo_rows = ctx->cfg.nproc > 1 ? 4 * (3 * 4) + 4 * (9 * 5) : 3 * 4 * 4 + 9 * 4 * 1;
+  ctx->halo_doubles = (size_t)SZ * ng * halo_rows;
   X3D2C_CHECK_CUDA(cudaMalloc(&ctx->halo, sizeof(double) * ctx->halo_doubles));
   X3D2C_CHECK_CUDA(cudaMemsetAsync(ctx->halo, 0, sizeof(double) * ctx->halo_doubles, ctx->stream));
   ctx->red_blocks = 1184;  // 8 CTAs per SM on 148 SMs

@@ -1,0 +1,212 @@
+// Shared pieces of the "m3" fast-path kernels (tds_m3.cu, transeq_m3.cu, m3_edge.cu).
+//
+// Method (see tds_m3.cu for the derivation): the compact operators of a periodic, uniform direction are
+// Toeplitz, A = L U holds with the converged factors of the tdsops tables, and a line is cut into 16-point
+// segments that are swept independently; segments are coupled through carries (the end value ze of the local
+// forward sweep, the start value ys of the local backward sweep) that decay like (alpha fw)^16 per segment, so
+// only the DMAX = 3 nearest segments on either side contribute (< 1e-18 relative).
+//
+// Rank-split directions use the same decomposition ACROSS ranks: the carries of the DMAX segments next to a
+// rank boundary only depend on local data and the 4-row halo, so they are computed by a small edge kernel
+// (m3_edge.cu), exchanged once, and the main kernel then treats the neighbour's segments like its own. This
+// replaces the reference's 2x2 reduced systems (der_univ_dist / der_univ_subs, omp/kernels/distributed.f90:11-200)
+// for periodic uniform directions; the result is the same solution of the same global periodic system.
+#pragma once
+#include <cmath>
+
+#include "common.cuh"
+
+namespace m3 {
+
+constexpr int S = 16;         // points per segment
+constexpr int SP = S + 1;     // rows per segment in shared memory (the pad row removes bank conflicts)
+constexpr int LOG2S = 4;
+constexpr int DMAX = 3;       // neighbouring segments that contribute to a carry
+constexpr int HALO_ROWS = 8;  // rank-split lines: 4 rows before the line + 4 rows after, kept behind the segments
+constexpr int EXP_ROWS = 5;   // rows per recurrence in an exchange buffer (to next: ze of the last 3 segments;
+                              // to prev: ys of the first 3 segments, ze of the first 2)
+constexpr int EXT_ROWS = 2 * EXP_ROWS;  // shared-memory rows per recurrence: EXP_ROWS from prev + EXP_ROWS from next
+
+struct Op {
+  double cfw[9];            // scale * fw * coeffs
+  double a, cb;             // forward / backward propagators: a = -fw*alpha, cb = -bw
+  double zw[DMAX], yw[DMAX];
+  double om[2 * DMAX - 1];  // index m + DMAX - 1, m = d - d'
+  double W[S], Cp[S];
+  unsigned mask;
+};
+
+struct Geom {
+  int n, n_pad, nseg, tiles, field_doubles;  // field_doubles includes the halo rows of a rank-split line
+};
+
+extern __shared__ __align__(16) double smem[];
+
+template <unsigned M>
+__device__ __forceinline__ double sten(const double (&c)[9], const double (&w)[9]) {
+  double t = 0.0;
+  bool first = true;
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+    if (M & (1u << k)) {
+      t = first ? c[k] * w[k] : fma(c[k], w[k], t);
+      first = false;
+    }
+  return t;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// Tile copies. Global: (32 lanes, n_pad rows, G groups); shared: [segment][SP rows][L lanes].
+// A thread owns chunk c (2 lanes) of rows j_t, j_t + R, j_t + 2R, ... with R = blockDim / (L/2) a multiple of 16,
+// so both addresses advance by constants.
+template <int L>
+struct Copier {
+  int c2, g_off, j, rows_per_pass;
+  __device__ __forceinline__ Copier() {
+    constexpr int cpr = L / 2;
+    j = threadIdx.x / cpr;
+    c2 = 2 * (threadIdx.x - j * cpr);
+    rows_per_pass = blockDim.x / cpr;
+    g_off = j * SZ + c2;
+  }
+  __device__ __forceinline__ const double* tile_base(const double* g, const Geom& q, int tile) const {
+    constexpr int tpg = SZ / L;
+    const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
+    return g + (size_t)grp * q.n_pad * SZ + l0 + g_off;
+  }
+  __device__ __forceinline__ void load(double* sm, const double* g, const Geom& q, int tile) const {
+    const double* src = tile_base(g, q, tile);
+    for (int r = j; r < q.n; r += rows_per_pass) {
+      cp_async16(sm + (r + (r >> LOG2S)) * L + c2, src);
+      src += (size_t)rows_per_pass * SZ;
+    }
+  }
+  __device__ __forceinline__ void store(double* g, const double* sm, const Geom& q, int tile) const {
+    double* dst = const_cast<double*>(tile_base(g, q, tile));
+    for (int r0 = j; r0 < q.n; r0 += 4 * rows_per_pass) {  // four chunks in flight per thread
+      double2 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + i * rows_per_pass;
+        if (r < q.n) v[i] = *reinterpret_cast<const double2*>(sm + (r + (r >> LOG2S)) * L + c2);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + i * rows_per_pass;
+        if (r < q.n) __stcs(reinterpret_cast<double2*>(dst + (size_t)i * rows_per_pass * SZ), v[i]);
+      }
+      dst += (size_t)4 * rows_per_pass * SZ;
+    }
+  }
+  // nr dense rows of the tile's L lanes from a (SZ, rows_per_group, G) array into shared [nr][L]
+  __device__ __forceinline__ void load_rows(double* sm, const double* g, int rows_per_group, int nr, int tile) const {
+    constexpr int tpg = SZ / L, cpr = L / 2;
+    const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
+    const double* src = g + (size_t)grp * rows_per_group * SZ + l0;
+    for (int idx = threadIdx.x; idx < nr * cpr; idx += blockDim.x) {
+      const int r = idx / cpr, c = 2 * (idx - r * cpr);
+      cp_async16(sm + r * L + c, src + (size_t)r * SZ + c);
+    }
+  }
+};
+
+// Carries of one recurrence for segment q: zin (from the left), yin (from the right).
+// ze / ys: shared-memory offsets (lane applied) of the carries of segment 0, `stride` doubles between segments.
+// DIST: segments beyond the line ends belong to the neighbouring ranks; their carries were received into
+// extp (rows 0..2 = ze of prev's last three segments) and extn (rows 0..2 = ys of next's first three segments,
+// rows 3..4 = ze of next's first two), lane applied. Otherwise the line is periodic and segment indices wrap.
+template <int L, bool DIST>
+__device__ __forceinline__ void carries(const int ze, const int ys, const int stride, const int extp, const int extn,
+                                        const Op& o, const int q, const int nseg, double& zin, double& yin) {
+  double zv[2 * DMAX];  // ze(q - DMAX .. q + DMAX - 1)
+#pragma unroll
+  for (int t = 0; t < 2 * DMAX; ++t) {
+    int s = q - DMAX + t;
+    int a;
+    if (DIST) {
+      a = s < 0 ? extp + (s + DMAX) * L : (s >= nseg ? extn + (DMAX + s - nseg) * L : ze + s * stride);
+    } else {
+      if (s < 0) s += nseg;
+      if (s >= nseg) s -= nseg;
+      a = ze + s * stride;
+    }
+    zv[t] = smem[a];
+  }
+  zin = 0.0;
+#pragma unroll
+  for (int d = 1; d <= DMAX; ++d) zin = fma(o.zw[d - 1], zv[DMAX - d], zin);
+  yin = 0.0;
+#pragma unroll
+  for (int d = 1; d <= DMAX; ++d) {
+    int s = q + d;
+    int a;
+    if (DIST) {
+      a = s >= nseg ? extn + (s - nseg) * L : ys + s * stride;
+    } else {
+      if (s >= nseg) s -= nseg;
+      a = ys + s * stride;
+    }
+    yin = fma(o.yw[d - 1], smem[a], yin);
+  }
+#pragma unroll
+  for (int m = -(DMAX - 1); m <= DMAX - 1; ++m) yin = fma(o.om[m + DMAX - 1], zv[DMAX + m], yin);
+}
+
+// window element t (row j0 - 4 + t, t = 0..S+7) given the bases of the previous, own and next segment
+template <int L>
+__device__ __forceinline__ int woff(int t, int bm, int b0, int bp) {
+  return t < 4 ? bm + (S - 4 + t) * L : (t < S + 4 ? b0 + (t - 4) * L : bp + (t - S - 4) * L);
+}
+
+// segment bases of thread (lane l, segment q). Rank-split lines read the rows before / after the line from the
+// halo rows stored behind the last segment (4 "before" rows, then 4 "after" rows).
+template <int L, bool DIST>
+__device__ __forceinline__ void segment_bases(int q, int l, int nseg, int& bm, int& b0, int& bp) {
+  const int qm = q == 0 ? nseg - 1 : q - 1, qp = q == nseg - 1 ? 0 : q + 1;
+  bm = qm * SP * L + l;
+  b0 = q * SP * L + l;
+  bp = qp * SP * L + l;
+  if (DIST) {
+    const int h = nseg * SP * L + l;
+    if (q == 0) bm = h - (S - 4) * L;
+    if (q == nseg - 1) bp = h + 4 * L;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+bool make_op(const x3d2c_tdsops* t, double scale, bool dist, Op* o);
+bool same_tables(const x3d2c_tdsops* a, const x3d2c_tdsops* b);
+int num_sms(const x3d2c_ctx* ctx);
+
+// Exchange buffers of a rank-split direction, carved from ctx->halo. Layouts:
+//   halo_*:  (SZ, 4 rows, nf fields, G)      carr_*: (SZ, EXP_ROWS, ns recurrences, G)
+struct DistBufs {
+  double *halo_send_s, *halo_send_e, *halo_recv_s, *halo_recv_e;
+  double *carr_to_prev, *carr_to_next, *carr_from_prev, *carr_from_next;
+};
+constexpr int kDistRows = 4 * (3 * 4) + 4 * (9 * EXP_ROWS);  // rows of SZ*G doubles that DistBufs needs
+DistBufs carve_dist(x3d2c_ctx* ctx);
+bool dist_supported(const x3d2c_ctx* ctx, int dir, int n);
+
+// One recurrence of the edge kernel: input f (times c when c != nullptr), operator ops[op].
+struct EdgeParams {
+  int n, n_pad, nseg, G, ns, nf;
+  const double* f[9];
+  const double* c[9];
+  int ff[9], cf[9];  // halo field slots of f and c
+  int op[9];
+  Op ops[3];
+  const double *halo_s, *halo_e;  // received halos (SZ, 4, nf, G)
+  double *to_prev, *to_next;      // (SZ, EXP_ROWS, ns, G)
+};
+// packs the halos of nf fields, exchanges them, computes and exchanges the boundary carries
+int exchange_edges(x3d2c_ctx* ctx, int dir, const double* const* fields, int nf, EdgeParams& ep, const DistBufs& b);
+
+}  // namespace m3

@@ -387,6 +387,13 @@ HaloBufs carve(x3d2c_ctx* ctx) {
   h.row = row;
   return h;
 }
+
+// X3D2C_TRACE=1: report on stderr which kernel family serves each call (used by tools/mgpu_check.py)
+void trace_path(const char* op, int dir, int P, bool fast) {
+  static int on = -1;
+  if (on < 0) on = std::getenv("X3D2C_TRACE") ? 1 : 0;
+  if (on) std::fprintf(stderr, "[x3d2c] %s dir=%d ranks=%d -> %s\n", op, dir, P, fast ? "m3 (fast path)" : "m1 (reference order)");
+}
 }  // namespace
 
 extern "C" {
@@ -398,8 +405,9 @@ int x3d2c_tds_solve(x3d2c_ctx* ctx, int dir, double* du, const double* u, const 
   const int n_pad = ctx->n_pad(dir), G = ctx->n_groups[dir];
   X3D2C_REQUIRE(ops->n_rhs <= n_pad, "x3d2c_tds_solve: operator longer than the padded line");
   const int P = ctx->cfg.nproc_dir[dir - 1];
-  if (P == 1 && !ctx->strict) {
+  if (!ctx->strict) {  // fast path: periodic uniform directions, single-rank or rank-split
     int rc = tds_solve_m3(ctx, dir, du, u, ops);
+    trace_path("tds_solve", dir, P, rc != X3D2C_EUNSUPPORTED);
     if (rc != X3D2C_EUNSUPPORTED) return rc;
   }
   const dim3 block(128), grid((G + 3) / 4);
@@ -449,8 +457,9 @@ int x3d2c_transeq(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, c
                     der1st->n_tds == der2nd->n_tds && der1st_sym->n_tds == der1st->n_tds &&
                     der2nd_sym->n_tds == der1st->n_tds, "x3d2c_transeq: operators must share n_tds == n_rhs");
   const int P = ctx->cfg.nproc_dir[dir - 1];
-  if (P == 1 && !ctx->strict) {
+  if (!ctx->strict) {
     int rc = transeq_m3(ctx, dir, du, dv, dw, u, v, w, nu, der1st, der1st_sym, der2nd, der2nd_sym);
+    trace_path("transeq", dir, P, rc != X3D2C_EUNSUPPORTED);
     if (rc != X3D2C_EUNSUPPORTED) return rc;
   }
   // argument permutation of omp/backend.f90:154,168,182: component 0 is the line-aligned velocity
