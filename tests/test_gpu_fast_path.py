@@ -49,3 +49,29 @@ def test_tgv_256_one_step(oracle, x3d2):
     scale = max(np.abs(y).max() for y in b)
     assert max(np.abs(x - y).max() for x, y in zip(a, b)) / scale < TOL
     sim.close()
+
+
+@pytest.mark.parametrize("dims", [(96, 128, 112), (512, 96, 256)])
+def test_rank_split_kernels_on_one_gpu(oracle, x3d2, dims, monkeypatch):
+    """The rank-split variant of the fast path (halo rows + neighbour carries from m3_edge.cu) with the rank acting
+    as its own periodic neighbour (X3D2C_FORCE_DIST): same answers as the oracle, plus a TGV step."""
+    monkeypatch.setenv("X3D2C_FORCE_DIST", "1")
+    sim, ref = x3d2.Sim(dims), oracle.World(dims)
+    monkeypatch.delenv("X3D2C_FORCE_DIST")
+    plain = x3d2.Sim(dims)
+    u, v, w = rnd(sim.shape(), 4), rnd(sim.shape(), 5), rnd(sim.shape(), 6)
+    worst = 0.0
+    for d in (1, 2, 3):
+        for op in ("der1st", "der2nd", "stagder_v2p", "interpl_v2p"):
+            worst = max(worst, rel(sim.tds_solve(d, op, u), ref.tds_solve(d, op, u)))
+        for op in ("stagder_p2v", "interpl_p2v"):
+            worst = max(worst, rel(sim.tds_solve(d, op, u, 1110), ref.tds_solve(d, op, u, 1110)))
+        got, exp, one = sim.transeq_dir(d, u, v, w), ref.transeq_dir(d, u, v, w), plain.transeq_dir(d, u, v, w)
+        for g, e, o in zip(got, exp, one):
+            worst = max(worst, rel(g, e))
+            assert rel(g, o) < 1e-13  # same segments, same carries: only the edge kernel's rounding may differ
+    assert sim.launch_count() > plain.launch_count()  # pack + edge kernels + exchanges were really used
+    print(dims, "worst rank-split rel err", worst)
+    assert worst < TOL
+    sim.close()
+    plain.close()

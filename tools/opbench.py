@@ -1,6 +1,8 @@
 """Per-operator device timing (CUDA events on the backend's stream) against the algorithmic bytes of SURVEY.md §8d.
 
-usage: python tools/opbench.py [N] [--strict]
+usage: python tools/opbench.py [N] [--strict] [--ops=transeq_z,poisson,...]
+       python -m torch.distributed.run --nnodes=1 --nproc-per-node P --master-addr 127.0.0.1 tools/opbench.py [N]
+           (P ranks, z-slabs of N^3 points each: the z operators run the rank-split kernels + NCCL exchanges)
 """
 import json
 import os
@@ -37,18 +39,38 @@ def main():
         peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    sim = X.Sim((n, n, n), strict=strict)
+    world, rank = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0))
+    if world > 1:
+        import ctypes
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", 0))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        buf = [None]
+        if rank == 0:
+            raw = ctypes.create_string_buffer(128)
+            assert X.load()[0].x3d2c_nccl_unique_id(raw) == 0
+            buf = [raw.raw]
+        dist.broadcast_object_list(buf, src=0)
+        sim = X.Sim((n, n, n * world), nproc_dir=(1, 1, world), rank=rank, nproc=world, device=local, strict=strict,
+                    nccl_unique_id=buf[0])
+    else:
+        sim = X.Sim((n, n, n), strict=strict)
     sim.init_tgv()
     stream = torch.cuda.ExternalStream(sim.stream())
     npts = n ** 3
     rows = []
+    only = [a.split("=", 1)[1].split(",") for a in sys.argv if a.startswith("--ops=")]
     for op, b in BYTES_PER_PT.items():
+        if only and op not in only[0]:
+            continue
         ms = time_op(sim, op, 5, stream)
         gbs = b * npts / ms / 1e6
         rows.append((op, ms, gbs, gbs / peak))
-        print(f"{op:22s} {ms:9.3f} ms  {gbs:9.1f} GB/s  {100 * gbs / peak:6.1f}% of measured {peak:.0f} GB/s", flush=True)
-    t0 = time_op(sim, "transeq", 3, stream) + time_op(sim, "pressure_correction", 3, stream)
-    print(f"N={n} strict={strict}")
+        if rank == 0:
+            print(f"{op:22s} {ms:9.3f} ms  {gbs:9.1f} GB/s  {100 * gbs / peak:6.1f}% of measured {peak:.0f} GB/s", flush=True)
+    if rank == 0:
+        print(f"N={n} per rank, ranks={world}, strict={strict}")
     sim.close()
 
 

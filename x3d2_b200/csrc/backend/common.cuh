@@ -88,6 +88,7 @@ struct x3d2c_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   int strict = 0;
+  int force_dist = 0;  // X3D2C_FORCE_DIST: run the rank-split fast path on a single rank (self exchange); tests, profiling
   int nx_pad = 0, ny_pad = 0, nz_pad = 0;
   int n_groups[4] = {0, 0, 0, 0};  // [dir]
   long long ngrid = 0;

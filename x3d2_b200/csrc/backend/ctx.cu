@@ -59,6 +59,7 @@ int x3d2c_create(const x3d2c_config* cfg, x3d2c_ctx** out) {
   X3D2C_CHECK_CUDA(cudaGetDevice(&ctx->device));
   X3D2C_CHECK_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->strict = (cfg->flags & X3D2C_FLAG_STRICT) ? 1 : 0;
+  ctx->force_dist = std::getenv("X3D2C_FORCE_DIST") ? 1 : 0;
   // src/allocator.f90:72-83
   const int nx = cfg->dims_vert[0], ny = cfg->dims_vert[1], nz = cfg->dims_vert[2];
   ctx->nx_pad = nx - 1 + (-(nx - 1)) % SZ + SZ;
@@ -73,7 +74,7 @@ int x3d2c_create(const x3d2c_config* cfg, x3d2c_ctx** out) {
   int ng = ctx->n_groups[1] > ctx->n_groups[2] ? ctx->n_groups[1] : ctx->n_groups[2];
   if (ctx->n_groups[3] > ng) ng = ctx->n_groups[3];
   // multi-rank contexts also hold the exchange buffers of the distributed fast path (m3_common.cuh: DistBufs)
-  const int halo_rows = ctx->cfg.nproc > 1 ? 4 * (3 * 4) + 4 * (9 * 5) : 3 * 4 * 4 + 9 * 4 * 1;
+  const int halo_rows = (ctx->cfg.nproc > 1 || ctx->force_dist) ? 4 * (3 * 4) + 4 * (9 * 3) : 3 * 4 * 4 + 9 * 4 * 1;  // m3::kDistRows
   ctx->halo_doubles = (size_t)SZ * ng * halo_rows;
   X3D2C_CHECK_CUDA(cudaMalloc(&ctx->halo, sizeof(double) * ctx->halo_doubles));
   X3D2C_CHECK_CUDA(cudaMemsetAsync(ctx->halo, 0, sizeof(double) * ctx->halo_doubles, ctx->stream));

@@ -23,8 +23,8 @@ constexpr int SP = S + 1;     // rows per segment in shared memory (the pad row 
 constexpr int LOG2S = 4;
 constexpr int DMAX = 3;       // neighbouring segments that contribute to a carry
 constexpr int HALO_ROWS = 8;  // rank-split lines: 4 rows before the line + 4 rows after, kept behind the segments
-constexpr int EXP_ROWS = 5;   // rows per recurrence in an exchange buffer (to next: ze of the last 3 segments;
-                              // to prev: ys of the first 3 segments, ze of the first 2)
+constexpr int EXP_ROWS = DMAX;  // rows per recurrence in an exchange buffer: to next, ze of the last 3 segments;
+                                // to prev, what this rank's first segments add to yin of prev's last 3 segments
 constexpr int EXT_ROWS = 2 * EXP_ROWS;  // shared-memory rows per recurrence: EXP_ROWS from prev + EXP_ROWS from next
 
 struct Op {
@@ -105,23 +105,41 @@ struct Copier {
       dst += (size_t)4 * rows_per_pass * SZ;
     }
   }
-  // nr dense rows of the tile's L lanes from a (SZ, rows_per_group, G) array into shared [nr][L]
-  __device__ __forceinline__ void load_rows(double* sm, const double* g, int rows_per_group, int nr, int tile) const {
+  // Neighbour data of a rank-split tile: nr rows of the tile's L lanes from each of two (SZ, nr, G) arrays into
+  // shared [2 nr][L] (g0's rows first).
+  __device__ __forceinline__ void load_rows2(double* sm, const double* g0, const double* g1, int nr, int tile) const {
     constexpr int tpg = SZ / L, cpr = L / 2;
     const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
-    const double* src = g + (size_t)grp * rows_per_group * SZ + l0;
-    for (int idx = threadIdx.x; idx < nr * cpr; idx += blockDim.x) {
-      const int r = idx / cpr, c = 2 * (idx - r * cpr);
-      cp_async16(sm + r * L + c, src + (size_t)r * SZ + c);
+    const size_t go = (size_t)grp * nr * SZ + l0;
+    for (int idx = threadIdx.x; idx < 2 * nr * cpr; idx += blockDim.x) {
+      const int row = idx / cpr, c = 2 * (idx - row * cpr);
+      const bool second = row >= nr;
+      const double* src = (second ? g1 : g0) + go + (size_t)(second ? row - nr : row) * SZ + c;
+      cp_async16(sm + row * L + c, src);
+    }
+  }
+  // Halo rows of three fields: (SZ, 4, 3, G) arrays hs (rows before the line) and he (rows after) into the 8 halo
+  // rows behind the segments of each field tile (field stride fd, halo offset hoff).
+  __device__ __forceinline__ void load_halos3(double* sm, int fd, int hoff, const double* hs, const double* he,
+                                              int tile) const {
+    constexpr int tpg = SZ / L, cpr = L / 2;
+    const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
+    const size_t go = (size_t)grp * 12 * SZ + l0;
+    for (int idx = threadIdx.x; idx < 24 * cpr; idx += blockDim.x) {
+      const int row = idx / cpr, c = 2 * (idx - row * cpr);
+      const int f = row >> 3, r = row & 3;
+      const double* src = ((row & 4) ? he : hs) + go + (size_t)(f * 4 + r) * SZ + c;
+      cp_async16(sm + f * fd + hoff + (row & 7) * L + c, src);
     }
   }
 };
 
 // Carries of one recurrence for segment q: zin (from the left), yin (from the right).
 // ze / ys: shared-memory offsets (lane applied) of the carries of segment 0, `stride` doubles between segments.
-// DIST: segments beyond the line ends belong to the neighbouring ranks; their carries were received into
-// extp (rows 0..2 = ze of prev's last three segments) and extn (rows 0..2 = ys of next's first three segments,
-// rows 3..4 = ze of next's first two), lane applied. Otherwise the line is periodic and segment indices wrap.
+// DIST: segments beyond the line ends belong to the neighbouring ranks: extp rows 0..2 hold ze of prev's last three
+// segments, extn rows 0..2 hold the sum of all terms that next's first segments contribute to yin of this rank's
+// last three segments (computed by next's edge kernel), lane applied. Otherwise the line is periodic and segment
+// indices wrap.
 template <int L, bool DIST>
 __device__ __forceinline__ void carries(const int ze, const int ys, const int stride, const int extp, const int extn,
                                         const Op& o, const int q, const int nseg, double& zin, double& yin) {
@@ -129,31 +147,37 @@ __device__ __forceinline__ void carries(const int ze, const int ys, const int st
 #pragma unroll
   for (int t = 0; t < 2 * DMAX; ++t) {
     int s = q - DMAX + t;
-    int a;
     if (DIST) {
-      a = s < 0 ? extp + (s + DMAX) * L : (s >= nseg ? extn + (DMAX + s - nseg) * L : ze + s * stride);
+      const bool beyond = s >= nseg;
+      const int a = s < 0 ? extp + (s + DMAX) * L : ze + (beyond ? 0 : s) * stride;
+      zv[t] = smem[a];
+      if (beyond) zv[t] = 0.0;
     } else {
       if (s < 0) s += nseg;
       if (s >= nseg) s -= nseg;
-      a = ze + s * stride;
+      zv[t] = smem[ze + s * stride];
     }
-    zv[t] = smem[a];
   }
   zin = 0.0;
 #pragma unroll
   for (int d = 1; d <= DMAX; ++d) zin = fma(o.zw[d - 1], zv[DMAX - d], zin);
   yin = 0.0;
+  if (DIST) {
+    const int r = q - (nseg - DMAX);
+    if (r >= 0) yin = smem[extn + r * L];
+  }
 #pragma unroll
   for (int d = 1; d <= DMAX; ++d) {
     int s = q + d;
-    int a;
     if (DIST) {
-      a = s >= nseg ? extn + (s - nseg) * L : ys + s * stride;
+      const bool beyond = s >= nseg;
+      double v = smem[ys + (beyond ? 0 : s) * stride];
+      if (beyond) v = 0.0;
+      yin = fma(o.yw[d - 1], v, yin);
     } else {
       if (s >= nseg) s -= nseg;
-      a = ys + s * stride;
+      yin = fma(o.yw[d - 1], smem[ys + s * stride], yin);
     }
-    yin = fma(o.yw[d - 1], smem[a], yin);
   }
 #pragma unroll
   for (int m = -(DMAX - 1); m <= DMAX - 1; ++m) yin = fma(o.om[m + DMAX - 1], zv[DMAX + m], yin);
@@ -195,13 +219,11 @@ constexpr int kDistRows = 4 * (3 * 4) + 4 * (9 * EXP_ROWS);  // rows of SZ*G dou
 DistBufs carve_dist(x3d2c_ctx* ctx);
 bool dist_supported(const x3d2c_ctx* ctx, int dir, int n);
 
-// One recurrence of the edge kernel: input f (times c when c != nullptr), operator ops[op].
+// Edge kernel input: nf fields; per field either one recurrence (ops[0] on f: tds_solve, ns = nf) or three
+// (ops[0] on f, ops[1] on f * f[0], ops[2] on f: transeq, ns = 3 nf). Recurrence index = field * (ns / nf) + k.
 struct EdgeParams {
   int n, n_pad, nseg, G, ns, nf;
-  const double* f[9];
-  const double* c[9];
-  int ff[9], cf[9];  // halo field slots of f and c
-  int op[9];
+  const double* f[3];
   Op ops[3];
   const double *halo_s, *halo_e;  // received halos (SZ, 4, nf, G)
   double *to_prev, *to_next;      // (SZ, EXP_ROWS, ns, G)

@@ -33,56 +33,74 @@ __global__ void __launch_bounds__(128) halo_pack_kernel(double* __restrict__ sen
   send_e[o] = ug[(size_t)(p.n - 4 + row) * SZ];
 }
 
-// One thread per (lane, edge segment): segments 0..2 and nseg-3..nseg-1 of every line; blockIdx.y = recurrence.
+// One thread per (lane, edge segment): segments 0..2 and nseg-3..nseg-1 of every line; blockIdx.y = field.
+// NR recurrences per field: 1 (tds_solve: ops[0] on f) or 3 (transeq: ops[0] on f, ops[1] on f*c, ops[2] on f).
+// The 24-row window is loaded up front (rows outside the line come from the received halos), then swept.
+template <int NR>
 __global__ void __launch_bounds__(32 * 2 * DMAX) edge_kernel(const __grid_constant__ EdgeParams p) {
-  const int lane = threadIdx.x, e = threadIdx.y, g = blockIdx.x, s = blockIdx.y;
+  const int lane = threadIdx.x, e = threadIdx.y, g = blockIdx.x, fi = blockIdx.y;
   const int q = e < DMAX ? e : p.nseg - 2 * DMAX + e;
   const int j0 = q * S;
-  const Op& o = p.ops[p.op[s]];
   const size_t base = (size_t)g * p.n_pad * SZ + lane;
-  const double* f = p.f[s] + base;
-  const double* c = p.c[s] ? p.c[s] + base : nullptr;
-  const size_t hf = ((size_t)g * p.nf + p.ff[s]) * 4 * SZ + lane, hc = ((size_t)g * p.nf + p.cf[s]) * 4 * SZ + lane;
-  auto val = [&](int row) -> double {
-    double v;
-    if (row < 0) {
-      v = p.halo_s[hf + (size_t)(row + 4) * SZ];
-      if (c) v *= p.halo_s[hc + (size_t)(row + 4) * SZ];
-    } else if (row >= p.n) {
-      v = p.halo_e[hf + (size_t)(row - p.n) * SZ];
-      if (c) v *= p.halo_e[hc + (size_t)(row - p.n) * SZ];
+  const size_t hf = ((size_t)g * p.nf + fi) * 4 * SZ + lane, hc = (size_t)g * p.nf * 4 * SZ + lane;
+  const double* f = p.f[fi] + base + (size_t)j0 * SZ;
+  const double* c = p.f[0] + base + (size_t)j0 * SZ;
+  double w[S + 8], wc[S + 8];
+#pragma unroll
+  for (int t = 0; t < S + 8; ++t) {
+    const int r = t - 4;  // row relative to j0
+    const double *pf, *pc;
+    if (t < 4 && e == 0) { pf = p.halo_s + hf + (size_t)t * SZ; pc = p.halo_s + hc + (size_t)t * SZ; }
+    else if (t >= S + 4 && e == 2 * DMAX - 1) { pf = p.halo_e + hf + (size_t)(t - S - 4) * SZ; pc = p.halo_e + hc + (size_t)(t - S - 4) * SZ; }
+    else { pf = f + (ptrdiff_t)r * SZ; pc = c + (ptrdiff_t)r * SZ; }
+    w[t] = *pf;
+    if (NR == 3) wc[t] = *pc;
+  }
+  if (NR == 3) {
+#pragma unroll
+    for (int t = 0; t < S + 8; ++t) wc[t] *= w[t];
+  }
+  __shared__ double sh[NR][2 * DMAX - 1][32];  // ys(0..2), ze(0..1) of the first segments
+#pragma unroll
+  for (int k = 0; k < NR; ++k) {
+    const Op& o = p.ops[k];
+    const double* src = (NR == 3 && k == 1) ? wc : w;
+    double z[S], pz = 0.0;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      double win[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) win[t] = src[i + t];
+      pz = fma(o.a, pz, sten<0x1FFu>(o.cfw, win));
+      z[i] = pz;
+    }
+    if (e >= DMAX) {  // ze of the last three segments, for the next rank
+      p.to_next[(((size_t)g * p.ns + fi * NR + k) * EXP_ROWS + (e - DMAX)) * SZ + lane] = z[S - 1];
     } else {
-      v = f[(size_t)row * SZ];
-      if (c) v *= c[(size_t)row * SZ];
+      if (e < DMAX - 1) sh[k][DMAX + e][lane] = z[S - 1];
+      double y = 0.0;
+#pragma unroll
+      for (int i = S - 1; i >= 0; --i) y = fma(o.cb, y, z[i]);
+      sh[k][e][lane] = y;
     }
-    return v;
-  };
-  double wf[9], z[S];
-#pragma unroll
-  for (int t = 0; t < 8; ++t) wf[t] = val(j0 - 4 + t);
-  double pz = 0.0;
-#pragma unroll
-  for (int k = 0; k < S; ++k) {
-    wf[8] = val(j0 + 4 + k);
-    pz = fma(o.a, pz, sten<0x1FFu>(o.cfw, wf));
-    z[k] = pz;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) wf[t] = wf[t + 1];
   }
-  const size_t ob = (((size_t)g * p.ns + s) * EXP_ROWS) * SZ + lane;
-  if (e >= DMAX) {  // ze of the last three segments, for the next rank
-    p.to_next[ob + (size_t)(e - DMAX) * SZ] = z[S - 1];
-    if (e == DMAX) {  // unused rows of the equally sized buffer
-      p.to_next[ob + (size_t)3 * SZ] = 0.0;
-      p.to_next[ob + (size_t)4 * SZ] = 0.0;
+  __syncthreads();
+  if (e < DMAX) {
+    // What this rank's first segments add to yin of the previous rank's segment nseg' - 3 + e (carries() in
+    // m3_common.cuh with q + d >= nseg', q + m >= nseg'): sum_{d >= 3-e} yw[d-1] ys(e+d-3) + sum_{m >= 3-e} om[m+2] ze(e+m-3)
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      const Op& o = p.ops[k];
+      double acc = 0.0;
+#pragma unroll
+      for (int d = 1; d <= DMAX; ++d)
+        if (e + d - DMAX >= 0) acc = fma(o.yw[d - 1], sh[k][e + d - DMAX][lane], acc);
+#pragma unroll
+      for (int m = 1; m <= DMAX - 1; ++m)
+        if (e + m - DMAX >= 0) acc = fma(o.om[m + DMAX - 1], sh[k][DMAX + e + m - DMAX][lane], acc);
+      p.to_prev[(((size_t)g * p.ns + fi * NR + k) * EXP_ROWS + e) * SZ + lane] = acc;
     }
-    return;
   }
-  if (e < DMAX - 1) p.to_prev[ob + (size_t)(DMAX + e) * SZ] = z[S - 1];  // ze of the first two segments
-  double y = 0.0;
-#pragma unroll
-  for (int k = S - 1; k >= 0; --k) y = fma(o.cb, y, z[k]);
-  p.to_prev[ob + (size_t)e * SZ] = y;  // ys of the first three segments
 }
 
 }  // namespace
@@ -134,8 +152,8 @@ int num_sms(const x3d2c_ctx* ctx) {
 // every rank must take the same decision: equal split of a periodic direction, enough segments per rank
 bool dist_supported(const x3d2c_ctx* ctx, int dir, int n) {
   const int d = dir - 1, P = ctx->cfg.nproc_dir[d];
-  if (P <= 1 || !ctx->cfg.periodic[d] || ctx->strict) return false;
-  if (!ctx->nccl_comm) return false;
+  if ((P <= 1 && !ctx->force_dist) || !ctx->cfg.periodic[d] || ctx->strict) return false;
+  if (P > 1 && !ctx->nccl_comm) return false;
   if (ctx->cfg.dims_vert_global[d] != n * P || ctx->cfg.dims_vert[d] != n) return false;
   return n % S == 0 && n >= 2 * DMAX * S;
 }
@@ -159,6 +177,13 @@ DistBufs carve_dist(x3d2c_ctx* ctx) {
 
 int exchange_edges(x3d2c_ctx* ctx, int dir, const double* const* fields, int nf, EdgeParams& ep, const DistBufs& b) {
   const int G = ctx->n_groups[dir];
+  // X3D2C_TRACE_TIMES=1: device time of the four phases on stderr (debugging aid; synchronises)
+  static const bool timing = std::getenv("X3D2C_TRACE_TIMES") != nullptr;
+  cudaEvent_t ev[5];
+  auto mark = [&](int i) {
+    if (timing) { if (i == 0) for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[i], ctx->stream); }
+  };
+  mark(0);
   PackParams pp;
   for (int f = 0; f < 3; ++f) pp.f[f] = fields[f < nf ? f : 0];
   pp.n = ep.n;
@@ -166,19 +191,35 @@ int exchange_edges(x3d2c_ctx* ctx, int dir, const double* const* fields, int nf,
   pp.nf = nf;
   halo_pack_kernel<<<dim3(G, nf), 128, 0, ctx->stream>>>(b.halo_send_s, b.halo_send_e, pp);
   X3D2C_CHECK_LAUNCH(ctx);
+  mark(1);
   int rc = x3d2c::sendrecv_fields(ctx, dir, b.halo_recv_s, b.halo_recv_e, b.halo_send_s, b.halo_send_e,
                                   (size_t)SZ * 4 * nf * G);
   if (rc) return rc;
+  mark(2);
   ep.G = G;
   ep.nf = nf;
   ep.halo_s = b.halo_recv_s;
   ep.halo_e = b.halo_recv_e;
   ep.to_prev = b.carr_to_prev;
   ep.to_next = b.carr_to_next;
-  edge_kernel<<<dim3(G, ep.ns), dim3(32, 2 * DMAX), 0, ctx->stream>>>(ep);
+  if (ep.ns == nf)
+    edge_kernel<1><<<dim3(G, nf), dim3(32, 2 * DMAX), 0, ctx->stream>>>(ep);
+  else
+    edge_kernel<3><<<dim3(G, nf), dim3(32, 2 * DMAX), 0, ctx->stream>>>(ep);
   X3D2C_CHECK_LAUNCH(ctx);
-  return x3d2c::sendrecv_fields(ctx, dir, b.carr_from_prev, b.carr_from_next, b.carr_to_prev, b.carr_to_next,
-                                (size_t)SZ * EXP_ROWS * ep.ns * G);
+  mark(3);
+  rc = x3d2c::sendrecv_fields(ctx, dir, b.carr_from_prev, b.carr_from_next, b.carr_to_prev, b.carr_to_next,
+                              (size_t)SZ * EXP_ROWS * ep.ns * G);
+  mark(4);
+  if (timing) {
+    cudaEventSynchronize(ev[4]);
+    float t[4];
+    for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
+    std::fprintf(stderr, "[x3d2c] rank %d edges dir=%d ns=%d: pack %.3f ms, halo exchange %.3f, edge kernel %.3f, "
+                 "carry exchange %.3f\n", ctx->cfg.rank, dir, ep.ns, t[0], t[1], t[2], t[3]);
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
+  return rc;
 }
 
 }  // namespace m3

@@ -49,11 +49,8 @@ __global__ void __launch_bounds__(256, 3) tds_m3_kernel(const __grid_constant__ 
   auto load_tile = [&](int buf, int tile) {
     cp.load(smem + buf * fd, p.in, g, tile);
     if (DIST) {
-      cp.load_rows(smem + buf * fd + nseg * SP * L, p.halo_s, 4, 4, tile);
-      cp.load_rows(smem + buf * fd + nseg * SP * L + 4 * L, p.halo_e, 4, 4, tile);
-      cp.load_rows(smem + 2 * fd + 2 * nseg * L + buf * EXT_ROWS * L, p.from_prev, EXP_ROWS, EXP_ROWS, tile);
-      cp.load_rows(smem + 2 * fd + 2 * nseg * L + buf * EXT_ROWS * L + EXP_ROWS * L, p.from_next, EXP_ROWS, EXP_ROWS,
-                   tile);
+      cp.load_rows2(smem + buf * fd + nseg * SP * L, p.halo_s, p.halo_e, 4, tile);
+      cp.load_rows2(smem + 2 * fd + 2 * nseg * L + buf * EXT_ROWS * L, p.from_prev, p.from_next, EXP_ROWS, tile);
     }
   };
   int it = 0;
@@ -165,7 +162,7 @@ namespace x3d2c {
 
 int tds_solve_m3(x3d2c_ctx* ctx, int dir, double* du, const double* u, const x3d2c_tdsops* ops) {
   const int n = ops->n_tds;
-  const bool split = ctx->cfg.nproc_dir[dir - 1] > 1;
+  const bool split = ctx->cfg.nproc_dir[dir - 1] > 1 || ctx->force_dist;
   if (split && !dist_supported(ctx, dir, n)) return X3D2C_EUNSUPPORTED;
   TdsParams p{};
   if (!make_op(ops, 1.0, split, &p.o)) return X3D2C_EUNSUPPORTED;
@@ -194,7 +191,6 @@ int tds_solve_m3(x3d2c_ctx* ctx, int dir, double* du, const double* u, const x3d
   ep.nseg = p.g.nseg;
   ep.ns = 1;
   ep.f[0] = u;
-  ep.c[0] = nullptr;
   ep.ops[0] = p.o;
   const double* fields[1] = {u};
   int rc = exchange_edges(ctx, dir, fields, 1, ep, b);

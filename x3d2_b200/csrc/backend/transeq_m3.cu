@@ -120,15 +120,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) transeq_m3_kernel(const __grid
 #pragma unroll
     for (int f = 0; f < 3; ++f) cp.load(smem + (3 * buf + f) * fd, p.in[f], g, tile);
     if (DIST) {
-#pragma unroll
-      for (int f = 0; f < 3; ++f) {
-        double* h = smem + (3 * buf + f) * fd + g.nseg * SP * L;
-        cp.load_rows(h, p.halo_s + (size_t)f * 4 * SZ, 12, 4, tile);
-        cp.load_rows(h + 4 * L, p.halo_e + (size_t)f * 4 * SZ, 12, 4, tile);
-      }
-      double* x = smem + 6 * fd + buf * xbuf;
-      cp.load_rows(x, p.from_prev, NS * EXP_ROWS, NS * EXP_ROWS, tile);
-      cp.load_rows(x + NS * EXP_ROWS * L, p.from_next, NS * EXP_ROWS, NS * EXP_ROWS, tile);
+      cp.load_halos3(smem + 3 * buf * fd, fd, g.nseg * SP * L, p.halo_s, p.halo_e, tile);
+      cp.load_rows2(smem + 6 * fd + buf * xbuf, p.from_prev, p.from_next, NS * EXP_ROWS, tile);
     }
   };
   int it = 0;
@@ -212,7 +205,7 @@ int transeq_m3(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, cons
   // periodic operators do not distinguish the symmetric variants (src/tdsops.f90:277-396 only edits BC rows)
   if (!same_tables(der1st, der1st_sym) || !same_tables(der2nd, der2nd_sym)) return X3D2C_EUNSUPPORTED;
   const int n = der1st->n_tds, nseg = n / S;
-  const bool split = ctx->cfg.nproc_dir[dir - 1] > 1;
+  const bool split = ctx->cfg.nproc_dir[dir - 1] > 1 || ctx->force_dist;
   if (split && !dist_supported(ctx, dir, n)) return X3D2C_EUNSUPPORTED;
   Params p{};
   if (!make_op(der1st, -0.5, split, &p.o_du) || !make_op(der1st, -0.5, split, &p.o_dud) ||
@@ -261,15 +254,7 @@ int transeq_m3(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, cons
   ep.ops[0] = p.o_du;
   ep.ops[1] = p.o_dud;
   ep.ops[2] = p.o_d2u;
-  for (int f = 0; f < 3; ++f) {  // recurrence f*3 + k: k = 0 d f, 1 d(f conv), 2 d2 f
-    for (int k = 0; k < 3; ++k) {
-      ep.f[3 * f + k] = p.in[f];
-      ep.c[3 * f + k] = k == 1 ? p.in[0] : nullptr;
-      ep.ff[3 * f + k] = f;
-      ep.cf[3 * f + k] = 0;
-      ep.op[3 * f + k] = k;
-    }
-  }
+  for (int f = 0; f < 3; ++f) ep.f[f] = p.in[f];  // recurrence f*3 + k: k = 0 d f, 1 d(f conv), 2 d2 f
   int rc = exchange_edges(ctx, dir, p.in, 3, ep, b);
   if (rc) return rc;
   p.halo_s = b.halo_recv_s;
