@@ -134,6 +134,19 @@ int x3d2c_transeq(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, c
  * (move_data_loc) stays on the caller's field_t. */
 int x3d2c_tds_solve(x3d2c_ctx* ctx, int dir, double* du, const double* u, const x3d2c_tdsops* ops);
 
+/* ---- fused tds_solve combinations (extensions: no counterpart in base_backend_t). Each equals the sequence of
+ * reference calls given below - and is executed as exactly that sequence in strict mode or when the operators
+ * do not qualify for the fast path - but moves 24 B per point instead of 56 / 32 / 40:
+ *   sum : tds_solve(out, in_a, op_a); tds_solve(tmp, in_b, op_b); vecadd(1, tmp, 1, out)
+ *         (divergence_v2c, src/vector_calculus.f90:185-214)
+ *   dual: tds_solve(out_a, in, op_a); tds_solve(out_b, in, op_b)   (gradient_c2v, src/vector_calculus.f90:275-300)
+ *   axpy: tds_solve(tmp, in, op); vecadd(a, tmp, 1, y)             (pressure correction, src/solver.f90:279-301) */
+int x3d2c_tds_solve_sum(x3d2c_ctx* ctx, int dir, double* out, const double* in_a, const x3d2c_tdsops* op_a,
+                        const double* in_b, const x3d2c_tdsops* op_b);
+int x3d2c_tds_solve_dual(x3d2c_ctx* ctx, int dir, double* out_a, double* out_b, const double* in,
+                         const x3d2c_tdsops* op_a, const x3d2c_tdsops* op_b);
+int x3d2c_tds_solve_axpy(x3d2c_ctx* ctx, int dir, double* y, double a, const double* in, const x3d2c_tdsops* op);
+
 /* ---- reorder (src/backend/backend.f90:128-144), rdr is one of X3D2C_RDR_* */
 int x3d2c_reorder(x3d2c_ctx* ctx, int rdr, double* dst, const double* src);
 /* ---- sum_yintox / sum_zintox (src/backend/backend.f90:146-159): u (DIR_X) += reorder(u_) */

@@ -79,6 +79,10 @@ int x3d2h_transeq(x3d2h_sim* sim, const double* u, const double* v, const double
 int x3d2h_transeq_dir(x3d2h_sim* sim, int dir, const double* u, const double* v, const double* w, double* du,
                       double* dv, double* dw);
 int x3d2h_tds_solve(x3d2h_sim* sim, int dir, const char* opname, int in_loc, const double* in, double* out, int* out_loc);
+/* x3d2c_tds_solve_sum / _dual / _axpy on host data. mode "sum": out_a = A(in_a) + B(in_b); "dual": out_a = A(in_a),
+ * out_b = B(in_a); "axpy": out_a = in_b + a A(in_a) (in_b has the output's extents) */
+int x3d2h_tds_fused(x3d2h_sim* sim, const char* mode, int dir, const char* op_a, const char* op_b, int in_loc,
+                    int out_loc, const double* in_a, const double* in_b, double a, double* out_a, double* out_b);
 int x3d2h_divergence(x3d2h_sim* sim, const double* u, const double* v, const double* w, double* div);
 int x3d2h_gradient(x3d2h_sim* sim, const double* p, double* gx, double* gy, double* gz);
 int x3d2h_curl(x3d2h_sim* sim, const double* u, const double* v, const double* w, double* ox, double* oy, double* oz);

@@ -75,3 +75,28 @@ def test_rank_split_kernels_on_one_gpu(oracle, x3d2, dims, monkeypatch):
     assert worst < TOL
     sim.close()
     plain.close()
+
+
+@pytest.mark.parametrize("dims,bcs,env", [((128, 96, 112), None, {}), ((128, 96, 112), None, {"X3D2C_FORCE_DIST": "1"}),
+                                          ((65, 64, 64), ((2, 2), (0, 0), (1, 1)), {})])
+@pytest.mark.parametrize("strict", [False, True], ids=["fast", "strict"])
+def test_fused_tds_combinations(oracle, x3d2, dims, bcs, env, strict, monkeypatch):
+    """x3d2c_tds_solve_sum / _dual / _axpy equal the reference's call sequences (two tds_solve [+ vecadd]):
+    bit-exact in strict mode, 1e-12 on the fast path (single-rank and rank-split kernels, non-periodic fallback)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    kw = dict(bcs=bcs) if bcs else {}
+    sim, ref = x3d2.Sim(dims, strict=strict, **kw), oracle.World(dims, **kw)
+    tol = 0 if strict else TOL
+    u, v = rnd(sim.shape(), 7), rnd(sim.shape(), 8)
+    c = rnd(sim.shape(1110), 9)
+    for d in (1, 2, 3):
+        e = ref.tds_solve(d, "interpl_v2p", u) + ref.tds_solve(d, "stagder_v2p", v)
+        assert rel(sim.tds_fused("sum", d, "interpl_v2p", "stagder_v2p", u, v), e) <= tol, ("sum", d)
+        ga, gb = sim.tds_fused("dual", d, "interpl_p2v", "stagder_p2v", c, in_loc=1110)
+        assert rel(ga, ref.tds_solve(d, "interpl_p2v", c, 1110)) <= tol, ("dual a", d)
+        assert rel(gb, ref.tds_solve(d, "stagder_p2v", c, 1110)) <= tol, ("dual b", d)
+        y = rnd(ga.shape, 10 + d)
+        e = -1.0 * ref.tds_solve(d, "stagder_p2v", c, 1110) + y
+        assert rel(sim.tds_fused("axpy", d, "stagder_p2v", None, c, y, a=-1.0, in_loc=1110), e) <= tol, ("axpy", d)
+    sim.close()

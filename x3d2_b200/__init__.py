@@ -213,6 +213,17 @@ class Sim:
         _chk(self._h.x3d2h_tds_solve(self.h, dir, opname.encode(), in_loc, _p(f), _p(out), C.byref(ol)))
         return out
 
+    def tds_fused(self, mode, dir, op_a, op_b, a_in, b_in=None, a=1.0, in_loc=VERT):
+        """x3d2c_tds_solve_sum / _dual / _axpy. sum: A(a_in) + B(b_in); dual: (A(a_in), B(a_in)); axpy: b_in + a A(a_in)."""
+        move = {"stagder_v2p": 1, "interpl_v2p": 1, "stagder_p2v": -1, "interpl_p2v": -1}.get(op_a, 0)
+        out_loc = in_loc + move * 10 ** dir
+        a_in = _f(a_in)
+        b_in = _f(b_in) if b_in is not None else a_in
+        oa, ob = self._out(out_loc), self._out(out_loc)
+        _chk(self._h.x3d2h_tds_fused(self.h, mode.encode(), dir, op_a.encode(), (op_b or op_a).encode(), in_loc, out_loc,
+                                     _p(a_in), _p(b_in), a, _p(oa), _p(ob)))
+        return (oa, ob) if mode == "dual" else oa
+
     def divergence(self, u, v, w):
         u, v, w = _f(u), _f(v), _f(w)
         d = self._out(CELL)

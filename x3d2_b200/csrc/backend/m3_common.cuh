@@ -118,14 +118,14 @@ struct Copier {
       cp_async16(sm + row * L + c, src);
     }
   }
-  // Halo rows of three fields: (SZ, 4, 3, G) arrays hs (rows before the line) and he (rows after) into the 8 halo
+  // Halo rows of nf fields: (SZ, 4, nf, G) arrays hs (rows before the line) and he (rows after) into the 8 halo
   // rows behind the segments of each field tile (field stride fd, halo offset hoff).
-  __device__ __forceinline__ void load_halos3(double* sm, int fd, int hoff, const double* hs, const double* he,
-                                              int tile) const {
+  __device__ __forceinline__ void load_halos(double* sm, int nf, int fd, int hoff, const double* hs, const double* he,
+                                             int tile) const {
     constexpr int tpg = SZ / L, cpr = L / 2;
     const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
-    const size_t go = (size_t)grp * 12 * SZ + l0;
-    for (int idx = threadIdx.x; idx < 24 * cpr; idx += blockDim.x) {
+    const size_t go = (size_t)grp * 4 * nf * SZ + l0;
+    for (int idx = threadIdx.x; idx < 8 * nf * cpr; idx += blockDim.x) {
       const int row = idx / cpr, c = 2 * (idx - row * cpr);
       const int f = row >> 3, r = row & 3;
       const double* src = ((row & 4) ? he : hs) + go + (size_t)(f * 4 + r) * SZ + c;
@@ -219,10 +219,10 @@ constexpr int kDistRows = 4 * (3 * 4) + 4 * (9 * EXP_ROWS);  // rows of SZ*G dou
 DistBufs carve_dist(x3d2c_ctx* ctx);
 bool dist_supported(const x3d2c_ctx* ctx, int dir, int n);
 
-// Edge kernel input: nf fields; per field either one recurrence (ops[0] on f: tds_solve, ns = nf) or three
-// (ops[0] on f, ops[1] on f * f[0], ops[2] on f: transeq, ns = 3 nf). Recurrence index = field * (ns / nf) + k.
+// Edge kernel input: nf fields with ns / nf recurrences each (m3_edge.cu: edge_kernel);
+// recurrence index = field * (ns / nf) + k.
 struct EdgeParams {
-  int n, n_pad, nseg, G, ns, nf;
+  int n, n_pad, nseg, G, ns, nf, transeq;
   const double* f[3];
   Op ops[3];
   const double *halo_s, *halo_e;  // received halos (SZ, 4, nf, G)

@@ -34,9 +34,11 @@ __global__ void __launch_bounds__(128) halo_pack_kernel(double* __restrict__ sen
 }
 
 // One thread per (lane, edge segment): segments 0..2 and nseg-3..nseg-1 of every line; blockIdx.y = field.
-// NR recurrences per field: 1 (tds_solve: ops[0] on f) or 3 (transeq: ops[0] on f, ops[1] on f*c, ops[2] on f).
+// NR recurrences per field. TRANSEQ (NR = 3): ops[0] on f, ops[1] on f * f[0], ops[2] on f. Otherwise recurrence k
+// of field fi applies ops[fi * NR + k] to f (tds_solve: one field, one operator; pair kernels: two fields with one
+// operator each, or one field with two operators).
 // The 24-row window is loaded up front (rows outside the line come from the received halos), then swept.
-template <int NR>
+template <int NR, bool TRANSEQ>
 __global__ void __launch_bounds__(32 * 2 * DMAX) edge_kernel(const __grid_constant__ EdgeParams p) {
   const int lane = threadIdx.x, e = threadIdx.y, g = blockIdx.x, fi = blockIdx.y;
   const int q = e < DMAX ? e : p.nseg - 2 * DMAX + e;
@@ -54,17 +56,17 @@ __global__ void __launch_bounds__(32 * 2 * DMAX) edge_kernel(const __grid_consta
     else if (t >= S + 4 && e == 2 * DMAX - 1) { pf = p.halo_e + hf + (size_t)(t - S - 4) * SZ; pc = p.halo_e + hc + (size_t)(t - S - 4) * SZ; }
     else { pf = f + (ptrdiff_t)r * SZ; pc = c + (ptrdiff_t)r * SZ; }
     w[t] = *pf;
-    if (NR == 3) wc[t] = *pc;
+    if (TRANSEQ) wc[t] = *pc;
   }
-  if (NR == 3) {
+  if (TRANSEQ) {
 #pragma unroll
     for (int t = 0; t < S + 8; ++t) wc[t] *= w[t];
   }
   __shared__ double sh[NR][2 * DMAX - 1][32];  // ys(0..2), ze(0..1) of the first segments
 #pragma unroll
   for (int k = 0; k < NR; ++k) {
-    const Op& o = p.ops[k];
-    const double* src = (NR == 3 && k == 1) ? wc : w;
+    const Op& o = p.ops[TRANSEQ ? k : fi * NR + k];
+    const double* src = (TRANSEQ && k == 1) ? wc : w;
     double z[S], pz = 0.0;
 #pragma unroll
     for (int i = 0; i < S; ++i) {
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(32 * 2 * DMAX) edge_kernel(const __grid_consta
     // m3_common.cuh with q + d >= nseg', q + m >= nseg'): sum_{d >= 3-e} yw[d-1] ys(e+d-3) + sum_{m >= 3-e} om[m+2] ze(e+m-3)
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
-      const Op& o = p.ops[k];
+      const Op& o = p.ops[TRANSEQ ? k : fi * NR + k];
       double acc = 0.0;
 #pragma unroll
       for (int d = 1; d <= DMAX; ++d)
@@ -202,10 +204,13 @@ int exchange_edges(x3d2c_ctx* ctx, int dir, const double* const* fields, int nf,
   ep.halo_e = b.halo_recv_e;
   ep.to_prev = b.carr_to_prev;
   ep.to_next = b.carr_to_next;
-  if (ep.ns == nf)
-    edge_kernel<1><<<dim3(G, nf), dim3(32, 2 * DMAX), 0, ctx->stream>>>(ep);
+  const dim3 eg(G, nf), eb(32, 2 * DMAX);
+  if (ep.transeq)
+    edge_kernel<3, true><<<eg, eb, 0, ctx->stream>>>(ep);
+  else if (ep.ns == 2 * nf)
+    edge_kernel<2, false><<<eg, eb, 0, ctx->stream>>>(ep);
   else
-    edge_kernel<3><<<dim3(G, nf), dim3(32, 2 * DMAX), 0, ctx->stream>>>(ep);
+    edge_kernel<1, false><<<eg, eb, 0, ctx->stream>>>(ep);
   X3D2C_CHECK_LAUNCH(ctx);
   mark(3);
   rc = x3d2c::sendrecv_fields(ctx, dir, b.carr_from_prev, b.carr_from_next, b.carr_to_prev, b.carr_to_next,

@@ -356,6 +356,9 @@ int sendrecv_fields(x3d2c_ctx* ctx, int dir, double* recv_s, double* recv_e, con
 
 // m3 fast path (tds_m3.cu); returns X3D2C_EUNSUPPORTED when the shape is not covered
 int tds_solve_m3(x3d2c_ctx* ctx, int dir, double* du, const double* u, const x3d2c_tdsops* ops);
+// pair kernels (tds_pair_m3.cu); mode 0 sum, 1 dual, 2 axpy
+int tds_pair_m3(x3d2c_ctx* ctx, int dir, int mode, double* out_a, double* out_b, const double* in_a,
+                const double* in_b, const x3d2c_tdsops* ta, const x3d2c_tdsops* tb, double scale_a);
 int transeq_m3(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, const double* u, const double* v,
                const double* w, double nu, const x3d2c_tdsops* der1st, const x3d2c_tdsops* der1st_sym,
                const x3d2c_tdsops* der2nd, const x3d2c_tdsops* der2nd_sym);
@@ -445,6 +448,53 @@ int x3d2c_tds_solve(x3d2c_ctx* ctx, int dir, double* du, const double* u, const 
                                                           ops->dev, ops->tap_mask, n_pad, G, PH_SUBS);
   X3D2C_CHECK_LAUNCH(ctx);
   return X3D2C_OK;
+}
+
+int x3d2c_tds_solve_sum(x3d2c_ctx* ctx, int dir, double* out, const double* in_a, const x3d2c_tdsops* op_a,
+                        const double* in_b, const x3d2c_tdsops* op_b) {
+  X3D2C_REQUIRE(ctx && out && in_a && in_b && op_a && op_b, "x3d2c_tds_solve_sum: null argument");
+  X3D2C_REQUIRE(dir >= 1 && dir <= 3, "x3d2c_tds_solve_sum: dir must be DIR_X/Y/Z");
+  X3D2C_REQUIRE(out != in_a && out != in_b, "x3d2c_tds_solve_sum: out must differ from the inputs");
+  if (!ctx->strict) {
+    int rc = tds_pair_m3(ctx, dir, 0, out, nullptr, in_a, in_b, op_a, op_b, 1.0);
+    trace_path("tds_solve_sum", dir, ctx->cfg.nproc_dir[dir - 1], rc != X3D2C_EUNSUPPORTED);
+    if (rc != X3D2C_EUNSUPPORTED) return rc;
+  }
+  int rc = ensure_scratch(ctx);
+  if (rc) return rc;
+  if ((rc = x3d2c_tds_solve(ctx, dir, out, in_a, op_a))) return rc;
+  if ((rc = x3d2c_tds_solve(ctx, dir, ctx->scratch[0], in_b, op_b))) return rc;
+  return x3d2c_vecadd(ctx, 1.0, ctx->scratch[0], 1.0, out);
+}
+
+int x3d2c_tds_solve_dual(x3d2c_ctx* ctx, int dir, double* out_a, double* out_b, const double* in,
+                         const x3d2c_tdsops* op_a, const x3d2c_tdsops* op_b) {
+  X3D2C_REQUIRE(ctx && out_a && out_b && in && op_a && op_b, "x3d2c_tds_solve_dual: null argument");
+  X3D2C_REQUIRE(dir >= 1 && dir <= 3, "x3d2c_tds_solve_dual: dir must be DIR_X/Y/Z");
+  X3D2C_REQUIRE(out_a != in && out_b != in && out_a != out_b, "x3d2c_tds_solve_dual: fields must be distinct");
+  if (!ctx->strict) {
+    int rc = tds_pair_m3(ctx, dir, 1, out_a, out_b, in, nullptr, op_a, op_b, 1.0);
+    trace_path("tds_solve_dual", dir, ctx->cfg.nproc_dir[dir - 1], rc != X3D2C_EUNSUPPORTED);
+    if (rc != X3D2C_EUNSUPPORTED) return rc;
+  }
+  int rc = x3d2c_tds_solve(ctx, dir, out_a, in, op_a);
+  if (rc) return rc;
+  return x3d2c_tds_solve(ctx, dir, out_b, in, op_b);
+}
+
+int x3d2c_tds_solve_axpy(x3d2c_ctx* ctx, int dir, double* y, double a, const double* in, const x3d2c_tdsops* op) {
+  X3D2C_REQUIRE(ctx && y && in && op, "x3d2c_tds_solve_axpy: null argument");
+  X3D2C_REQUIRE(dir >= 1 && dir <= 3, "x3d2c_tds_solve_axpy: dir must be DIR_X/Y/Z");
+  X3D2C_REQUIRE(y != in, "x3d2c_tds_solve_axpy: y and in must be different fields");
+  if (!ctx->strict) {
+    int rc = tds_pair_m3(ctx, dir, 2, y, nullptr, in, y, op, op, a);
+    trace_path("tds_solve_axpy", dir, ctx->cfg.nproc_dir[dir - 1], rc != X3D2C_EUNSUPPORTED);
+    if (rc != X3D2C_EUNSUPPORTED) return rc;
+  }
+  int rc = ensure_scratch(ctx);
+  if (rc) return rc;
+  if ((rc = x3d2c_tds_solve(ctx, dir, ctx->scratch[0], in, op))) return rc;
+  return x3d2c_vecadd(ctx, a, ctx->scratch[0], 1.0, y);
 }
 
 int x3d2c_transeq(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, const double* u, const double* v,

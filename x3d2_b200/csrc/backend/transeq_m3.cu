@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) transeq_m3_kernel(const __grid
 #pragma unroll
     for (int f = 0; f < 3; ++f) cp.load(smem + (3 * buf + f) * fd, p.in[f], g, tile);
     if (DIST) {
-      cp.load_halos3(smem + 3 * buf * fd, fd, g.nseg * SP * L, p.halo_s, p.halo_e, tile);
+      cp.load_halos(smem + 3 * buf * fd, 3, fd, g.nseg * SP * L, p.halo_s, p.halo_e, tile);
       cp.load_rows2(smem + 6 * fd + buf * xbuf, p.from_prev, p.from_next, NS * EXP_ROWS, tile);
     }
   };
@@ -251,6 +251,7 @@ int transeq_m3(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, cons
   ep.n_pad = p.g.n_pad;
   ep.nseg = nseg;
   ep.ns = NS;
+  ep.transeq = 1;
   ep.ops[0] = p.o_du;
   ep.ops[1] = p.o_dud;
   ep.ops[2] = p.o_d2u;

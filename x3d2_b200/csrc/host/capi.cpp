@@ -204,6 +204,31 @@ int x3d2h_tds_solve(x3d2h_sim* sim, int dir, const char* opname, int in_loc, con
   S.get_field(out, *fo, fo->data_loc);
   H_CATCH
 }
+int x3d2h_tds_fused(x3d2h_sim* sim, const char* mode, int dir, const char* op_a, const char* op_b, int in_loc,
+                    int out_loc, const double* in_a, const double* in_b, double a, double* out_a, double* out_b) {
+  H_TRY
+  Sim& S = *sim->s;
+  Tmp t(S.allocator);
+  const std::string m = mode;
+  Field *fa = t.get(dir), *fb = t.get(dir), *oa = t.get(dir), *ob = t.get(dir);
+  S.set_field(*fa, in_a, in_loc);
+  if (m == "sum") {
+    S.set_field(*fb, in_b, in_loc);
+    S.backend.tds_solve_sum(*oa, *fa, S.pick(dir, op_a), *fb, S.pick(dir, op_b));
+    S.get_field(out_a, *oa, out_loc);
+  } else if (m == "dual") {
+    S.backend.tds_solve_dual(*oa, *ob, *fa, S.pick(dir, op_a), S.pick(dir, op_b));
+    S.get_field(out_a, *oa, out_loc);
+    S.get_field(out_b, *ob, out_loc);
+  } else if (m == "axpy") {
+    S.set_field(*oa, in_b, out_loc);  // y
+    S.backend.tds_solve_axpy(*oa, a, *fa, S.pick(dir, op_a));
+    S.get_field(out_a, *oa, out_loc);
+  } else {
+    fail("x3d2h_tds_fused: mode must be sum, dual or axpy");
+  }
+  H_CATCH
+}
 int x3d2h_divergence(x3d2h_sim* sim, const double* u, const double* v, const double* w, double* div) {
   H_TRY
   Sim& S = *sim->s;

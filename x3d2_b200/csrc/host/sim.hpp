@@ -272,6 +272,24 @@ class Backend {  // cuda_c_backend_t: every method is one deferred procedure of 
     if (u.data_loc != NULL_LOC) du.data_loc = move_data_loc(u.data_loc, u.dir, ops.t.move);
     X3D2H_CALL(x3d2c_tds_solve(ctx, u.dir, du.dev, u.dev, ops.h));
   }
+  // fused combinations (x3d2c.h): identical to the reference's call sequences, one pass over memory on the fast path
+  void tds_solve_sum(Field& out, const Field& a, const DevTdsops& opa, const Field& b, const DevTdsops& opb) {
+    if (a.dir != out.dir || b.dir != out.dir) fail("DIR mismatch between fields in tds_solve.");
+    if (a.data_loc != NULL_LOC) out.data_loc = move_data_loc(a.data_loc, a.dir, opa.t.move);
+    X3D2H_CALL(x3d2c_tds_solve_sum(ctx, a.dir, out.dev, a.dev, opa.h, b.dev, opb.h));
+  }
+  void tds_solve_dual(Field& oa, Field& ob, const Field& u, const DevTdsops& opa, const DevTdsops& opb) {
+    if (u.dir != oa.dir || u.dir != ob.dir) fail("DIR mismatch between fields in tds_solve.");
+    if (u.data_loc != NULL_LOC) {
+      oa.data_loc = move_data_loc(u.data_loc, u.dir, opa.t.move);
+      ob.data_loc = move_data_loc(u.data_loc, u.dir, opb.t.move);
+    }
+    X3D2H_CALL(x3d2c_tds_solve_dual(ctx, u.dir, oa.dev, ob.dev, u.dev, opa.h, opb.h));
+  }
+  void tds_solve_axpy(Field& y, double a, const Field& u, const DevTdsops& op) {
+    if (u.dir != y.dir) fail("DIR mismatch between fields in tds_solve.");
+    X3D2H_CALL(x3d2c_tds_solve_axpy(ctx, u.dir, y.dev, a, u.dev, op.h));
+  }
   void reorder(Field& u_, const Field& u, int direction) {
     X3D2H_CALL(x3d2c_reorder(ctx, direction, u_.dev, u.dev));
     u_.data_loc = u.data_loc;
@@ -513,36 +531,32 @@ class Sim {
     Field *u_y = A.get_block(DIR_Y), *v_y = A.get_block(DIR_Y), *w_y = A.get_block(DIR_Y);
     backend.reorder(*u_y, *du_x, RDR_X2Y); backend.reorder(*v_y, *dv_x, RDR_X2Y); backend.reorder(*w_y, *dw_x, RDR_X2Y);
     A.release_block(du_x); A.release_block(dv_x); A.release_block(dw_x);
-    Field *du_y = A.get_block(DIR_Y), *dv_y = A.get_block(DIR_Y), *dw_y = A.get_block(DIR_Y);
-    backend.tds_solve(*du_y, *u_y, ydirps.interpl_v2p);
-    backend.tds_solve(*dv_y, *v_y, ydirps.stagder_v2p);
+    // du_y = interpl(u_y) + stagder(v_y); dw_y = interpl(w_y)   (:185-199: two tds_solve + vecadd, fused)
+    Field *du_y = A.get_block(DIR_Y), *dw_y = A.get_block(DIR_Y);
+    backend.tds_solve_sum(*du_y, *u_y, ydirps.interpl_v2p, *v_y, ydirps.stagder_v2p);
     backend.tds_solve(*dw_y, *w_y, ydirps.interpl_v2p);
     A.release_block(u_y); A.release_block(v_y); A.release_block(w_y);
     Field *u_z = A.get_block(DIR_Z), *w_z = A.get_block(DIR_Z);
-    backend.vecadd(1.0, *dv_y, 1.0, *du_y);
     backend.reorder(*u_z, *du_y, RDR_Y2Z); backend.reorder(*w_z, *dw_y, RDR_Y2Z);
-    A.release_block(du_y); A.release_block(dv_y); A.release_block(dw_y);
-    Field* dw_z = A.get_block(DIR_Z);
-    backend.tds_solve(div_u, *u_z, zdirps.interpl_v2p);
-    backend.tds_solve(*dw_z, *w_z, zdirps.stagder_v2p);
-    backend.vecadd(1.0, *dw_z, 1.0, div_u);
-    A.release_block(u_z); A.release_block(w_z); A.release_block(dw_z);
+    A.release_block(du_y); A.release_block(dw_y);
+    // div = interpl(u_z) + stagder(w_z)   (:205-214)
+    backend.tds_solve_sum(div_u, *u_z, zdirps.interpl_v2p, *w_z, zdirps.stagder_v2p);
+    A.release_block(u_z); A.release_block(w_z);
   }
 
-  // vector_calculus.f90:248-332
-  void gradient_c2v(Field& dpdx, Field& dpdy, Field& dpdz, const Field& p) {
+  // vector_calculus.f90:248-332. With sub != nullptr the x stage subtracts the gradient from (sub[0], sub[1],
+  // sub[2]) instead of writing it (the vecadd(-1, dpdx, 1, u) calls of solver.f90:296-298 fused into the last solve).
+  void gradient_c2v(Field& dpdx, Field& dpdy, Field& dpdz, const Field& p, Field* const* sub = nullptr) {
     if (dpdx.dir != DIR_X || dpdy.dir != DIR_X || dpdz.dir != DIR_X || p.dir != DIR_Z)
       fail("Error in gradient_c2v input/output field dirs: outputs must be in DIR_X, input must be in DIR_Z layout.");
     Allocator& A = allocator;
     Field *p_sxy_z = A.get_block(DIR_Z), *dpdz_sxy_z = A.get_block(DIR_Z);
-    backend.tds_solve(*p_sxy_z, p, zdirps.interpl_p2v);
-    backend.tds_solve(*dpdz_sxy_z, p, zdirps.stagder_p2v);
+    backend.tds_solve_dual(*p_sxy_z, *dpdz_sxy_z, p, zdirps.interpl_p2v, zdirps.stagder_p2v);
     Field *p_sxy_y = A.get_block(DIR_Y), *dpdz_sxy_y = A.get_block(DIR_Y);
     backend.reorder(*p_sxy_y, *p_sxy_z, RDR_Z2Y); backend.reorder(*dpdz_sxy_y, *dpdz_sxy_z, RDR_Z2Y);
     A.release_block(p_sxy_z); A.release_block(dpdz_sxy_z);
     Field *p_sx_y = A.get_block(DIR_Y), *dpdy_sx_y = A.get_block(DIR_Y);
-    backend.tds_solve(*p_sx_y, *p_sxy_y, ydirps.interpl_p2v);
-    backend.tds_solve(*dpdy_sx_y, *p_sxy_y, ydirps.stagder_p2v);
+    backend.tds_solve_dual(*p_sx_y, *dpdy_sx_y, *p_sxy_y, ydirps.interpl_p2v, ydirps.stagder_p2v);
     A.release_block(p_sxy_y);
     Field* dpdz_sx_y = A.get_block(DIR_Y);
     backend.tds_solve(*dpdz_sx_y, *dpdz_sxy_y, ydirps.interpl_p2v);
@@ -553,9 +567,15 @@ class Sim {
     backend.reorder(*dpdy_sx_x, *dpdy_sx_y, RDR_Y2X); A.release_block(dpdy_sx_y);
     Field* dpdz_sx_x = A.get_block(DIR_X);
     backend.reorder(*dpdz_sx_x, *dpdz_sx_y, RDR_Y2X); A.release_block(dpdz_sx_y);
-    backend.tds_solve(dpdx, *p_sx_x, xdirps.stagder_p2v);
-    backend.tds_solve(dpdy, *dpdy_sx_x, xdirps.interpl_p2v);
-    backend.tds_solve(dpdz, *dpdz_sx_x, xdirps.interpl_p2v);
+    if (sub) {
+      backend.tds_solve_axpy(*sub[0], -1.0, *p_sx_x, xdirps.stagder_p2v);
+      backend.tds_solve_axpy(*sub[1], -1.0, *dpdy_sx_x, xdirps.interpl_p2v);
+      backend.tds_solve_axpy(*sub[2], -1.0, *dpdz_sx_x, xdirps.interpl_p2v);
+    } else {
+      backend.tds_solve(dpdx, *p_sx_x, xdirps.stagder_p2v);
+      backend.tds_solve(dpdy, *dpdy_sx_x, xdirps.interpl_p2v);
+      backend.tds_solve(dpdz, *dpdz_sx_x, xdirps.interpl_p2v);
+    }
     A.release_block(p_sx_x); A.release_block(dpdy_sx_x); A.release_block(dpdz_sx_x);
   }
 
@@ -613,13 +633,9 @@ class Sim {
     Field* p = A.get_block(DIR_Z);
     poisson_fft(*p, *div_u);
     A.release_block(div_u);
-    Field *dpdx = A.get_block(DIR_X), *dpdy = A.get_block(DIR_X), *dpdz = A.get_block(DIR_X);
-    gradient_c2v(*dpdx, *dpdy, *dpdz, *p);
+    Field* vel[3] = {&uu, &vv, &ww};
+    gradient_c2v(uu, vv, ww, *p, vel);  // u -= dpdx, v -= dpdy, w -= dpdz
     A.release_block(p);
-    backend.vecadd(-1.0, *dpdx, 1.0, uu);
-    backend.vecadd(-1.0, *dpdy, 1.0, vv);
-    backend.vecadd(-1.0, *dpdz, 1.0, ww);
-    A.release_block(dpdx); A.release_block(dpdy); A.release_block(dpdz);
   }
 
   // time_integrator.f90:70-164
