@@ -157,6 +157,11 @@ int x3d2c_sum_zintox(x3d2c_ctx* ctx, double* u, const double* u_z);
 int x3d2c_veccopy(x3d2c_ctx* ctx, double* dst, const double* src);
 int x3d2c_vecadd(x3d2c_ctx* ctx, double a, const double* x, double b, double* y);
 int x3d2c_vecmult(x3d2c_ctx* ctx, double* y, const double* x);
+/* extension: out = base, then out = coef[k] * x[k] + 1.0 * out for k = 0..n-1 (n <= 4) in one pass; the same values as
+ * veccopy(out, base) followed by vecadd(coef[k], x[k], 1.0, out) (time integrators, src/time_integrator.f90:166-231).
+ * out may alias base, not a term. */
+int x3d2c_veclincomb(x3d2c_ctx* ctx, double* out, const double* base, int n, const double* coef,
+                     const double* const* x);
 /* ---- field_scale / field_shift (src/backend/backend.f90:255-266) */
 int x3d2c_field_scale(x3d2c_ctx* ctx, double* f, double a);
 int x3d2c_field_shift(x3d2c_ctx* ctx, double* f, double a);

@@ -71,3 +71,18 @@ def test_elementwise_ops(x3d2):
     c = rng.standard_normal(sim.shape(1110))
     assert abs(sim.fieldop("volume_integral", 1, c, loc=1110) - c.sum()) < 1e-10 * np.abs(c).sum()
     sim.close()
+
+
+def test_veclincomb_matches_vecadd_chain(x3d2):
+    """x3d2c_veclincomb == the vecadd(c_k, x_k, 1.0, out) chain of the time integrators: exact in strict mode."""
+    sim = x3d2.Sim((33, 20, 24), bcs=((2, 2), (1, 1), (0, 0)), strict=True)
+    rng = np.random.default_rng(6)
+    x, y = rng.standard_normal(sim.shape()), rng.standard_normal(sim.shape())
+    a = 0.37
+    exp = (-a / 2) * y + ((a * y) + x)
+    for d in (1, 2, 3):
+        assert np.array_equal(sim.fieldop("lincomb", d, x, y, a=a), exp)
+    sim.close()
+    fast = x3d2.Sim((33, 20, 24), bcs=((2, 2), (1, 1), (0, 0)))
+    assert np.abs(fast.fieldop("lincomb", 1, x, y, a=a) - exp).max() < 1e-15
+    fast.close()

@@ -61,6 +61,40 @@ axpby_strict_kernel(double* __restrict__ y, const double* __restrict__ x, const 
     y[i] = __dadd_rn(__dmul_rn(a, x[i]), __dmul_rn(b, y[i]));
 }
 
+// out = base; out = c_k x_k + out, k = 0..n-1: the vecadd(c_k, x_k, 1.0, out) chain of the time integrators
+// (src/time_integrator.f90:166-231) in one pass, each term rounded exactly like OP_AXPBY / axpby_strict_kernel.
+struct LinComb {
+  const double* base;
+  const double* x[4];
+  double c[4];
+  int n;
+};
+template <bool STRICT>
+__global__ void __launch_bounds__(kThreads)
+lincomb_kernel(double* out, const __grid_constant__ LinComb q, const long long n2) {  // out may alias q.base
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  double2* o2 = reinterpret_cast<double2*>(out);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+    double2 r = reinterpret_cast<const double2*>(q.base)[i];
+    double2 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < q.n) v[k] = reinterpret_cast<const double2*>(q.x[k])[i];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < q.n) {
+        if (STRICT) {
+          r.x = __dadd_rn(__dmul_rn(q.c[k], v[k].x), __dmul_rn(1.0, r.x));
+          r.y = __dadd_rn(__dmul_rn(q.c[k], v[k].y), __dmul_rn(1.0, r.y));
+        } else {
+          r.x = q.c[k] * v[k].x + 1.0 * r.x;
+          r.y = q.c[k] * v[k].y + 1.0 * r.y;
+        }
+      }
+    o2[i] = r;
+  }
+}
+
 struct RedGeom {
   int dir;
   int n_pad;        // padded line length
@@ -198,6 +232,24 @@ int x3d2c_vecadd(x3d2c_ctx* ctx, double a, const double* x, double b, double* y)
     return X3D2C_OK;
   }
   return run_stream<OP_AXPBY>(ctx, y, x, a, b);
+}
+int x3d2c_veclincomb(x3d2c_ctx* ctx, double* out, const double* base, int n, const double* coef,
+                     const double* const* x) {
+  X3D2C_REQUIRE(ctx && out && base && n >= 1 && n <= 4 && coef && x, "x3d2c_veclincomb: bad argument");
+  LinComb q{};
+  q.base = base;
+  q.n = n;
+  for (int k = 0; k < n; ++k) {
+    X3D2C_REQUIRE(x[k] && x[k] != out, "x3d2c_veclincomb: a term is null or aliases out");
+    q.x[k] = x[k];
+    q.c[k] = coef[k];
+  }
+  if (ctx->strict)
+    lincomb_kernel<true><<<kBlocks, kThreads, 0, ctx->stream>>>(out, q, ctx->ngrid / 2);
+  else
+    lincomb_kernel<false><<<kBlocks, kThreads, 0, ctx->stream>>>(out, q, ctx->ngrid / 2);
+  X3D2C_CHECK_LAUNCH(ctx);
+  return X3D2C_OK;
 }
 int x3d2c_vecmult(x3d2c_ctx* ctx, double* y, const double* x) {
   X3D2C_REQUIRE(ctx && x && y, "x3d2c_vecmult: null argument");

@@ -413,6 +413,9 @@ extern "C" int x3d2h_fieldop(x3d2h_sim* sim, const char* op_c, int dir, int data
   else if (op == "vecmult") { X3D2H_CALL(x3d2c_vecmult(S.ctx, fy->dev, fx->dev)); fx = fy; }
   else if (op == "veccopy") { S.backend.veccopy(*fy, *fx); fx = fy; }
   else if (op == "fill") X3D2H_CALL(x3d2c_field_fill(S.ctx, fx->dev, a));
+  else if (op == "lincomb") {  // out = x; out = a y + out; out = (-a / 2) y + out, written over x (out aliases base)
+    S.backend.veclincomb(*fx, *fx, {{a, fy}, {-a / 2, fy}});
+  }
   else if (op == "volume_integral") X3D2H_CALL(x3d2c_field_volume_integral(S.ctx, data_loc, fx->dev, s));
   else fail("x3d2h_fieldop: unknown op " + op);
   if (out) S.get_field(out, *fx, data_loc);

@@ -306,6 +306,18 @@ class Backend {  // cuda_c_backend_t: every method is one deferred procedure of 
     if (y.dir == DIR_C) fail("vecadd does not support DIR_C fields");
     X3D2H_CALL(x3d2c_vecadd(ctx, a, x.dev, b, y.dev));
   }
+  // out = base, then out = c[k] x[k] + out for every term: the vecadd chains of the time integrators in one pass
+  void veclincomb(Field& out, const Field& base, const std::vector<std::pair<double, const Field*>>& terms) {
+    if (terms.empty() || terms.size() > 4) fail("veclincomb takes 1 to 4 terms");
+    double c[4];
+    const double* x[4];
+    for (size_t k = 0; k < terms.size(); ++k) {
+      if (terms[k].second->dir != out.dir) fail("Called vector add with incompatible fields");
+      c[k] = terms[k].first;
+      x[k] = terms[k].second->dev;
+    }
+    X3D2H_CALL(x3d2c_veclincomb(ctx, out.dev, base.dev, (int)terms.size(), c, x));
+  }
   double scalar_product(const Field& x, const Field& y) {
     if (x.data_loc == NULL_LOC || y.data_loc == NULL_LOC) fail("You must set the data_loc before calling scalar product");
     if (x.data_loc != y.data_loc) fail("Called scalar product with incompatible fields");
@@ -666,31 +678,50 @@ class Sim {
       for (int j = 1; j <= ti_nolds; ++j) olds[i][j] = allocator.get_block(DIR_X);
   }
   // time_integrator.f90:166-231
+  // The vecadd / veccopy chains of the reference are executed as one veclincomb per field (same values, same
+  // rounding sequence; terms with a zero coefficient are dropped on the fast path, where c*x + y == y), and the
+  // copies "olds <- deriv", "olds(1) <- curr" become pointer swaps: deriv[i] / curr[i] are exchanged with the
+  // block they would have been copied into (the caller releases whatever deriv[i] points to afterwards).
+  using Terms = std::vector<std::pair<double, const Field*>>;
+  void lincomb_or_copy(Field& out, const Field& base, Terms terms) {
+    if (!(cfg.flags & X3D2C_FLAG_STRICT)) {
+      Terms kept;
+      for (auto& t : terms) if (t.first != 0.0) kept.push_back(t);
+      terms.swap(kept);
+    }
+    if (terms.empty()) { if (&out != &base) backend.veccopy(out, base); return; }
+    backend.veclincomb(out, base, terms);
+  }
   void runge_kutta(Field* curr[3], Field* deriv[3], double dt_) {
     if (ti_istage == ti_nstage) {
       for (int i = 0; i < 3; ++i) {
-        if (ti_nstage > 1) backend.veccopy(*curr[i], *olds[i][1]);
-        for (int j = 1; j <= ti_nstage - 1; ++j) backend.vecadd(ti_rk_b[j][ti_nstage] * dt_, *olds[i][j + 1], 1.0, *curr[i]);
-        backend.vecadd(ti_rk_b[ti_nstage][ti_nstage] * dt_, *deriv[i], 1.0, *curr[i]);
+        Terms terms;
+        for (int j = 1; j <= ti_nstage - 1; ++j) terms.push_back({ti_rk_b[j][ti_nstage] * dt_, olds[i][j + 1]});
+        terms.push_back({ti_rk_b[ti_nstage][ti_nstage] * dt_, deriv[i]});
+        lincomb_or_copy(*curr[i], ti_nstage > 1 ? *olds[i][1] : *curr[i], terms);
       }
       ti_istage = 1;
     } else {
       for (int i = 0; i < 3; ++i) {
-        if (ti_istage == 1) backend.veccopy(*olds[i][1], *curr[i]);
-        backend.veccopy(*olds[i][ti_istage + 1], *deriv[i]);
-        if (ti_istage > 1) backend.veccopy(*curr[i], *olds[i][1]);
-        for (int j = 1; j <= ti_istage; ++j)
-          backend.vecadd(ti_rk_a[j][ti_istage][ti_nstage] * dt_, *olds[i][j + 1], 1.0, *curr[i]);
+        if (ti_istage == 1) {  // olds(1) <- curr: keep the block as olds(1), continue in the former olds(1) block
+          std::swap(olds[i][1], curr[i]);
+          curr[i]->data_loc = olds[i][1]->data_loc;
+        }
+        std::swap(olds[i][ti_istage + 1], deriv[i]);  // olds(istage + 1) <- deriv
+        Terms terms;
+        for (int j = 1; j <= ti_istage; ++j) terms.push_back({ti_rk_a[j][ti_istage][ti_nstage] * dt_, olds[i][j + 1]});
+        lincomb_or_copy(*curr[i], *olds[i][1], terms);
       }
       ti_istage = ti_istage + 1;
     }
   }
-  // time_integrator.f90:233-300
   void adams_bashforth(Field* curr[3], Field* deriv[3], double dt_) {
     const int nstep = std::min(ti_istep, ti_nstep);
     for (int i = 0; i < 3; ++i) {
-      backend.vecadd(ti_coeffs[1][nstep] * dt_, *deriv[i], 1.0, *curr[i]);
-      for (int j = 2; j <= nstep; ++j) backend.vecadd(ti_coeffs[j][nstep] * dt_, *olds[i][j - 1], 1.0, *curr[i]);
+      Terms terms;
+      terms.push_back({ti_coeffs[1][nstep] * dt_, deriv[i]});
+      for (int j = 2; j <= nstep; ++j) terms.push_back({ti_coeffs[j][nstep] * dt_, olds[i][j - 1]});
+      lincomb_or_copy(*curr[i], *curr[i], terms);
       auto rotate = [&](int n) {
         Field* ptr = olds[i][n];
         for (int q = n; q >= 2; --q) olds[i][q] = olds[i][q - 1];
@@ -698,7 +729,7 @@ class Sim {
       };
       if (nstep < ti_nstep) { if (ti_istep > 1) rotate(nstep); }
       else { if (ti_nstep > 2) rotate(nstep - 1); }
-      if (ti_nstep > 1) backend.veccopy(*olds[i][1], *deriv[i]);
+      if (ti_nstep > 1) std::swap(olds[i][1], deriv[i]);  // olds(1) <- deriv
     }
     ti_istep = ti_istep + 1;
   }
@@ -710,6 +741,7 @@ class Sim {
       Field* deriv[3] = {allocator.get_block(DIR_X), allocator.get_block(DIR_X), allocator.get_block(DIR_X)};
       transeq_default(*deriv[0], *deriv[1], *deriv[2], *u, *v, *w);
       if (ti_is_ab) adams_bashforth(curr, deriv, dt); else runge_kutta(curr, deriv, dt);
+      u = curr[0]; v = curr[1]; w = curr[2];  // the integrators may continue in another block
       for (int i = 0; i < 3; ++i) allocator.release_block(deriv[i]);
       pressure_correction(*u, *v, *w);
     }
