@@ -152,6 +152,8 @@ int x3d2c_reorder(x3d2c_ctx* ctx, int rdr, double* dst, const double* src);
 /* ---- sum_yintox / sum_zintox (src/backend/backend.f90:146-159): u (DIR_X) += reorder(u_) */
 int x3d2c_sum_yintox(x3d2c_ctx* ctx, double* u, const double* u_y);
 int x3d2c_sum_zintox(x3d2c_ctx* ctx, double* u, const double* u_z);
+/* extension: sum_yintox(u, u_y) followed by sum_zintox(u, u_z) in one pass over u (same order of additions) */
+int x3d2c_sum_yzintox(x3d2c_ctx* ctx, double* u, const double* u_y, const double* u_z);
 
 /* ---- veccopy / vecadd / vecmult (src/backend/backend.f90:161-201): whole padded block */
 int x3d2c_veccopy(x3d2c_ctx* ctx, double* dst, const double* src);

@@ -59,6 +59,33 @@ reorder_tile_kernel(double* __restrict__ dst, const double* __restrict__ src, co
   }
 }
 
+// u (DIR_X) = (u + reorder(a)) + reorder(b): sum_yintox followed by sum_zintox in one pass over u
+// (same order of additions as the two reference calls, src/solver.f90:340-372).
+__global__ void __launch_bounds__(256)
+sum2_tile_kernel(double* __restrict__ dst, const double* __restrict__ a, const double* __restrict__ b, const Lay la,
+                 const Lay lb, const Lay ld) {
+  __shared__ double ta[32][33], tb[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const long long ba = blockIdx.x * la.sxb + blockIdx.y * la.syb + blockIdx.z * la.sz;
+  const long long bb = blockIdx.x * lb.sxb + blockIdx.y * lb.syb + blockIdx.z * lb.sz;
+  const long long bd = blockIdx.x * ld.sxb + blockIdx.y * ld.syb + blockIdx.z * ld.sz;
+  // both sources have x_l fastest (DIR_Y / DIR_Z), the destination y_l (DIR_X)
+  double va[4], vb[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    va[r] = a[ba + tx * la.sxl + (ty + 8 * r) * la.syl];
+    vb[r] = b[bb + tx * lb.sxl + (ty + 8 * r) * lb.syl];
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { ta[ty + 8 * r][tx] = va[r]; tb[ty + 8 * r][tx] = vb[r]; }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    double* p = dst + bd + tx * ld.syl + (ty + 8 * r) * ld.sxl;
+    *p = (*p + ta[tx][ty + 8 * r]) + tb[tx][ty + 8 * r];
+  }
+}
+
 }  // namespace
 
 namespace x3d2c {
@@ -90,6 +117,16 @@ int x3d2c_reorder(x3d2c_ctx* ctx, int rdr, double* dst, const double* src) {
 int x3d2c_sum_yintox(x3d2c_ctx* ctx, double* u, const double* u_y) {
   X3D2C_REQUIRE(ctx && u && u_y, "x3d2c_sum_yintox: null argument");
   return launch_reorder(ctx, X3D2C_DIR_Y, X3D2C_DIR_X, u, u_y, true);
+}
+
+int x3d2c_sum_yzintox(x3d2c_ctx* ctx, double* u, const double* u_y, const double* u_z) {
+  X3D2C_REQUIRE(ctx && u && u_y && u_z, "x3d2c_sum_yzintox: null argument");
+  X3D2C_REQUIRE(ctx->nz_pad <= 65535, "x3d2c_sum_yzintox: nz exceeds the grid limit");
+  const dim3 grid(ctx->nx_pad / SZ, ctx->ny_pad / SZ, ctx->nz_pad), block(32, 8);
+  sum2_tile_kernel<<<grid, block, 0, ctx->stream>>>(u, u_y, u_z, layout_of(ctx, X3D2C_DIR_Y), layout_of(ctx, X3D2C_DIR_Z),
+                                                    layout_of(ctx, X3D2C_DIR_X));
+  X3D2C_CHECK_LAUNCH(ctx);
+  return X3D2C_OK;
 }
 
 int x3d2c_sum_zintox(x3d2c_ctx* ctx, double* u, const double* u_z) {

@@ -296,6 +296,7 @@ class Backend {  // cuda_c_backend_t: every method is one deferred procedure of 
   }
   void sum_yintox(Field& u, const Field& u_) { X3D2H_CALL(x3d2c_sum_yintox(ctx, u.dev, u_.dev)); }
   void sum_zintox(Field& u, const Field& u_) { X3D2H_CALL(x3d2c_sum_zintox(ctx, u.dev, u_.dev)); }
+  void sum_yzintox(Field& u, const Field& u_y, const Field& u_z) { X3D2H_CALL(x3d2c_sum_yzintox(ctx, u.dev, u_y.dev, u_z.dev)); }
   void veccopy(Field& dst, const Field& src) {
     if (src.dir != dst.dir) fail("Called vector copy with incompatible fields");
     if (dst.dir == DIR_C) fail("veccopy does not support DIR_C fields");
@@ -520,14 +521,14 @@ class Sim {
     backend.reorder(*u_y, uu, RDR_X2Y); backend.reorder(*v_y, vv, RDR_X2Y); backend.reorder(*w_y, ww, RDR_X2Y);
     backend.transeq_y(*du_y, *dv_y, *dw_y, *u_y, *v_y, *w_y, nu, ydirps);
     A.release_block(u_y); A.release_block(v_y); A.release_block(w_y);
-    backend.sum_yintox(du, *du_y); backend.sum_yintox(dv, *dv_y); backend.sum_yintox(dw, *dw_y);
-    A.release_block(du_y); A.release_block(dv_y); A.release_block(dw_y);
+    // sum_yintox is deferred: one pass adds the y and the z contributions (in the reference's order)
     Field *u_z = A.get_block(DIR_Z), *v_z = A.get_block(DIR_Z), *w_z = A.get_block(DIR_Z), *du_z = A.get_block(DIR_Z),
           *dv_z = A.get_block(DIR_Z), *dw_z = A.get_block(DIR_Z);
     backend.reorder(*u_z, uu, RDR_X2Z); backend.reorder(*v_z, vv, RDR_X2Z); backend.reorder(*w_z, ww, RDR_X2Z);
     backend.transeq_z(*du_z, *dv_z, *dw_z, *u_z, *v_z, *w_z, nu, zdirps);
     A.release_block(u_z); A.release_block(v_z); A.release_block(w_z);
-    backend.sum_zintox(du, *du_z); backend.sum_zintox(dv, *dv_z); backend.sum_zintox(dw, *dw_z);
+    backend.sum_yzintox(du, *du_y, *du_z); backend.sum_yzintox(dv, *dv_y, *dv_z); backend.sum_yzintox(dw, *dw_y, *dw_z);
+    A.release_block(du_y); A.release_block(dv_y); A.release_block(dw_y);
     A.release_block(du_z); A.release_block(dv_z); A.release_block(dw_z);
   }
 
