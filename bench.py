@@ -22,7 +22,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_PT = {"transeq": 48, "tds_solve": 16}  # per transeq_{x,y,z} / tds_solve call
-STEP_BYTES_PER_PT = 3888                                # whole RK3 step
+STEP_BYTES_PER_PT = 3888                                # whole RK3 step, the reference's operator graph
+# What this backend's operator graph moves per RK3 step (DESIGN.md "bytes per step"): per stage transeq 336
+# (3 x 48 kernels, 6 reorders, 3 fused y+z sums), divergence 192, Poisson 152, gradient + correction 216; RK3 updates 264
+STEP_BYTES_MOVED_PER_PT = 3 * (336 + 192 + 152 + 216) + 264
 
 
 def grid_for(n_gpus, base):
@@ -242,7 +245,10 @@ def main():
                               "ms_per_launch": roof["tds_solve"]["ms"], "algorithmic_bytes_per_launch": 16 * pts_local},
                 "whole_step": {"achieved": STEP_BYTES_PER_PT * pts_local / (ms_per_step * 1e-3) / 1e9,
                                "frac": STEP_BYTES_PER_PT * pts_local / (ms_per_step * 1e-3) / 1e9 / peak,
-                               "algorithmic_bytes_per_step": STEP_BYTES_PER_PT * pts_local}}
+                               "algorithmic_bytes_per_step": STEP_BYTES_PER_PT * pts_local,
+                               "note": "bytes of the reference's operator graph (SURVEY.md 8d); fused operators move fewer",
+                               "moved_bytes_per_step": STEP_BYTES_MOVED_PER_PT * pts_local,
+                               "moved_frac": STEP_BYTES_MOVED_PER_PT * pts_local / (ms_per_step * 1e-3) / 1e9 / peak}}
 
     # ---------------------------------------------------------------- end to end: host buffers in, host buffers out
     nz, ny, nx = sim.shape()

@@ -1,6 +1,6 @@
 """Per-operator device timing (CUDA events on the backend's stream) against the algorithmic bytes of SURVEY.md §8d.
 
-usage: python tools/opbench.py [N] [--strict] [--ops=transeq_z,poisson,...]
+usage: python tools/opbench.py [N | nx,ny,nz] [--strict] [--ops=transeq_z,poisson,...]
        python -m torch.distributed.run --nnodes=1 --nproc-per-node P --master-addr 127.0.0.1 tools/opbench.py [N]
            (P ranks, z-slabs of N^3 points each: the z operators run the rank-split kernels + NCCL exchanges)
 """
@@ -33,6 +33,7 @@ def time_op(sim, op, reps, stream):
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 256
+    local = [int(a) for a in sys.argv[1].split(",")] if len(sys.argv) > 1 and "," in sys.argv[1] else [n, n, n]
     strict = "--strict" in sys.argv
     peak = 6541.8
     try:
@@ -52,13 +53,13 @@ def main():
             assert X.load()[0].x3d2c_nccl_unique_id(raw) == 0
             buf = [raw.raw]
         dist.broadcast_object_list(buf, src=0)
-        sim = X.Sim((n, n, n * world), nproc_dir=(1, 1, world), rank=rank, nproc=world, device=local, strict=strict,
+        sim = X.Sim((local[0], local[1], local[2] * world), nproc_dir=(1, 1, world), rank=rank, nproc=world, device=local, strict=strict,
                     nccl_unique_id=buf[0])
     else:
-        sim = X.Sim((n, n, n), strict=strict)
+        sim = X.Sim(tuple(local), strict=strict)
     sim.init_tgv()
     stream = torch.cuda.ExternalStream(sim.stream())
-    npts = n ** 3
+    npts = local[0] * local[1] * local[2]
     rows = []
     only = [a.split("=", 1)[1].split(",") for a in sys.argv if a.startswith("--ops=")]
     for op, b in BYTES_PER_PT.items():
@@ -70,7 +71,7 @@ def main():
         if rank == 0:
             print(f"{op:22s} {ms:9.3f} ms  {gbs:9.1f} GB/s  {100 * gbs / peak:6.1f}% of measured {peak:.0f} GB/s", flush=True)
     if rank == 0:
-        print(f"N={n} per rank, ranks={world}, strict={strict}")
+        print(f"local grid {local} per rank, ranks={world}, strict={strict}")
     sim.close()
 
 

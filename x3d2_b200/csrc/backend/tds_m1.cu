@@ -359,6 +359,9 @@ int tds_solve_m3(x3d2c_ctx* ctx, int dir, double* du, const double* u, const x3d
 // pair kernels (tds_pair_m3.cu); mode 0 sum, 1 dual, 2 axpy
 int tds_pair_m3(x3d2c_ctx* ctx, int dir, int mode, double* out_a, double* out_b, const double* in_a,
                 const double* in_b, const x3d2c_tdsops* ta, const x3d2c_tdsops* tb, double scale_a);
+int transeq_m4(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, const double* u, const double* v,
+               const double* w, double nu, const x3d2c_tdsops* der1st, const x3d2c_tdsops* der1st_sym,
+               const x3d2c_tdsops* der2nd, const x3d2c_tdsops* der2nd_sym);
 int transeq_m3(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, const double* u, const double* v,
                const double* w, double nu, const x3d2c_tdsops* der1st, const x3d2c_tdsops* der1st_sym,
                const x3d2c_tdsops* der2nd, const x3d2c_tdsops* der2nd_sym);
@@ -508,8 +511,10 @@ int x3d2c_transeq(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, c
                     der2nd_sym->n_tds == der1st->n_tds, "x3d2c_transeq: operators must share n_tds == n_rhs");
   const int P = ctx->cfg.nproc_dir[dir - 1];
   if (!ctx->strict) {
-    int rc = transeq_m3(ctx, dir, du, dv, dw, u, v, w, nu, der1st, der1st_sym, der2nd, der2nd_sym);
-    trace_path("transeq", dir, P, rc != X3D2C_EUNSUPPORTED);
+    int rc = transeq_m4(ctx, dir, du, dv, dw, u, v, w, nu, der1st, der1st_sym, der2nd, der2nd_sym);  // TMA tiles
+    const bool tma = rc != X3D2C_EUNSUPPORTED;
+    if (!tma) rc = transeq_m3(ctx, dir, du, dv, dw, u, v, w, nu, der1st, der1st_sym, der2nd, der2nd_sym);
+    trace_path(tma ? "transeq[tma tiles]" : "transeq", dir, P, rc != X3D2C_EUNSUPPORTED);
     if (rc != X3D2C_EUNSUPPORTED) return rc;
   }
   // argument permutation of omp/backend.f90:154,168,182: component 0 is the line-aligned velocity
