@@ -139,7 +139,8 @@ __device__ __forceinline__ void component4(const int fF, const int fC, const int
       smem4[fF + b0 + k * NT] = fma(smem4[fC + b0 + k * NT], du, z2[k]);
     }
   }
-  __syncthreads();  // the carries are overwritten by the next component; F is complete
+  fence_async_smem();  // F was written through the generic proxy, the TMA store reads through the async proxy
+  __syncthreads();     // the carries are overwritten by the next component; F is complete
 }
 
 template <int L, int NT>
@@ -172,17 +173,22 @@ __global__ void __launch_bounds__(NT, 1) transeq_m4_kernel(const __grid_constant
     const int buf = it & 1;
     mbar_wait(buf ? bar1 : bar0, (it >> 1) & 1);
     const int bo = buf * 3 * fd;
-    // components 1 and 2 first: they read the aligned velocity (field 0) as conv; field 0 is overwritten last
+    // components 1 and 2 first: they read the aligned velocity (field 0) as conv; field 0 is overwritten last.
+    // Each result is stored as soon as its component is complete.
+    const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
+    auto store_field = [&](int f) {
+      if (tid == 0) {
+        tma_store_4d(&p.out[f], saddr(smem4 + bo + f * fd), l0, 0, 0, grp);
+        tma_commit();
+      }
+    };
     component4<L, NT, false>(bo + 1 * fd, bo, cz, p, q, l, bm, b0, bp);
+    store_field(1);
     component4<L, NT, false>(bo + 2 * fd, bo, cz, p, q, l, bm, b0, bp);
+    store_field(2);
     component4<L, NT, true>(bo, bo, cz, p, q, l, bm, b0, bp);
-    fence_async_smem();  // results were written through the generic proxy, the TMA reads through the async proxy
-    __syncthreads();
+    store_field(0);
     if (tid == 0) {
-      const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
-#pragma unroll
-      for (int f = 0; f < 3; ++f) tma_store_4d(&p.out[f], saddr(smem4 + bo + f * fd), l0, 0, 0, grp);
-      tma_commit();
       const int nn = tile + 2 * gridDim.x;
       if (nn < p.tiles) {
         tma_wait_read();  // the stores have read this buffer
@@ -220,8 +226,13 @@ bool make_map(CUtensorMap* m, const double* field, int L, int nseg, int n_pad, i
   const cuuint64_t strides[3] = {(cuuint64_t)S * SZ * 8, (cuuint64_t)SZ * 8, (cuuint64_t)n_pad * SZ * 8};
   const cuuint32_t box[4] = {(cuuint32_t)L, (cuuint32_t)nseg, (cuuint32_t)S, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
+  static int promo = -1;  // X3D2C_TMA_L2PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B (tuning knob)
+  if (promo < 0) {
+    const char* e = std::getenv("X3D2C_TMA_L2PROMO");
+    promo = e ? std::atoi(e) & 3 : 0;
+  }
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(field), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)promo,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
