@@ -1,0 +1,57 @@
+// Host-side helpers of the TMA-based kernels (m4_common.cuh).
+#include "m4_common.cuh"
+
+namespace m4 {
+
+namespace {
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn encode_fn() {
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(sym);
+  }
+  return fn;
+}
+
+// (lane, segment, row in segment, group) view of a directional field: a box of (L, nseg, 16, 1) is one tile
+}  // namespace
+
+bool make_line_map(CUtensorMap* m, const double* field, int L, int nseg, int n_pad, int groups) {
+  EncodeFn enc = encode_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)SZ, (cuuint64_t)nseg, (cuuint64_t)S, (cuuint64_t)groups};
+  const cuuint64_t strides[3] = {(cuuint64_t)S * SZ * 8, (cuuint64_t)SZ * 8, (cuuint64_t)n_pad * SZ * 8};
+  const cuuint32_t box[4] = {(cuuint32_t)L, (cuuint32_t)nseg, (cuuint32_t)S, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  static int promo = -1;  // X3D2C_TMA_L2PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B (tuning knob)
+  if (promo < 0) {
+    const char* e = std::getenv("X3D2C_TMA_L2PROMO");
+    promo = e ? std::atoi(e) & 3 : 0;
+  }
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(field), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)promo,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+
+bool tile_shape(int n, int* L, int* NT) {
+  switch (n) {
+    case 64: *L = 32; *NT = 128; return true;
+    case 128: *L = 16; *NT = 128; return true;
+    case 256: *L = 8; *NT = 128; return true;
+    case 512: *L = 4; *NT = 128; return true;
+    case 1024: *L = 4; *NT = 256; return true;
+    default: return false;
+  }
+}
+
+}  // namespace m4

@@ -1,0 +1,215 @@
+// tds_solve and its fused pairs with the tile copies done by the TMA engine ("m4"; same arithmetic as tds_m3.cu and
+// tds_pair_m3.cu, shared-memory layout [row in segment][segment][lane] as in transeq_m4.cu).
+//   SINGLE: out   = A(in)                  16 B/pt
+//   SUM   : out   = A(in_a) + B(in_b)      24 B/pt
+//   DUAL  : out_a = A(in), out_b = B(in)   24 B/pt
+//   AXPY  : y     = y + a A(in)            24 B/pt
+// Periodic, uniform, single-rank directions with n = 64..512 a power of two; other shapes use the cp.async kernels.
+// Measured at 512^3: tds_solve 0.395 -> 0.376 ms (87% of HBM peak) with 64-byte rows (L = 8, 256 threads); with
+// 32-byte rows (L = 4, 128 threads) the TMA version is slower (0.52 ms), so narrow tiles stay on the cp.async path.
+#include "m4_common.cuh"
+
+using namespace m4;
+
+namespace {
+
+enum Mode { SINGLE = 0, SUM = 1, DUAL = 2, AXPY = 3 };
+
+struct TdsParams4 {
+  CUtensorMap in_a, in_b;    // SUM: two inputs; AXPY: in_b = y
+  CUtensorMap out_a, out_b;  // DUAL: two outputs; AXPY: out_a = y
+  int tiles;
+  Op oa, ob;
+};
+
+template <int NT, unsigned M>
+__device__ __forceinline__ void local_sweeps4(const int F, const Op& o, int bm, int b0, int bp, double (&z)[S],
+                                              double& ze) {
+  double wf[9];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) wf[t] = smem4[F + woff4<NT>(t, bm, b0, bp)];
+  double pz = 0.0;
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    wf[8] = smem4[F + woff4<NT>(k + 8, bm, b0, bp)];
+    pz = fma(o.a, pz, sten<M>(o.cfw, wf));
+    z[k] = pz;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) wf[t] = wf[t + 1];
+  }
+  ze = pz;
+  double y = 0.0;
+#pragma unroll
+  for (int k = S - 1; k >= 0; --k) {
+    y = fma(o.cb, y, z[k]);
+    z[k] = y;
+  }
+}
+
+// shared memory: [2 buffers][NSLOT tiles of 16 x NT] [NR x (ze, ys)[NT]] [2 mbarriers]
+template <int L, int NT, unsigned M, int MODE>
+__global__ void __launch_bounds__(NT, 512 / NT) tds_m4_kernel(const __grid_constant__ TdsParams4 p) {
+  constexpr int nseg = NT / L, fd = S * NT, tpg = SZ / L;
+  constexpr int NSLOT = MODE == SINGLE ? 1 : 2;
+  constexpr int NR = (MODE == SUM || MODE == DUAL) ? 2 : 1;
+  constexpr int NLOAD = (MODE == SUM || MODE == AXPY) ? 2 : 1;
+  constexpr int cz = 2 * NSLOT * fd;
+  constexpr unsigned tile_bytes = fd * sizeof(double);
+  const int tid = threadIdx.x, l = tid & (L - 1), q = tid / L;
+  const int b0 = tid, bm = tid - L + (q == 0 ? NT : 0), bp = tid + L - (q == nseg - 1 ? NT : 0);
+  const unsigned bar0 = saddr(smem4 + cz + 2 * NR * NT), bar1 = bar0 + 8;
+  auto issue_loads = [&](int buf, int tile) {
+    const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
+    const unsigned bar = buf ? bar1 : bar0;
+    mbar_expect_tx(bar, NLOAD * tile_bytes);
+    tma_load_4d(saddr(smem4 + buf * NSLOT * fd), &p.in_a, bar, l0, 0, 0, grp);
+    if (NLOAD == 2) tma_load_4d(saddr(smem4 + (buf * NSLOT + 1) * fd), &p.in_b, bar, l0, 0, 0, grp);
+  };
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    issue_loads(0, blockIdx.x);
+    if ((int)(blockIdx.x + gridDim.x) < p.tiles) issue_loads(1, blockIdx.x + gridDim.x);
+  }
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    mbar_wait(buf ? bar1 : bar0, (it >> 1) & 1);
+    const int F0 = buf * NSLOT * fd, F1 = F0 + fd;
+    double za[S], zb[S], ze;
+    local_sweeps4<NT, M>(F0, p.oa, bm, b0, bp, za, ze);
+    smem4[cz + b0] = ze;
+    smem4[cz + NT + b0] = za[0];
+    if (NR == 2) {
+      local_sweeps4<NT, M>(MODE == SUM ? F1 : F0, p.ob, bm, b0, bp, zb, ze);
+      smem4[cz + 2 * NT + b0] = ze;
+      smem4[cz + 3 * NT + b0] = zb[0];
+    }
+    __syncthreads();
+    double zin, yin;
+    carries<L, false>(cz + l, cz + NT + l, L, 0, 0, p.oa, q, nseg, zin, yin);
+#pragma unroll
+    for (int k = 0; k < S; ++k) za[k] = fma(p.oa.Cp[k], yin, fma(p.oa.W[k], zin, za[k]));
+    if (NR == 2) {
+      carries<L, false>(cz + 2 * NT + l, cz + 3 * NT + l, L, 0, 0, p.ob, q, nseg, zin, yin);
+#pragma unroll
+      for (int k = 0; k < S; ++k) zb[k] = fma(p.ob.Cp[k], yin, fma(p.ob.W[k], zin, zb[k]));
+    }
+    if (MODE == SINGLE) {
+#pragma unroll
+      for (int k = 0; k < S; ++k) smem4[F0 + b0 + k * NT] = za[k];
+    } else if (MODE == SUM) {
+#pragma unroll
+      for (int k = 0; k < S; ++k) smem4[F0 + b0 + k * NT] = za[k] + zb[k];
+    } else if (MODE == DUAL) {
+#pragma unroll
+      for (int k = 0; k < S; ++k) { smem4[F0 + b0 + k * NT] = za[k]; smem4[F1 + b0 + k * NT] = zb[k]; }
+    } else {  // AXPY: the scale is folded into oa.cfw
+#pragma unroll
+      for (int k = 0; k < S; ++k) smem4[F1 + b0 + k * NT] += za[k];
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
+      tma_store_4d(&p.out_a, saddr(smem4 + (MODE == AXPY ? F1 : F0)), l0, 0, 0, grp);
+      if (MODE == DUAL) tma_store_4d(&p.out_b, saddr(smem4 + F1), l0, 0, 0, grp);
+      tma_commit();
+      const int nn = tile + 2 * gridDim.x;
+      if (nn < p.tiles) {
+        tma_wait_read();  // the stores have read this buffer
+        issue_loads(buf, nn);
+      }
+    }
+  }
+  if (tid == 0) tma_wait_all();
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+template <int L, int NT, unsigned M, int MODE>
+int launch(x3d2c_ctx* ctx, const TdsParams4& p) {
+  constexpr int NSLOT = MODE == SINGLE ? 1 : 2, NR = (MODE == SUM || MODE == DUAL) ? 2 : 1;
+  constexpr size_t smem = sizeof(double) * (2 * NSLOT * S * NT + 2 * NR * NT) + 16;
+  static int per_sm = 0;  // resident CTAs per SM (registers and shared memory), queried once
+  if (!per_sm) {
+    X3D2C_CHECK_CUDA(cudaFuncSetAttribute(tds_m4_kernel<L, NT, M, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+    X3D2C_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tds_m4_kernel<L, NT, M, MODE>, NT, smem));
+    if (per_sm < 1) per_sm = 1;
+  }
+  int grid = num_sms(ctx) * per_sm;
+  if (grid > p.tiles) grid = p.tiles;
+  tds_m4_kernel<L, NT, M, MODE><<<grid, NT, smem, ctx->stream>>>(p);
+  X3D2C_CHECK_LAUNCH(ctx);
+  return X3D2C_OK;
+}
+
+template <int L, int NT, int MODE>
+int dispatch_mask(x3d2c_ctx* ctx, const TdsParams4& p, unsigned mask) {
+  switch (mask) {
+    case 0x78u: return launch<L, NT, 0x78u, MODE>(ctx, p);  // staggered derivative / interpolation v2p
+    case 0x3Cu: return launch<L, NT, 0x3Cu, MODE>(ctx, p);  // p2v
+    case 0x6Cu: if (MODE == SINGLE) return launch<L, NT, 0x6Cu, SINGLE>(ctx, p);  // first derivative
+    case 0x7Cu: if (MODE == SINGLE) return launch<L, NT, 0x7Cu, SINGLE>(ctx, p);  // second derivative
+    default: return launch<L, NT, 0x1FFu, MODE>(ctx, p);
+  }
+}
+
+// Tiles of 256 threads: the copy-bound tds kernels want rows of at least 64 bytes (L >= 8) where the line allows it
+bool tds_shape(int n, int* L, int* NT) {
+  switch (n) {
+    case 64: *L = 32; *NT = 128; return true;
+    case 128: *L = 32; *NT = 256; return true;
+    case 256: *L = 16; *NT = 256; return true;
+    case 512: *L = 8; *NT = 256; return true;
+    default: return false;  // n = 1024 would need 32-byte rows: measured slower than the cp.async kernel
+  }
+}
+
+template <int MODE>
+int dispatch_shape(x3d2c_ctx* ctx, const TdsParams4& p, int L, int NT, unsigned mask) {
+  if (NT == 128) return dispatch_mask<32, 128, MODE>(ctx, p, mask);
+  switch (L) {
+    case 8: return dispatch_mask<8, 256, MODE>(ctx, p, mask);
+    case 16: return dispatch_mask<16, 256, MODE>(ctx, p, mask);
+    default: return dispatch_mask<32, 256, MODE>(ctx, p, mask);
+  }
+}
+
+}  // namespace
+
+namespace x3d2c {
+
+// mode: 0 single (out_a = A(in_a)), 1 sum, 2 dual, 3 axpy (out_a = y, scale_a folded into A)
+int tds_m4(x3d2c_ctx* ctx, int dir, int mode, double* out_a, double* out_b, const double* in_a, const double* in_b,
+           const x3d2c_tdsops* ta, const x3d2c_tdsops* tb, double scale_a) {
+  static const bool disabled = std::getenv("X3D2C_NO_TMA") != nullptr;
+  if (disabled || ctx->cfg.nproc_dir[dir - 1] > 1 || ctx->force_dist) return X3D2C_EUNSUPPORTED;
+  const int n = ta->n_tds;
+  int L = 0, NT = 0;
+  if (!tds_shape(n, &L, &NT)) return X3D2C_EUNSUPPORTED;
+  const bool two_ops = mode == SUM || mode == DUAL;
+  if (two_ops && (tb->n_tds != n || tb->n_rhs != ta->n_rhs)) return X3D2C_EUNSUPPORTED;
+  TdsParams4 p{};
+  if (!make_op(ta, mode == AXPY ? scale_a : 1.0, false, &p.oa)) return X3D2C_EUNSUPPORTED;
+  if (two_ops && !make_op(tb, 1.0, false, &p.ob)) return X3D2C_EUNSUPPORTED;
+  const int G = ctx->n_groups[dir], n_pad = ctx->n_pad(dir), nseg = n / S;
+  auto map = [&](CUtensorMap* m, const double* f) { return make_line_map(m, f, L, nseg, n_pad, G); };
+  if (!map(&p.in_a, in_a) || !map(&p.out_a, out_a)) return X3D2C_EUNSUPPORTED;
+  if ((mode == SUM || mode == AXPY) && !map(&p.in_b, in_b)) return X3D2C_EUNSUPPORTED;
+  if (mode == DUAL && !map(&p.out_b, out_b)) return X3D2C_EUNSUPPORTED;
+  p.tiles = G * (SZ / L);
+  const unsigned mask = two_ops ? (ta->tap_mask | tb->tap_mask) : ta->tap_mask;
+  switch (mode) {
+    case SINGLE: return dispatch_shape<SINGLE>(ctx, p, L, NT, mask);
+    case SUM: return dispatch_shape<SUM>(ctx, p, L, NT, mask);
+    case DUAL: return dispatch_shape<DUAL>(ctx, p, L, NT, mask);
+    default: return dispatch_shape<AXPY>(ctx, p, L, NT, mask);
+  }
+}
+
+}  // namespace x3d2c

@@ -14,11 +14,9 @@
 //  * two CTAs x two buffers per SM as before (104 KB each).
 // Periodic, uniform, single-rank directions with n a power of two (64..2048) and the compact6 tap masks; everything
 // else uses transeq_m3.cu.
-#include <cuda.h>
+#include "m4_common.cuh"
 
-#include "m3_common.cuh"
-
-using namespace m3;
+using namespace m4;
 
 namespace {
 
@@ -28,51 +26,6 @@ struct Params4 {
   int tiles;
   Op o_du, o_dud, o_d2u;  // scaled by -1/2, -1/2, nu
 };
-
-extern __shared__ __align__(1024) double smem4[];
-
-__device__ __forceinline__ unsigned saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, unsigned src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
-               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// window element t (row j0 - 4 + t, t = 0..S+7): rows 12..15 of the previous segment, own rows, rows 0..3 of the next
-template <int NT>
-__device__ __forceinline__ int woff4(int t, int bm, int b0, int bp) {
-  return t < 4 ? bm + (S - 4 + t) * NT : (t < S + 4 ? b0 + (t - 4) * NT : bp + (t - S - 4) * NT);
-}
 
 // One velocity component of one tile. fF / fC: offsets of the field and conv tiles ([16][NT] each); cz: offset of the
 // carry arrays ze[3][NT], ys[3][NT].
@@ -200,42 +153,6 @@ __global__ void __launch_bounds__(NT, 1) transeq_m4_kernel(const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeFn encode_fn() {
-  static EncodeFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qr) == cudaSuccess &&
-        qr == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeFn>(sym);
-  }
-  return fn;
-}
-
-// (lane, segment, row in segment, group) view of a directional field: a box of (L, nseg, 16, 1) is one tile
-bool make_map(CUtensorMap* m, const double* field, int L, int nseg, int n_pad, int groups) {
-  EncodeFn enc = encode_fn();
-  if (!enc) return false;
-  const cuuint64_t dims[4] = {(cuuint64_t)SZ, (cuuint64_t)nseg, (cuuint64_t)S, (cuuint64_t)groups};
-  const cuuint64_t strides[3] = {(cuuint64_t)S * SZ * 8, (cuuint64_t)SZ * 8, (cuuint64_t)n_pad * SZ * 8};
-  const cuuint32_t box[4] = {(cuuint32_t)L, (cuuint32_t)nseg, (cuuint32_t)S, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  static int promo = -1;  // X3D2C_TMA_L2PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B (tuning knob)
-  if (promo < 0) {
-    const char* e = std::getenv("X3D2C_TMA_L2PROMO");
-    promo = e ? std::atoi(e) & 3 : 0;
-  }
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(field), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)promo,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <int L, int NT>
 int launch4(x3d2c_ctx* ctx, const Params4& p) {
   constexpr size_t smem = sizeof(double) * (6 * S * NT + 6 * NT) + 16;
@@ -265,14 +182,7 @@ int transeq_m4(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, cons
   if (der1st->tap_mask != 0x6Cu || der2nd->tap_mask != 0x7Cu) return X3D2C_EUNSUPPORTED;
   const int n = der1st->n_tds, nseg = n / S;
   int L = 0, NT = 0;
-  switch (n) {
-    case 64: L = 32; NT = 128; break;
-    case 128: L = 16; NT = 128; break;
-    case 256: L = 8; NT = 128; break;
-    case 512: L = 4; NT = 128; break;
-    case 1024: L = 4; NT = 256; break;
-    default: return X3D2C_EUNSUPPORTED;
-  }
+  if (!tile_shape(n, &L, &NT)) return X3D2C_EUNSUPPORTED;
   Params4 p{};
   if (!make_op(der1st, -0.5, false, &p.o_du) || !make_op(der1st, -0.5, false, &p.o_dud) ||
       !make_op(der2nd, nu, false, &p.o_d2u))
@@ -284,7 +194,7 @@ int transeq_m4(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, cons
   else { out[0] = dw; out[1] = du; out[2] = dv; in[0] = w; in[1] = u; in[2] = v; }
   const int G = ctx->n_groups[dir], n_pad = ctx->n_pad(dir);
   for (int f = 0; f < 3; ++f)
-    if (!make_map(&p.in[f], in[f], L, nseg, n_pad, G) || !make_map(&p.out[f], out[f], L, nseg, n_pad, G))
+    if (!make_line_map(&p.in[f], in[f], L, nseg, n_pad, G) || !make_line_map(&p.out[f], out[f], L, nseg, n_pad, G))
       return X3D2C_EUNSUPPORTED;
   p.tiles = G * (SZ / L);
   if (L == 32) return launch4<32, 128>(ctx, p);
