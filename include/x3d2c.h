@@ -146,6 +146,18 @@ int x3d2c_tds_solve_sum(x3d2c_ctx* ctx, int dir, double* out, const double* in_a
 int x3d2c_tds_solve_dual(x3d2c_ctx* ctx, int dir, double* out_a, double* out_b, const double* in,
                          const x3d2c_tdsops* op_a, const x3d2c_tdsops* op_b);
 int x3d2c_tds_solve_axpy(x3d2c_ctx* ctx, int dir, double* y, double a, const double* in, const x3d2c_tdsops* op);
+/* ... and through a reorder: reorder(in, rdr_in) -> operator(s) in `dir` -> reorder(out, rdr_out); rdr = 0 means the
+ * field already is / stays in the DIR_`dir` layout, otherwise rdr_in must end in `dir` (e.g. X3D2C_RDR_C2Z for dir = Z)
+ * and rdr_out must start from it (e.g. X3D2C_RDR_Y2Z for dir = Y). The fast path addresses the foreign layout from
+ * inside the kernel (Y / Z lines, layouts Y, Z, C); otherwise the three steps run one after the other. Removes the
+ * y2z, z2c, c2z and z2y reorder passes of divergence_v2c / poisson_fft / gradient_c2v
+ * (src/vector_calculus.f90:200-203,275-285, src/solver.f90:755-772). */
+int x3d2c_tds_solve_r(x3d2c_ctx* ctx, int dir, double* out, const double* in, const x3d2c_tdsops* op, int rdr_in,
+                      int rdr_out);
+int x3d2c_tds_solve_sum_r(x3d2c_ctx* ctx, int dir, double* out, const double* in_a, const x3d2c_tdsops* op_a,
+                          const double* in_b, const x3d2c_tdsops* op_b, int rdr_in, int rdr_out);
+int x3d2c_tds_solve_dual_r(x3d2c_ctx* ctx, int dir, double* out_a, double* out_b, const double* in,
+                           const x3d2c_tdsops* op_a, const x3d2c_tdsops* op_b, int rdr_in, int rdr_out);
 
 /* ---- reorder (src/backend/backend.f90:128-144), rdr is one of X3D2C_RDR_* */
 int x3d2c_reorder(x3d2c_ctx* ctx, int rdr, double* dst, const double* src);

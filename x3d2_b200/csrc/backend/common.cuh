@@ -94,7 +94,9 @@ struct x3d2c_ctx {
   long long ngrid = 0;
   long long launches = 0;
   // scratch
-  double* scratch[2] = {nullptr, nullptr};  // dud / d2u blocks of transeq (omp/backend.f90:319-320)
+  // [0], [1]: dud / d2u blocks of transeq (omp/backend.f90:319-320), temporaries of the fused tds fallbacks;
+  // [2..5]: reordered inputs / outputs of the *_r fallbacks (tds_fused.cu). Allocated on first use.
+  double* scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double* halo = nullptr;                   // packed halo / reduced-row exchange buffers
   size_t halo_doubles = 0;
   double* red = nullptr;       // device reduction scratch
@@ -122,6 +124,6 @@ struct x3d2c_poisson {
 // internal launch helpers implemented across the .cu files
 namespace x3d2c {
 int launch_reorder(x3d2c_ctx* ctx, int dir_from, int dir_to, double* dst, const double* src, bool accumulate);
-int ensure_scratch(x3d2c_ctx* ctx);
+int ensure_scratch(x3d2c_ctx* ctx, int count = 2);
 int get_dims_dataloc(const x3d2c_ctx* ctx, int data_loc, int dims[3], bool global);
 }  // namespace x3d2c

@@ -25,8 +25,8 @@ int get_dims_dataloc(const x3d2c_ctx* ctx, int data_loc, int dims[3], bool globa
   return X3D2C_OK;
 }
 
-int ensure_scratch(x3d2c_ctx* ctx) {
-  for (int i = 0; i < 2; ++i)
+int ensure_scratch(x3d2c_ctx* ctx, int count) {
+  for (int i = 0; i < count; ++i)
     if (!ctx->scratch[i]) X3D2C_CHECK_CUDA(cudaMalloc(&ctx->scratch[i], sizeof(double) * ctx->ngrid));
   return X3D2C_OK;
 }
@@ -97,7 +97,7 @@ int x3d2c_destroy(x3d2c_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   nccl_finalize(ctx);
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 6; ++i)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   if (ctx->halo) cudaFree(ctx->halo);
   if (ctx->red) cudaFree(ctx->red);

@@ -42,6 +42,19 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, unsigned sr
                "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, unsigned src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -57,5 +70,11 @@ __device__ __forceinline__ int woff4(int t, int bm, int b0, int bp) {
 bool make_line_map(CUtensorMap* m, const double* field, int L, int nseg, int n_pad, int groups);
 // tile geometry for a line of n points: L lanes x nseg segments = NT threads (128, or 256 for n = 1024)
 bool tile_shape(int n, int* L, int* NT);
+// The tiles of line direction `line_dir` (L lanes x all segments x 16 rows of group g = c3 + nb * c4) inside a field
+// stored in layout `layout_dir`, as a 5-D tensor (lane, segment, row in segment, c3, c4). Y and Z lines can address
+// fields stored as DIR_Y, DIR_Z or DIR_C (all keep 32 consecutive x in a row): this is how a kernel reads or writes
+// "through" a reorder. *nb returns the extent of c3 (tile coordinates: c3 = g % nb, c4 = g / nb).
+bool make_map5(CUtensorMap* m, const double* field, int layout_dir, int line_dir, int L, int nseg,
+               const x3d2c_ctx* ctx, int* nb);
 
 }  // namespace m4

@@ -43,6 +43,39 @@ bool make_line_map(CUtensorMap* m, const double* field, int L, int nseg, int n_p
 }
 
 
+bool make_map5(CUtensorMap* m, const double* field, int layout_dir, int line_dir, int L, int nseg,
+               const x3d2c_ctx* ctx, int* nb) {
+  EncodeFn enc = encode_fn();
+  if (!enc) return false;
+  const cuuint64_t R = (cuuint64_t)SZ * 8;  // one row of 32 lanes
+  const cuuint64_t nxp = ctx->nx_pad, nyp = ctx->ny_pad, nz = ctx->nz_pad, nxb = nxp / SZ, nyb = nyp / SZ;
+  cuuint64_t sk, s3, s4, d3, d4;  // byte strides of one line point, c3, c4; extents of c3, c4
+  if (line_dir == X3D2C_DIR_X) {
+    if (layout_dir != X3D2C_DIR_X) return false;
+    d3 = nyb; d4 = nz; sk = R; s3 = nxp * R; s4 = nyb * nxp * R;
+  } else if (line_dir == X3D2C_DIR_Y) {  // group = xb + nxb * z
+    d3 = nxb; d4 = nz;
+    if (layout_dir == X3D2C_DIR_Y) { sk = R; s3 = nyp * R; s4 = nxb * nyp * R; }
+    else if (layout_dir == X3D2C_DIR_Z) { sk = R * nz * nxb; s3 = R * nz; s4 = R; }
+    else if (layout_dir == X3D2C_DIR_C) { sk = nxp * 8; s3 = R; s4 = nxp * nyp * 8; }
+    else return false;
+  } else {  // Z lines, group = xb + nxb * y
+    d3 = nxb; d4 = nyp;
+    if (layout_dir == X3D2C_DIR_Z) { sk = R; s3 = nz * R; s4 = nxb * nz * R; }
+    else if (layout_dir == X3D2C_DIR_Y) { sk = R * nyp * nxb; s3 = R * nyp; s4 = R; }
+    else if (layout_dir == X3D2C_DIR_C) { sk = nxp * nyp * 8; s3 = R; s4 = nxp * 8; }
+    else return false;
+  }
+  *nb = (int)d3;
+  const cuuint64_t dims[5] = {(cuuint64_t)SZ, (cuuint64_t)nseg, (cuuint64_t)S, d3, d4};
+  const cuuint64_t strides[4] = {S * sk, sk, s3, s4};
+  const cuuint32_t box[5] = {(cuuint32_t)L, (cuuint32_t)nseg, (cuuint32_t)S, 1, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, const_cast<double*>(field), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool tile_shape(int n, int* L, int* NT) {
   switch (n) {
     case 64: *L = 32; *NT = 128; return true;

@@ -359,7 +359,7 @@ int tds_solve_m3(x3d2c_ctx* ctx, int dir, double* du, const double* u, const x3d
 // pair kernels (tds_pair_m3.cu); mode 0 sum, 1 dual, 2 axpy
 // TMA kernels (tds_m4.cu); mode 0 single, 1 sum, 2 dual, 3 axpy
 int tds_m4(x3d2c_ctx* ctx, int dir, int mode, double* out_a, double* out_b, const double* in_a, const double* in_b,
-           const x3d2c_tdsops* ta, const x3d2c_tdsops* tb, double scale_a);
+           const x3d2c_tdsops* ta, const x3d2c_tdsops* tb, double scale_a, int lay_in, int lay_out);
 int tds_pair_m3(x3d2c_ctx* ctx, int dir, int mode, double* out_a, double* out_b, const double* in_a,
                 const double* in_b, const x3d2c_tdsops* ta, const x3d2c_tdsops* tb, double scale_a);
 int transeq_m4(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, const double* u, const double* v,
@@ -415,7 +415,7 @@ int x3d2c_tds_solve(x3d2c_ctx* ctx, int dir, double* du, const double* u, const 
   X3D2C_REQUIRE(ops->n_rhs <= n_pad, "x3d2c_tds_solve: operator longer than the padded line");
   const int P = ctx->cfg.nproc_dir[dir - 1];
   if (!ctx->strict) {  // fast path: periodic uniform directions, single-rank or rank-split
-    int rc = tds_m4(ctx, dir, 0, du, nullptr, u, nullptr, ops, ops, 1.0);
+    int rc = tds_m4(ctx, dir, 0, du, nullptr, u, nullptr, ops, ops, 1.0, dir, dir);
     if (rc == X3D2C_EUNSUPPORTED) rc = tds_solve_m3(ctx, dir, du, u, ops);
     trace_path("tds_solve", dir, P, rc != X3D2C_EUNSUPPORTED);
     if (rc != X3D2C_EUNSUPPORTED) return rc;
@@ -463,7 +463,7 @@ int x3d2c_tds_solve_sum(x3d2c_ctx* ctx, int dir, double* out, const double* in_a
   X3D2C_REQUIRE(dir >= 1 && dir <= 3, "x3d2c_tds_solve_sum: dir must be DIR_X/Y/Z");
   X3D2C_REQUIRE(out != in_a && out != in_b, "x3d2c_tds_solve_sum: out must differ from the inputs");
   if (!ctx->strict) {
-    int rc = tds_m4(ctx, dir, 1, out, nullptr, in_a, in_b, op_a, op_b, 1.0);
+    int rc = tds_m4(ctx, dir, 1, out, nullptr, in_a, in_b, op_a, op_b, 1.0, dir, dir);
     if (rc == X3D2C_EUNSUPPORTED) rc = tds_pair_m3(ctx, dir, 0, out, nullptr, in_a, in_b, op_a, op_b, 1.0);
     trace_path("tds_solve_sum", dir, ctx->cfg.nproc_dir[dir - 1], rc != X3D2C_EUNSUPPORTED);
     if (rc != X3D2C_EUNSUPPORTED) return rc;
@@ -481,7 +481,7 @@ int x3d2c_tds_solve_dual(x3d2c_ctx* ctx, int dir, double* out_a, double* out_b, 
   X3D2C_REQUIRE(dir >= 1 && dir <= 3, "x3d2c_tds_solve_dual: dir must be DIR_X/Y/Z");
   X3D2C_REQUIRE(out_a != in && out_b != in && out_a != out_b, "x3d2c_tds_solve_dual: fields must be distinct");
   if (!ctx->strict) {
-    int rc = tds_m4(ctx, dir, 2, out_a, out_b, in, nullptr, op_a, op_b, 1.0);
+    int rc = tds_m4(ctx, dir, 2, out_a, out_b, in, nullptr, op_a, op_b, 1.0, dir, dir);
     if (rc == X3D2C_EUNSUPPORTED) rc = tds_pair_m3(ctx, dir, 1, out_a, out_b, in, nullptr, op_a, op_b, 1.0);
     trace_path("tds_solve_dual", dir, ctx->cfg.nproc_dir[dir - 1], rc != X3D2C_EUNSUPPORTED);
     if (rc != X3D2C_EUNSUPPORTED) return rc;
@@ -496,7 +496,7 @@ int x3d2c_tds_solve_axpy(x3d2c_ctx* ctx, int dir, double* y, double a, const dou
   X3D2C_REQUIRE(dir >= 1 && dir <= 3, "x3d2c_tds_solve_axpy: dir must be DIR_X/Y/Z");
   X3D2C_REQUIRE(y != in, "x3d2c_tds_solve_axpy: y and in must be different fields");
   if (!ctx->strict) {
-    int rc = tds_m4(ctx, dir, 3, y, nullptr, in, y, op, op, a);
+    int rc = tds_m4(ctx, dir, 3, y, nullptr, in, y, op, op, a, dir, dir);
     if (rc == X3D2C_EUNSUPPORTED) rc = tds_pair_m3(ctx, dir, 2, y, nullptr, in, y, op, op, a);
     trace_path("tds_solve_axpy", dir, ctx->cfg.nproc_dir[dir - 1], rc != X3D2C_EUNSUPPORTED);
     if (rc != X3D2C_EUNSUPPORTED) return rc;

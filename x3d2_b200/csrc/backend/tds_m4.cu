@@ -18,7 +18,7 @@ enum Mode { SINGLE = 0, SUM = 1, DUAL = 2, AXPY = 3 };
 struct TdsParams4 {
   CUtensorMap in_a, in_b;    // SUM: two inputs; AXPY: in_b = y
   CUtensorMap out_a, out_b;  // DUAL: two outputs; AXPY: out_a = y
-  int tiles;
+  int tiles, nb;  // tile coordinates: (lane0, 0, 0, group % nb, group / nb)
   Op oa, ob;
 };
 
@@ -62,8 +62,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) tds_m4_kernel(const __grid_const
     const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
     const unsigned bar = buf ? bar1 : bar0;
     mbar_expect_tx(bar, NLOAD * tile_bytes);
-    tma_load_4d(saddr(smem4 + buf * NSLOT * fd), &p.in_a, bar, l0, 0, 0, grp);
-    if (NLOAD == 2) tma_load_4d(saddr(smem4 + (buf * NSLOT + 1) * fd), &p.in_b, bar, l0, 0, 0, grp);
+    const int c4 = grp / p.nb, c3 = grp - c4 * p.nb;
+    tma_load_5d(saddr(smem4 + buf * NSLOT * fd), &p.in_a, bar, l0, 0, 0, c3, c4);
+    if (NLOAD == 2) tma_load_5d(saddr(smem4 + (buf * NSLOT + 1) * fd), &p.in_b, bar, l0, 0, 0, c3, c4);
   };
   if (tid == 0) {
     mbar_init(bar0, 1);
@@ -116,8 +117,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) tds_m4_kernel(const __grid_const
     __syncthreads();
     if (tid == 0) {
       const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
-      tma_store_4d(&p.out_a, saddr(smem4 + (MODE == AXPY ? F1 : F0)), l0, 0, 0, grp);
-      if (MODE == DUAL) tma_store_4d(&p.out_b, saddr(smem4 + F1), l0, 0, 0, grp);
+      const int c4 = grp / p.nb, c3 = grp - c4 * p.nb;
+      tma_store_5d(&p.out_a, saddr(smem4 + (MODE == AXPY ? F1 : F0)), l0, 0, 0, c3, c4);
+      if (MODE == DUAL) tma_store_5d(&p.out_b, saddr(smem4 + F1), l0, 0, 0, c3, c4);
       tma_commit();
       const int nn = tile + 2 * gridDim.x;
       if (nn < p.tiles) {
@@ -184,9 +186,11 @@ int dispatch_shape(x3d2c_ctx* ctx, const TdsParams4& p, int L, int NT, unsigned 
 
 namespace x3d2c {
 
-// mode: 0 single (out_a = A(in_a)), 1 sum, 2 dual, 3 axpy (out_a = y, scale_a folded into A)
+// mode: 0 single (out_a = A(in_a)), 1 sum, 2 dual, 3 axpy (out_a = y, scale_a folded into A).
+// lay_in / lay_out: layout (DIR_*) in which the input / output fields are stored; different from `dir` when the
+// kernel reads or writes through a reorder (Y and Z lines, layouts Y, Z, C).
 int tds_m4(x3d2c_ctx* ctx, int dir, int mode, double* out_a, double* out_b, const double* in_a, const double* in_b,
-           const x3d2c_tdsops* ta, const x3d2c_tdsops* tb, double scale_a) {
+           const x3d2c_tdsops* ta, const x3d2c_tdsops* tb, double scale_a, int lay_in, int lay_out) {
   static const bool disabled = std::getenv("X3D2C_NO_TMA") != nullptr;
   if (disabled || ctx->cfg.nproc_dir[dir - 1] > 1 || ctx->force_dist) return X3D2C_EUNSUPPORTED;
   const int n = ta->n_tds;
@@ -197,11 +201,12 @@ int tds_m4(x3d2c_ctx* ctx, int dir, int mode, double* out_a, double* out_b, cons
   TdsParams4 p{};
   if (!make_op(ta, mode == AXPY ? scale_a : 1.0, false, &p.oa)) return X3D2C_EUNSUPPORTED;
   if (two_ops && !make_op(tb, 1.0, false, &p.ob)) return X3D2C_EUNSUPPORTED;
-  const int G = ctx->n_groups[dir], n_pad = ctx->n_pad(dir), nseg = n / S;
-  auto map = [&](CUtensorMap* m, const double* f) { return make_line_map(m, f, L, nseg, n_pad, G); };
-  if (!map(&p.in_a, in_a) || !map(&p.out_a, out_a)) return X3D2C_EUNSUPPORTED;
-  if ((mode == SUM || mode == AXPY) && !map(&p.in_b, in_b)) return X3D2C_EUNSUPPORTED;
-  if (mode == DUAL && !map(&p.out_b, out_b)) return X3D2C_EUNSUPPORTED;
+  const int G = ctx->n_groups[dir], nseg = n / S;
+  auto map = [&](CUtensorMap* m, const double* f, int layout) { return make_map5(m, f, layout, dir, L, nseg, ctx, &p.nb); };
+  if (!map(&p.in_a, in_a, lay_in) || !map(&p.out_a, out_a, lay_out)) return X3D2C_EUNSUPPORTED;
+  if (mode == SUM && !map(&p.in_b, in_b, lay_in)) return X3D2C_EUNSUPPORTED;
+  if (mode == AXPY && !map(&p.in_b, in_b, lay_out)) return X3D2C_EUNSUPPORTED;  // y
+  if (mode == DUAL && !map(&p.out_b, out_b, lay_out)) return X3D2C_EUNSUPPORTED;
   p.tiles = G * (SZ / L);
   const unsigned mask = two_ops ? (ta->tap_mask | tb->tap_mask) : ta->tap_mask;
   switch (mode) {

@@ -286,6 +286,33 @@ class Backend {  // cuda_c_backend_t: every method is one deferred procedure of 
     }
     X3D2H_CALL(x3d2c_tds_solve_dual(ctx, u.dir, oa.dev, ob.dev, u.dev, opa.h, opb.h));
   }
+  // ... through reorders (x3d2c.h): rdr_in brings the input(s) into DIR_`dir`, rdr_out takes the output(s) out of it
+  void check_r(int dir, const Field& in, const Field& out, int rdr_in, int rdr_out) {
+    if (in.dir != (rdr_in ? rdr_in / 10 : dir) || out.dir != (rdr_out ? rdr_out % 10 : dir))
+      fail("DIR mismatch between fields in tds_solve.");
+  }
+  void tds_solve_r(int dir, Field& out, const Field& u, const DevTdsops& op, int rdr_in, int rdr_out) {
+    check_r(dir, u, out, rdr_in, rdr_out);
+    if (u.data_loc != NULL_LOC) out.data_loc = move_data_loc(u.data_loc, dir, op.t.move);
+    X3D2H_CALL(x3d2c_tds_solve_r(ctx, dir, out.dev, u.dev, op.h, rdr_in, rdr_out));
+  }
+  void tds_solve_sum_r(int dir, Field& out, const Field& a, const DevTdsops& opa, const Field& b, const DevTdsops& opb,
+                       int rdr_in, int rdr_out) {
+    check_r(dir, a, out, rdr_in, rdr_out);
+    check_r(dir, b, out, rdr_in, rdr_out);
+    if (a.data_loc != NULL_LOC) out.data_loc = move_data_loc(a.data_loc, dir, opa.t.move);
+    X3D2H_CALL(x3d2c_tds_solve_sum_r(ctx, dir, out.dev, a.dev, opa.h, b.dev, opb.h, rdr_in, rdr_out));
+  }
+  void tds_solve_dual_r(int dir, Field& oa, Field& ob, const Field& u, const DevTdsops& opa, const DevTdsops& opb,
+                        int rdr_in, int rdr_out) {
+    check_r(dir, u, oa, rdr_in, rdr_out);
+    check_r(dir, u, ob, rdr_in, rdr_out);
+    if (u.data_loc != NULL_LOC) {
+      oa.data_loc = move_data_loc(u.data_loc, dir, opa.t.move);
+      ob.data_loc = move_data_loc(u.data_loc, dir, opb.t.move);
+    }
+    X3D2H_CALL(x3d2c_tds_solve_dual_r(ctx, dir, oa.dev, ob.dev, u.dev, opa.h, opb.h, rdr_in, rdr_out));
+  }
   void tds_solve_axpy(Field& y, double a, const Field& u, const DevTdsops& op) {
     if (u.dir != y.dir) fail("DIR mismatch between fields in tds_solve.");
     X3D2H_CALL(x3d2c_tds_solve_axpy(ctx, u.dir, y.dev, a, u.dev, op.h));
@@ -534,7 +561,8 @@ class Sim {
 
   // vector_calculus.f90:142-246
   void divergence_v2c(Field& div_u, const Field& uu, const Field& vv, const Field& ww) {
-    if (div_u.dir != DIR_Z || uu.dir != DIR_X || vv.dir != DIR_X || ww.dir != DIR_X)
+    // div_u in DIR_Z as in the reference, or in DIR_C (then the z2c reorder of poisson_fft is part of the last solve)
+    if ((div_u.dir != DIR_Z && div_u.dir != DIR_C) || uu.dir != DIR_X || vv.dir != DIR_X || ww.dir != DIR_X)
       fail("Error in divergence_v2c input/output field dirs: output must be in DIR_Z, inputs must be in DIR_X layout.");
     Allocator& A = allocator;
     Field *du_x = A.get_block(DIR_X), *dv_x = A.get_block(DIR_X), *dw_x = A.get_block(DIR_X);
@@ -544,30 +572,28 @@ class Sim {
     Field *u_y = A.get_block(DIR_Y), *v_y = A.get_block(DIR_Y), *w_y = A.get_block(DIR_Y);
     backend.reorder(*u_y, *du_x, RDR_X2Y); backend.reorder(*v_y, *dv_x, RDR_X2Y); backend.reorder(*w_y, *dw_x, RDR_X2Y);
     A.release_block(du_x); A.release_block(dv_x); A.release_block(dw_x);
-    // du_y = interpl(u_y) + stagder(v_y); dw_y = interpl(w_y)   (:185-199: two tds_solve + vecadd, fused)
-    Field *du_y = A.get_block(DIR_Y), *dw_y = A.get_block(DIR_Y);
-    backend.tds_solve_sum(*du_y, *u_y, ydirps.interpl_v2p, *v_y, ydirps.stagder_v2p);
-    backend.tds_solve(*dw_y, *w_y, ydirps.interpl_v2p);
-    A.release_block(u_y); A.release_block(v_y); A.release_block(w_y);
+    // u_z = y2z(interpl(u_y) + stagder(v_y)); w_z = y2z(interpl(w_y))   (:185-203: tds_solve x3, vecadd, reorder x2)
     Field *u_z = A.get_block(DIR_Z), *w_z = A.get_block(DIR_Z);
-    backend.reorder(*u_z, *du_y, RDR_Y2Z); backend.reorder(*w_z, *dw_y, RDR_Y2Z);
-    A.release_block(du_y); A.release_block(dw_y);
+    backend.tds_solve_sum_r(DIR_Y, *u_z, *u_y, ydirps.interpl_v2p, *v_y, ydirps.stagder_v2p, 0, RDR_Y2Z);
+    backend.tds_solve_r(DIR_Y, *w_z, *w_y, ydirps.interpl_v2p, 0, RDR_Y2Z);
+    A.release_block(u_y); A.release_block(v_y); A.release_block(w_y);
     // div = interpl(u_z) + stagder(w_z)   (:205-214)
-    backend.tds_solve_sum(div_u, *u_z, zdirps.interpl_v2p, *w_z, zdirps.stagder_v2p);
+    backend.tds_solve_sum_r(DIR_Z, div_u, *u_z, zdirps.interpl_v2p, *w_z, zdirps.stagder_v2p, 0,
+                            div_u.dir == DIR_C ? RDR_Z2C : 0);
     A.release_block(u_z); A.release_block(w_z);
   }
 
   // vector_calculus.f90:248-332. With sub != nullptr the x stage subtracts the gradient from (sub[0], sub[1],
   // sub[2]) instead of writing it (the vecadd(-1, dpdx, 1, u) calls of solver.f90:296-298 fused into the last solve).
   void gradient_c2v(Field& dpdx, Field& dpdy, Field& dpdz, const Field& p, Field* const* sub = nullptr) {
-    if (dpdx.dir != DIR_X || dpdy.dir != DIR_X || dpdz.dir != DIR_X || p.dir != DIR_Z)
+    // p in DIR_Z as in the reference, or in DIR_C (then the c2z reorder of poisson_fft is part of the first solve)
+    if (dpdx.dir != DIR_X || dpdy.dir != DIR_X || dpdz.dir != DIR_X || (p.dir != DIR_Z && p.dir != DIR_C))
       fail("Error in gradient_c2v input/output field dirs: outputs must be in DIR_X, input must be in DIR_Z layout.");
     Allocator& A = allocator;
-    Field *p_sxy_z = A.get_block(DIR_Z), *dpdz_sxy_z = A.get_block(DIR_Z);
-    backend.tds_solve_dual(*p_sxy_z, *dpdz_sxy_z, p, zdirps.interpl_p2v, zdirps.stagder_p2v);
+    // (p_sxy_y, dpdz_sxy_y) = z2y(interpl(p), stagder(p))   (:275-285: tds_solve x2, reorder x2)
     Field *p_sxy_y = A.get_block(DIR_Y), *dpdz_sxy_y = A.get_block(DIR_Y);
-    backend.reorder(*p_sxy_y, *p_sxy_z, RDR_Z2Y); backend.reorder(*dpdz_sxy_y, *dpdz_sxy_z, RDR_Z2Y);
-    A.release_block(p_sxy_z); A.release_block(dpdz_sxy_z);
+    backend.tds_solve_dual_r(DIR_Z, *p_sxy_y, *dpdz_sxy_y, p, zdirps.interpl_p2v, zdirps.stagder_p2v,
+                             p.dir == DIR_C ? RDR_C2Z : 0, RDR_Z2Y);
     Field *p_sx_y = A.get_block(DIR_Y), *dpdy_sx_y = A.get_block(DIR_Y);
     backend.tds_solve_dual(*p_sx_y, *dpdy_sx_y, *p_sxy_y, ydirps.interpl_p2v, ydirps.stagder_p2v);
     A.release_block(p_sxy_y);
@@ -625,8 +651,15 @@ class Sim {
   }
 
   // solver.f90:653-678 + poisson_fft.f90:206-226
+  // both fields in DIR_Z as in the reference, or the same DIR_C field (solved in place, no reorders)
   void poisson_fft(Field& pressure, const Field& div_u) {
     if (!backend.poisson) fail("FFT Poisson solver is not initialised for these BCs");
+    if (pressure.dir == DIR_C && &pressure == &div_u) {
+      X3D2H_CALL(x3d2c_fft_forward(ctx, backend.poisson, pressure.dev));
+      X3D2H_CALL(x3d2c_fft_postprocess_000(ctx, backend.poisson));
+      X3D2H_CALL(x3d2c_fft_backward(ctx, backend.poisson, pressure.dev));
+      return;
+    }
     Field* p_temp = allocator.get_block(DIR_C);
     backend.reorder(*p_temp, div_u, RDR_Z2C);
     Field* temp = allocator.get_block(DIR_C);
@@ -641,11 +674,11 @@ class Sim {
   // solver.f90:693-739
   void pressure_correction(Field& uu, Field& vv, Field& ww) {
     Allocator& A = allocator;
-    Field* div_u = A.get_block(DIR_Z);
-    divergence_v2c(*div_u, uu, vv, ww);
-    Field* p = A.get_block(DIR_Z);
-    poisson_fft(*p, *div_u);
-    A.release_block(div_u);
+    // the Cartesian field of the FFT is written by the last solve of the divergence and read by the first solve of
+    // the gradient: no z2c / c2z passes (same values as the reference's sequence)
+    Field* p = A.get_block(DIR_C);
+    divergence_v2c(*p, uu, vv, ww);
+    poisson_fft(*p, *p);
     Field* vel[3] = {&uu, &vv, &ww};
     gradient_c2v(uu, vv, ww, *p, vel);  // u -= dpdx, v -= dpdy, w -= dpdz
     A.release_block(p);
