@@ -12,42 +12,60 @@
 //  * loads complete on an mbarrier (expect_tx = 3 tiles), stores are bulk-async groups; a buffer is reloaded as
 //    soon as its stores have read it (cp.async.bulk.wait_group.read), while the other buffer is being computed;
 //  * two CTAs x two buffers per SM as before (104 KB each).
-// Periodic, uniform, single-rank directions with n a power of two (64..2048) and the compact6 tap masks; everything
-// else uses transeq_m3.cu.
+//  * rank-split directions (DIST): the halo rows and the neighbouring ranks' carries (m3_edge.cu) are staged with
+//    cp.async by all threads and complete on the same mbarrier as the tensor loads; the first / last segment's
+//    threads read the rows beyond the line from that staging area.
+// Periodic, uniform directions with n a power of two (64..1024) and the compact6 tap masks; everything else uses
+// transeq_m3.cu.
 #include "m4_common.cuh"
 
 using namespace m4;
 
 namespace {
 
+constexpr int NS = 9;  // recurrences per tile: 3 fields x (d f, d(f conv), d2 f)
+
 struct Params4 {
   CUtensorMap in[3];   // in[0] is the line-aligned velocity (conv)
   CUtensorMap out[3];
   int tiles;
   Op o_du, o_dud, o_d2u;  // scaled by -1/2, -1/2, nu
+  // rank-split direction only: received halos (SZ, 4, 3, G) and carries (SZ, 3, 9, G)
+  const double *halo_s, *halo_e, *from_prev, *from_next;
 };
 
+// Halo staging (DIST): group j = (buffer * 3 + field) * 2 + side holds 4 rows of L lanes with row stride NT, so that
+// the window offsets of woff4 apply unchanged; nseg groups share one block of 4 x NT doubles.
+template <int L, int NT>
+__device__ __forceinline__ constexpr int stage_off(int j) {
+  return (j / (NT / L)) * 4 * NT + (j % (NT / L)) * L;
+}
+template <int L, int NT>
+struct Stage { static constexpr int doubles = ((12 + NT / L - 1) / (NT / L)) * 4 * NT; };
+
 // One velocity component of one tile. fF / fC: offsets of the field and conv tiles ([16][NT] each); cz: offset of the
-// carry arrays ze[3][NT], ys[3][NT].
-template <int L, int NT, bool SELF>
+// carry arrays ze[3][NT], ys[3][NT]. oFm / oCm: base of the four rows before the own segment (field / conv), oFp / oCp:
+// base of the four rows after it; xp / xn: neighbouring ranks' carries of this field's recurrences (DIST).
+template <int L, int NT, bool SELF, bool DIST>
 __device__ __forceinline__ void component4(const int fF, const int fC, const int cz, const Params4& p, const int q,
-                                           const int l, const int bm, const int b0, const int bp) {
+                                           const int l, const int b0, const int oFm, const int oCm, const int oFp,
+                                           const int oCp, const int xp, const int xn) {
   constexpr int nseg = NT / L;
   double z1[S], z2[S], z3[S];
   {
     double wf[9], wp[9];
+    auto load = [&](int t, double& f, double& pr) {  // window element t: row j0 - 4 + t
+      const int oF = t < 4 ? oFm + t * NT : (t < S + 4 ? fF + b0 + (t - 4) * NT : oFp + (t - S - 4) * NT);
+      const int oC = t < 4 ? oCm + t * NT : (t < S + 4 ? fC + b0 + (t - 4) * NT : oCp + (t - S - 4) * NT);
+      f = smem4[oF];
+      pr = f * (SELF ? f : smem4[oC]);
+    };
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int o = woff4<NT>(t, bm, b0, bp);
-      wf[t] = smem4[fF + o];
-      wp[t] = wf[t] * (SELF ? wf[t] : smem4[fC + o]);
-    }
+    for (int t = 0; t < 8; ++t) load(t, wf[t], wp[t]);
     double p1 = 0.0, p2 = 0.0, p3 = 0.0;
 #pragma unroll
     for (int k = 0; k < S; ++k) {
-      const int o = woff4<NT>(k + 8, bm, b0, bp);
-      wf[8] = smem4[fF + o];
-      wp[8] = wf[8] * (SELF ? wf[8] : smem4[fC + o]);
+      load(k + 8, wf[8], wp[8]);
       p1 = fma(p.o_du.a, p1, sten<0x6Cu>(p.o_du.cfw, wf));
       p2 = fma(p.o_dud.a, p2, sten<0x6Cu>(p.o_dud.cfw, wp));
       p3 = fma(p.o_d2u.a, p3, sten<0x7Cu>(p.o_d2u.cfw, wf));
@@ -74,18 +92,19 @@ __device__ __forceinline__ void component4(const int fF, const int fC, const int
   smem4[cz + 5 * NT + b0] = z3[0];
   __syncthreads();
   // carries(): the shared array of m3_common.cuh is the same dynamic shared memory as smem4
+  constexpr int xs = EXP_ROWS * L;
   {
     double zi, yi;
-    carries<L, false>(cz + 2 * NT + l, cz + 5 * NT + l, L, 0, 0, p.o_d2u, q, nseg, zi, yi);
+    carries<L, DIST>(cz + 2 * NT + l, cz + 5 * NT + l, L, xp + 2 * xs, xn + 2 * xs, p.o_d2u, q, nseg, zi, yi);
 #pragma unroll
     for (int k = 0; k < S; ++k) z3[k] = fma(p.o_d2u.Cp[k], yi, fma(p.o_d2u.W[k], zi, z3[k]));
-    carries<L, false>(cz + 1 * NT + l, cz + 4 * NT + l, L, 0, 0, p.o_dud, q, nseg, zi, yi);
+    carries<L, DIST>(cz + 1 * NT + l, cz + 4 * NT + l, L, xp + 1 * xs, xn + 1 * xs, p.o_dud, q, nseg, zi, yi);
 #pragma unroll
     for (int k = 0; k < S; ++k) z2[k] = fma(p.o_dud.Cp[k], yi, fma(p.o_dud.W[k], zi, z2[k])) + z3[k];
   }
   {
     double zi, yi;
-    carries<L, false>(cz + 0 * NT + l, cz + 3 * NT + l, L, 0, 0, p.o_du, q, nseg, zi, yi);
+    carries<L, DIST>(cz + 0 * NT + l, cz + 3 * NT + l, L, xp, xn, p.o_du, q, nseg, zi, yi);
 #pragma unroll
     for (int k = 0; k < S; ++k) {
       const double du = fma(p.o_du.Cp[k], yi, fma(p.o_du.W[k], zi, z1[k]));
@@ -96,30 +115,58 @@ __device__ __forceinline__ void component4(const int fF, const int fC, const int
   __syncthreads();     // the carries are overwritten by the next component; F is complete
 }
 
-template <int L, int NT>
+// shared memory: [2 buffers][3 fields][16][NT] | carries ze[3][NT], ys[3][NT] | 2 mbarriers (16 B)
+//                DIST: | halo staging (Stage::doubles) | neighbour carries [2 buffers][prev 27 rows | next 27 rows][L]
+template <int L, int NT, bool DIST>
 __global__ void __launch_bounds__(NT, 1) transeq_m4_kernel(const __grid_constant__ Params4 p) {
-  constexpr int nseg = NT / L, fd = S * NT, tpg = SZ / L;
-  constexpr int cz = 6 * fd;                       // carries
+  constexpr int nseg = NT / L, fd = S * NT, tpg = SZ / L, cpr = L / 2;
+  constexpr int cz = 6 * fd;                           // carries
+  constexpr int hs0 = cz + 6 * NT + 2;                 // halo staging (after the two mbarriers)
+  constexpr int xb0 = hs0 + Stage<L, NT>::doubles;    // neighbour carries
+  constexpr int xbuf = 2 * NS * EXP_ROWS * L;
   constexpr unsigned tile_bytes = fd * sizeof(double);
   const int tid = threadIdx.x, l = tid & (L - 1), q = tid / L;
   const int b0 = tid, bm = tid - L + (q == 0 ? NT : 0), bp = tid + L - (q == nseg - 1 ? NT : 0);
   const unsigned bar0 = saddr(smem4 + cz + 6 * NT), bar1 = bar0 + 8;
-  auto issue_loads = [&](int buf, int tile) {
+  auto issue_loads = [&](int buf, int tile) {  // thread 0
     const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
     const unsigned bar = buf ? bar1 : bar0;
     mbar_expect_tx(bar, 3 * tile_bytes);
 #pragma unroll
     for (int f = 0; f < 3; ++f) tma_load_4d(saddr(smem4 + (3 * buf + f) * fd), &p.in[f], bar, l0, 0, 0, grp);
   };
+  auto stage_neighbours = [&](int buf, int tile) {  // all threads: halo rows and neighbour carries of one tile
+    const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
+    for (int idx = tid; idx < (24 + 2 * NS * EXP_ROWS) * cpr; idx += NT) {
+      const int row = idx / cpr, c = 2 * (idx - row * cpr);
+      if (row < 24) {
+        const int f = row >> 3, side = (row >> 2) & 1, r = row & 3;
+        const double* src = (side ? p.halo_e : p.halo_s) + ((size_t)(grp * 3 + f) * 4 + r) * SZ + l0 + c;
+        cp_async16(smem4 + hs0 + stage_off<L, NT>((buf * 3 + f) * 2 + side) + r * NT + c, src);
+      } else {
+        const int e = row - 24, second = e >= NS * EXP_ROWS, rr = e - second * NS * EXP_ROWS;
+        const double* src = (second ? p.from_next : p.from_prev) + ((size_t)grp * NS * EXP_ROWS + rr) * SZ + l0 + c;
+        cp_async16(smem4 + xb0 + buf * xbuf + e * L + c, src);
+      }
+    }
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(buf ? bar1 : bar0) : "memory");
+  };
   if (tid == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar1, 1);
+    mbar_init(bar0, DIST ? 1 + NT : 1);
+    mbar_init(bar1, DIST ? 1 + NT : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid == 0) {
-    issue_loads(0, blockIdx.x);
-    if ((int)(blockIdx.x + gridDim.x) < p.tiles) issue_loads(1, blockIdx.x + gridDim.x);
+  {
+    const int t1 = blockIdx.x + gridDim.x;
+    if (tid == 0) {
+      issue_loads(0, blockIdx.x);
+      if (t1 < p.tiles) issue_loads(1, t1);
+    }
+    if (DIST) {
+      stage_neighbours(0, blockIdx.x);
+      if (t1 < p.tiles) stage_neighbours(1, t1);
+    }
   }
   int it = 0;
   for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
@@ -135,15 +182,28 @@ __global__ void __launch_bounds__(NT, 1) transeq_m4_kernel(const __grid_constant
         tma_commit();
       }
     };
-    component4<L, NT, false>(bo + 1 * fd, bo, cz, p, q, l, bm, b0, bp);
+    // rows before / after the own segment: the neighbouring segment, or (first / last segment of a rank-split line)
+    // the staged halo rows
+    auto before = [&](int f) {
+      return (DIST && q == 0) ? hs0 + stage_off<L, NT>((buf * 3 + f) * 2) + l : bo + f * fd + bm + (S - 4) * NT;
+    };
+    auto after = [&](int f) {
+      return (DIST && q == nseg - 1) ? hs0 + stage_off<L, NT>((buf * 3 + f) * 2 + 1) + l : bo + f * fd + bp;
+    };
+    const int xp = xb0 + buf * xbuf + l, xn = xp + NS * EXP_ROWS * L;
+    constexpr int xf = 3 * EXP_ROWS * L;  // three recurrences per field
+    const int m0 = before(0), a0 = after(0);
+    component4<L, NT, false, DIST>(bo + 1 * fd, bo, cz, p, q, l, b0, before(1), m0, after(1), a0, xp + xf, xn + xf);
     store_field(1);
-    component4<L, NT, false>(bo + 2 * fd, bo, cz, p, q, l, bm, b0, bp);
+    component4<L, NT, false, DIST>(bo + 2 * fd, bo, cz, p, q, l, b0, before(2), m0, after(2), a0, xp + 2 * xf,
+                                   xn + 2 * xf);
     store_field(2);
-    component4<L, NT, true>(bo, bo, cz, p, q, l, bm, b0, bp);
+    component4<L, NT, true, DIST>(bo, bo, cz, p, q, l, b0, m0, m0, a0, a0, xp, xn);
     store_field(0);
-    if (tid == 0) {
-      const int nn = tile + 2 * gridDim.x;
-      if (nn < p.tiles) {
+    const int nn = tile + 2 * gridDim.x;
+    if (nn < p.tiles) {
+      if (DIST) stage_neighbours(buf, nn);  // the staging areas of this buffer are free (barrier of component 3)
+      if (tid == 0) {
         tma_wait_read();  // the stores have read this buffer
         issue_loads(buf, nn);
       }
@@ -153,20 +213,33 @@ __global__ void __launch_bounds__(NT, 1) transeq_m4_kernel(const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-template <int L, int NT>
+template <int L, int NT, bool DIST>
 int launch4(x3d2c_ctx* ctx, const Params4& p) {
-  constexpr size_t smem = sizeof(double) * (6 * S * NT + 6 * NT) + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    X3D2C_CHECK_CUDA(cudaFuncSetAttribute(transeq_m4_kernel<L, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  constexpr size_t smem = sizeof(double) * (6 * S * NT + 6 * NT + 2 +
+                                            (DIST ? Stage<L, NT>::doubles + 2 * 2 * NS * EXP_ROWS * L : 0));
+  static int per_sm = 0;
+  if (!per_sm) {
+    X3D2C_CHECK_CUDA(cudaFuncSetAttribute(transeq_m4_kernel<L, NT, DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
-    attr_set = true;
+    X3D2C_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, transeq_m4_kernel<L, NT, DIST>, NT, smem));
+    if (per_sm < 1) per_sm = 1;
   }
-  int grid = num_sms(ctx) * (256 / NT);
+  int grid = num_sms(ctx) * per_sm;
   if (grid > p.tiles) grid = p.tiles;
-  transeq_m4_kernel<L, NT><<<grid, NT, smem, ctx->stream>>>(p);
+  transeq_m4_kernel<L, NT, DIST><<<grid, NT, smem, ctx->stream>>>(p);
   X3D2C_CHECK_LAUNCH(ctx);
   return X3D2C_OK;
+}
+
+// rank-split lines want smaller tiles: the staging areas must fit next to two (or three) CTAs' buffers
+bool dist_shape(int n, int* L, int* NT) {
+  switch (n) {
+    case 128: *L = 8; *NT = 64; return true;
+    case 256: *L = 4; *NT = 64; return true;
+    case 512: *L = 4; *NT = 128; return true;
+    case 1024: *L = 4; *NT = 256; return true;
+    default: return false;
+  }
 }
 
 }  // namespace
@@ -177,15 +250,17 @@ int transeq_m4(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, cons
                const double* w, double nu, const x3d2c_tdsops* der1st, const x3d2c_tdsops* der1st_sym,
                const x3d2c_tdsops* der2nd, const x3d2c_tdsops* der2nd_sym) {
   static const bool disabled = std::getenv("X3D2C_NO_TMA") != nullptr;
-  if (disabled || ctx->cfg.nproc_dir[dir - 1] > 1 || ctx->force_dist) return X3D2C_EUNSUPPORTED;
+  if (disabled) return X3D2C_EUNSUPPORTED;
   if (!same_tables(der1st, der1st_sym) || !same_tables(der2nd, der2nd_sym)) return X3D2C_EUNSUPPORTED;
   if (der1st->tap_mask != 0x6Cu || der2nd->tap_mask != 0x7Cu) return X3D2C_EUNSUPPORTED;
   const int n = der1st->n_tds, nseg = n / S;
+  const bool split = ctx->cfg.nproc_dir[dir - 1] > 1 || ctx->force_dist;
+  if (split && !dist_supported(ctx, dir, n)) return X3D2C_EUNSUPPORTED;
   int L = 0, NT = 0;
-  if (!tile_shape(n, &L, &NT)) return X3D2C_EUNSUPPORTED;
+  if (!(split ? dist_shape(n, &L, &NT) : tile_shape(n, &L, &NT))) return X3D2C_EUNSUPPORTED;
   Params4 p{};
-  if (!make_op(der1st, -0.5, false, &p.o_du) || !make_op(der1st, -0.5, false, &p.o_dud) ||
-      !make_op(der2nd, nu, false, &p.o_d2u))
+  if (!make_op(der1st, -0.5, split, &p.o_du) || !make_op(der1st, -0.5, split, &p.o_dud) ||
+      !make_op(der2nd, nu, split, &p.o_d2u))
     return X3D2C_EUNSUPPORTED;
   const double* in[3];
   double* out[3];
@@ -197,11 +272,34 @@ int transeq_m4(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, cons
     if (!make_line_map(&p.in[f], in[f], L, nseg, n_pad, G) || !make_line_map(&p.out[f], out[f], L, nseg, n_pad, G))
       return X3D2C_EUNSUPPORTED;
   p.tiles = G * (SZ / L);
-  if (L == 32) return launch4<32, 128>(ctx, p);
-  if (L == 16) return launch4<16, 128>(ctx, p);
-  if (L == 8) return launch4<8, 128>(ctx, p);
-  if (NT == 128) return launch4<4, 128>(ctx, p);
-  return launch4<4, 256>(ctx, p);
+  if (!split) {
+    if (L == 32) return launch4<32, 128, false>(ctx, p);
+    if (L == 16) return launch4<16, 128, false>(ctx, p);
+    if (L == 8) return launch4<8, 128, false>(ctx, p);
+    if (NT == 128) return launch4<4, 128, false>(ctx, p);
+    return launch4<4, 256, false>(ctx, p);
+  }
+  // rank-split direction: halos and boundary carries first (m3_edge.cu), then the main kernel
+  const DistBufs b = carve_dist(ctx);
+  EdgeParams ep{};
+  ep.n = n;
+  ep.n_pad = n_pad;
+  ep.nseg = nseg;
+  ep.ns = NS;
+  ep.transeq = 1;
+  ep.ops[0] = p.o_du;
+  ep.ops[1] = p.o_dud;
+  ep.ops[2] = p.o_d2u;
+  for (int f = 0; f < 3; ++f) ep.f[f] = in[f];
+  int rc = exchange_edges(ctx, dir, in, 3, ep, b);
+  if (rc) return rc;
+  p.halo_s = b.halo_recv_s;
+  p.halo_e = b.halo_recv_e;
+  p.from_prev = b.carr_from_prev;
+  p.from_next = b.carr_from_next;
+  if (NT == 64) return L == 8 ? launch4<8, 64, true>(ctx, p) : launch4<4, 64, true>(ctx, p);
+  if (NT == 128) return launch4<4, 128, true>(ctx, p);
+  return launch4<4, 256, true>(ctx, p);
 }
 
 }  // namespace x3d2c
