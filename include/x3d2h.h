@@ -83,6 +83,10 @@ int x3d2h_tds_solve(x3d2h_sim* sim, int dir, const char* opname, int in_loc, con
  * out_b = B(in_a); "axpy": out_a = in_b + a A(in_a) (in_b has the output's extents) */
 int x3d2h_tds_fused(x3d2h_sim* sim, const char* mode, int dir, const char* op_a, const char* op_b, int in_loc,
                     int out_loc, const double* in_a, const double* in_b, double a, double* out_a, double* out_b);
+/* x3d2c_tds_solve_r / _sum_r / _dual_r on host data (mode "single" | "sum" | "dual"); rdr_in / rdr_out: 0 or RDR codes */
+int x3d2h_tds_fused_r(x3d2h_sim* sim, const char* mode, int dir, const char* op_a, const char* op_b, int in_loc,
+                      int out_loc, int rdr_in, int rdr_out, const double* in_a, const double* in_b, double* out_a,
+                      double* out_b);
 int x3d2h_divergence(x3d2h_sim* sim, const double* u, const double* v, const double* w, double* div);
 int x3d2h_gradient(x3d2h_sim* sim, const double* p, double* gx, double* gy, double* gz);
 int x3d2h_curl(x3d2h_sim* sim, const double* u, const double* v, const double* w, double* ox, double* oy, double* oz);

@@ -100,3 +100,30 @@ def test_fused_tds_combinations(oracle, x3d2, dims, bcs, env, strict, monkeypatc
         e = -1.0 * ref.tds_solve(d, "stagder_p2v", c, 1110) + y
         assert rel(sim.tds_fused("axpy", d, "stagder_p2v", None, c, y, a=-1.0, in_loc=1110), e) <= tol, ("axpy", d)
     sim.close()
+
+
+RDR_CASES = [(2, 0, 23), (2, 0, 24), (2, 32, 0), (2, 42, 23), (3, 43, 0), (3, 23, 0), (3, 0, 34), (3, 43, 32),
+             (1, 0, 12), (1, 21, 13)]  # (dir, rdr_in, rdr_out); the X cases always run as reorder + operator sequences
+
+
+@pytest.mark.parametrize("dims,bcs", [((128, 64, 256), None), ((96, 64, 80), None), ((65, 64, 64), ((2, 2), (0, 0), (1, 1)))])
+@pytest.mark.parametrize("strict", [False, True], ids=["fast", "strict"])
+def test_tds_through_reorders(oracle, x3d2, dims, bcs, strict):
+    """x3d2c_tds_solve_r / _sum_r / _dual_r == reorder -> operator(s) -> reorder. Host arrays are Cartesian, so the
+    reorders are invisible in the result: it must equal the plain operator (tensor-map path, sequence fallback)."""
+    kw = dict(bcs=bcs) if bcs else {}
+    sim, ref = x3d2.Sim(dims, strict=strict, **kw), oracle.World(dims, **kw)
+    tol = 0 if strict else TOL
+    u, v = rnd(sim.shape(), 21), rnd(sim.shape(), 22)
+    c = rnd(sim.shape(1110), 23)
+    for d, rin, rout in RDR_CASES:
+        e1 = ref.tds_solve(d, "interpl_v2p", u)
+        assert rel(sim.tds_fused_r("single", d, "interpl_v2p", None, u, rdr_in=rin, rdr_out=rout), e1) <= tol, (d, rin, rout)
+        e2 = e1 + ref.tds_solve(d, "stagder_v2p", v)
+        assert rel(sim.tds_fused_r("sum", d, "interpl_v2p", "stagder_v2p", u, v, rdr_in=rin, rdr_out=rout), e2) <= tol
+        ga, gb = sim.tds_fused_r("dual", d, "interpl_p2v", "stagder_p2v", c, rdr_in=rin, rdr_out=rout, in_loc=1110)
+        assert rel(ga, ref.tds_solve(d, "interpl_p2v", c, 1110)) <= tol, ("dual a", d, rin, rout)
+        assert rel(gb, ref.tds_solve(d, "stagder_p2v", c, 1110)) <= tol, ("dual b", d, rin, rout)
+    with pytest.raises(RuntimeError, match="rdr_out must be a reorder code that starts from dir"):
+        sim.tds_fused_r("single", 2, "interpl_v2p", None, u, rdr_out=34)
+    sim.close()

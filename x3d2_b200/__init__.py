@@ -224,6 +224,17 @@ class Sim:
                                      _p(a_in), _p(b_in), a, _p(oa), _p(ob)))
         return (oa, ob) if mode == "dual" else oa
 
+    def tds_fused_r(self, mode, dir, op_a, op_b, a_in, b_in=None, rdr_in=0, rdr_out=0, in_loc=VERT):
+        """x3d2c_tds_solve_r / _sum_r / _dual_r: reorder(rdr_in) -> operator(s) along `dir` -> reorder(rdr_out)."""
+        move = {"stagder_v2p": 1, "interpl_v2p": 1, "stagder_p2v": -1, "interpl_p2v": -1}.get(op_a, 0)
+        out_loc = in_loc + move * 10 ** dir
+        a_in = _f(a_in)
+        b_in = _f(b_in) if b_in is not None else a_in
+        oa, ob = self._out(out_loc), self._out(out_loc)
+        _chk(self._h.x3d2h_tds_fused_r(self.h, mode.encode(), dir, op_a.encode(), (op_b or op_a).encode(), in_loc,
+                                       out_loc, rdr_in, rdr_out, _p(a_in), _p(b_in), _p(oa), _p(ob)))
+        return (oa, ob) if mode == "dual" else oa
+
     def divergence(self, u, v, w):
         u, v, w = _f(u), _f(v), _f(w)
         d = self._out(CELL)

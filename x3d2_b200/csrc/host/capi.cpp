@@ -229,6 +229,30 @@ int x3d2h_tds_fused(x3d2h_sim* sim, const char* mode, int dir, const char* op_a,
   }
   H_CATCH
 }
+int x3d2h_tds_fused_r(x3d2h_sim* sim, const char* mode, int dir, const char* op_a, const char* op_b, int in_loc,
+                      int out_loc, int rdr_in, int rdr_out, const double* in_a, const double* in_b, double* out_a,
+                      double* out_b) {
+  H_TRY
+  Sim& S = *sim->s;
+  Tmp t(S.allocator);
+  const std::string m = mode;
+  const int din = rdr_in ? rdr_in / 10 : dir, dout = rdr_out ? rdr_out % 10 : dir;
+  Field *fa = t.get(din), *fb = t.get(din), *oa = t.get(dout), *ob = t.get(dout);
+  S.set_field(*fa, in_a, in_loc);
+  if (m == "single") {
+    S.backend.tds_solve_r(dir, *oa, *fa, S.pick(dir, op_a), rdr_in, rdr_out);
+  } else if (m == "sum") {
+    S.set_field(*fb, in_b, in_loc);
+    S.backend.tds_solve_sum_r(dir, *oa, *fa, S.pick(dir, op_a), *fb, S.pick(dir, op_b), rdr_in, rdr_out);
+  } else if (m == "dual") {
+    S.backend.tds_solve_dual_r(dir, *oa, *ob, *fa, S.pick(dir, op_a), S.pick(dir, op_b), rdr_in, rdr_out);
+    S.get_field(out_b, *ob, out_loc);
+  } else {
+    fail("x3d2h_tds_fused_r: mode must be single, sum or dual");
+  }
+  S.get_field(out_a, *oa, out_loc);
+  H_CATCH
+}
 int x3d2h_divergence(x3d2h_sim* sim, const double* u, const double* v, const double* w, double* div) {
   H_TRY
   Sim& S = *sim->s;
