@@ -33,7 +33,7 @@ def time_op(sim, op, reps, stream):
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 256
-    local = [int(a) for a in sys.argv[1].split(",")] if len(sys.argv) > 1 and "," in sys.argv[1] else [n, n, n]
+    grid = [int(a) for a in sys.argv[1].split(",")] if len(sys.argv) > 1 and "," in sys.argv[1] else [n, n, n]
     strict = "--strict" in sys.argv
     peak = 6541.8
     try:
@@ -53,13 +53,13 @@ def main():
             assert X.load()[0].x3d2c_nccl_unique_id(raw) == 0
             buf = [raw.raw]
         dist.broadcast_object_list(buf, src=0)
-        sim = X.Sim((local[0], local[1], local[2] * world), nproc_dir=(1, 1, world), rank=rank, nproc=world, device=local, strict=strict,
+        sim = X.Sim((grid[0], grid[1], grid[2] * world), nproc_dir=(1, 1, world), rank=rank, nproc=world, device=local, strict=strict,
                     nccl_unique_id=buf[0])
     else:
-        sim = X.Sim(tuple(local), strict=strict)
+        sim = X.Sim(tuple(grid), strict=strict)
     sim.init_tgv()
     stream = torch.cuda.ExternalStream(sim.stream())
-    npts = local[0] * local[1] * local[2]
+    npts = grid[0] * grid[1] * grid[2]
     rows = []
     only = [a.split("=", 1)[1].split(",") for a in sys.argv if a.startswith("--ops=")]
     for op, b in BYTES_PER_PT.items():
@@ -71,7 +71,7 @@ def main():
         if rank == 0:
             print(f"{op:22s} {ms:9.3f} ms  {gbs:9.1f} GB/s  {100 * gbs / peak:6.1f}% of measured {peak:.0f} GB/s", flush=True)
     if rank == 0:
-        print(f"local grid {local} per rank, ranks={world}, strict={strict}")
+        print(f"local grid {grid} per rank, ranks={world}, strict={strict}")
     sim.close()
 
 
