@@ -161,6 +161,8 @@ int x3d2c_tds_solve_dual_r(x3d2c_ctx* ctx, int dir, double* out_a, double* out_b
 
 /* ---- reorder (src/backend/backend.f90:128-144), rdr is one of X3D2C_RDR_* */
 int x3d2c_reorder(x3d2c_ctx* ctx, int rdr, double* dst, const double* src);
+/* extension: reorder(dst_y, src, RDR_X2Y) and reorder(dst_z, src, RDR_X2Z) with one read of src */
+int x3d2c_reorder_x2yz(x3d2c_ctx* ctx, double* dst_y, double* dst_z, const double* src);
 /* ---- sum_yintox / sum_zintox (src/backend/backend.f90:146-159): u (DIR_X) += reorder(u_) */
 int x3d2c_sum_yintox(x3d2c_ctx* ctx, double* u, const double* u_y);
 int x3d2c_sum_zintox(x3d2c_ctx* ctx, double* u, const double* u_z);

@@ -106,11 +106,15 @@ RDR_CASES = [(2, 0, 23), (2, 0, 24), (2, 32, 0), (2, 42, 23), (3, 43, 0), (3, 23
              (1, 0, 12), (1, 21, 13)]  # (dir, rdr_in, rdr_out); the X cases always run as reorder + operator sequences
 
 
-@pytest.mark.parametrize("dims,bcs", [((128, 64, 256), None), ((96, 64, 80), None), ((65, 64, 64), ((2, 2), (0, 0), (1, 1)))])
+@pytest.mark.parametrize("dims,bcs,env", [((128, 64, 256), None, {}), ((128, 128, 256), None, {"X3D2C_FORCE_DIST": "1"}),
+                                          ((96, 64, 80), None, {}), ((65, 64, 64), ((2, 2), (0, 0), (1, 1)), {})])
 @pytest.mark.parametrize("strict", [False, True], ids=["fast", "strict"])
-def test_tds_through_reorders(oracle, x3d2, dims, bcs, strict):
+def test_tds_through_reorders(oracle, x3d2, dims, bcs, env, strict, monkeypatch):
     """x3d2c_tds_solve_r / _sum_r / _dual_r == reorder -> operator(s) -> reorder. Host arrays are Cartesian, so the
-    reorders are invisible in the result: it must equal the plain operator (tensor-map path, sequence fallback)."""
+    reorders are invisible in the result: it must equal the plain operator (tensor-map path, rank-split kernels with
+    explicit input reorders, sequence fallback)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     kw = dict(bcs=bcs) if bcs else {}
     sim, ref = x3d2.Sim(dims, strict=strict, **kw), oracle.World(dims, **kw)
     tol = 0 if strict else TOL

@@ -59,6 +59,27 @@ reorder_tile_kernel(double* __restrict__ dst, const double* __restrict__ src, co
   }
 }
 
+// dst_y = reorder_x2y(src), dst_z = reorder_x2z(src): the source tile is read once (transeq_default reorders u, v, w
+// into both pencil layouts, src/solver.f90:325-327,355-357). Both destinations have x_l fastest.
+__global__ void __launch_bounds__(256)
+reorder_x2yz_kernel(double* __restrict__ dst_y, double* __restrict__ dst_z, const double* __restrict__ src, const Lay ls,
+                    const Lay ly, const Lay lz) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const long long bs = blockIdx.x * ls.sxb + blockIdx.y * ls.syb + blockIdx.z * ls.sz;
+  const long long by = blockIdx.x * ly.sxb + blockIdx.y * ly.syb + blockIdx.z * ly.sz;
+  const long long bz = blockIdx.x * lz.sxb + blockIdx.y * lz.syb + blockIdx.z * lz.sz;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) tile[ty + 8 * r][tx] = src[bs + tx * ls.syl + (ty + 8 * r) * ls.sxl];  // [x_l][y_l]
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const double t = tile[tx][ty + 8 * r];  // x_l = tx, y_l = ty + 8 r
+    dst_y[by + tx * ly.sxl + (ty + 8 * r) * ly.syl] = t;
+    dst_z[bz + tx * lz.sxl + (ty + 8 * r) * lz.syl] = t;
+  }
+}
+
 // u (DIR_X) = (u + reorder(a)) + reorder(b): sum_yintox followed by sum_zintox in one pass over u
 // (same order of additions as the two reference calls, src/solver.f90:340-372).
 __global__ void __launch_bounds__(256)
@@ -112,6 +133,17 @@ int x3d2c_reorder(x3d2c_ctx* ctx, int rdr, double* dst, const double* src) {
   X3D2C_REQUIRE(from >= 1 && from <= 4 && to >= 1 && to <= 4 && from != to, "x3d2c_reorder: unknown RDR code");
   X3D2C_REQUIRE(ctx->nz_pad <= 65535, "x3d2c_reorder: nz exceeds the grid limit");
   return launch_reorder(ctx, from, to, dst, src, false);
+}
+
+int x3d2c_reorder_x2yz(x3d2c_ctx* ctx, double* dst_y, double* dst_z, const double* src) {
+  X3D2C_REQUIRE(ctx && dst_y && dst_z && src, "x3d2c_reorder_x2yz: null argument");
+  X3D2C_REQUIRE(dst_y != src && dst_z != src && dst_y != dst_z, "x3d2c_reorder_x2yz: fields must be distinct");
+  X3D2C_REQUIRE(ctx->nz_pad <= 65535, "x3d2c_reorder_x2yz: nz exceeds the grid limit");
+  const dim3 grid(ctx->nx_pad / SZ, ctx->ny_pad / SZ, ctx->nz_pad), block(32, 8);
+  reorder_x2yz_kernel<<<grid, block, 0, ctx->stream>>>(dst_y, dst_z, src, layout_of(ctx, X3D2C_DIR_X),
+                                                       layout_of(ctx, X3D2C_DIR_Y), layout_of(ctx, X3D2C_DIR_Z));
+  X3D2C_CHECK_LAUNCH(ctx);
+  return X3D2C_OK;
 }
 
 int x3d2c_sum_yintox(x3d2c_ctx* ctx, double* u, const double* u_y) {

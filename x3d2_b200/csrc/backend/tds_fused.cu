@@ -44,15 +44,19 @@ int run(x3d2c_ctx* ctx, const char* what, int dir, int mode, double* out_a, doub
   int lay_in, lay_out;
   int rc = layouts(dir, rdr_in, rdr_out, &lay_in, &lay_out);
   if (rc) return rc;
+  static const bool trace = std::getenv("X3D2C_TRACE") != nullptr;
+  auto report = [&](const char* how) {
+    if (trace) std::fprintf(stderr, "[x3d2c] %s dir=%d rdr_in=%d rdr_out=%d -> %s\n", what, dir, rdr_in, rdr_out, how);
+  };
   if (!ctx->strict && (rdr_in || rdr_out)) {
     rc = tds_m4(ctx, dir, mode, out_a, out_b, in_a, in_b, op_a, op_b, 1.0, lay_in, lay_out);
-    static const bool trace = std::getenv("X3D2C_TRACE") != nullptr;
-    if (trace)
-      std::fprintf(stderr, "[x3d2c] %s dir=%d rdr_in=%d rdr_out=%d -> %s\n", what, dir, rdr_in, rdr_out,
-                   rc == X3D2C_EUNSUPPORTED ? "reorder + operator sequence" : "through the tensor map");
-    if (rc != X3D2C_EUNSUPPORTED) return rc;
+    if (rc != X3D2C_EUNSUPPORTED) {
+      report("through the tensor maps");
+      return rc;
+    }
   }
-  // the sequence itself
+  // the sequence itself; the output side can still go through the tensor map (rank-split directions need their
+  // inputs in the direction's own layout)
   if ((rc = ensure_scratch(ctx, 6))) return rc;
   const double *a = in_a, *b = in_b;
   if (rdr_in) {
@@ -63,6 +67,14 @@ int run(x3d2c_ctx* ctx, const char* what, int dir, int mode, double* out_a, doub
       b = ctx->scratch[3];
     }
   }
+  if (!ctx->strict && rdr_out) {
+    rc = tds_m4(ctx, dir, mode, out_a, out_b, a, b, op_a, op_b, 1.0, dir, lay_out);
+    if (rc != X3D2C_EUNSUPPORTED) {
+      report(rdr_in ? "input reorder, then output through the tensor map" : "output through the tensor map");
+      return rc;
+    }
+  }
+  if (rdr_in || rdr_out) report("reorder + operator sequence");
   double* oa = rdr_out ? ctx->scratch[4] : out_a;
   double* ob = rdr_out ? ctx->scratch[5] : out_b;
   if (mode == 0) rc = x3d2c_tds_solve(ctx, dir, oa, a, op_a);

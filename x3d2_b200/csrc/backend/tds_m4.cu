@@ -4,7 +4,9 @@
 //   SUM   : out   = A(in_a) + B(in_b)      24 B/pt
 //   DUAL  : out_a = A(in), out_b = B(in)   24 B/pt
 //   AXPY  : y     = y + a A(in)            24 B/pt
-// Periodic, uniform, single-rank directions with n = 64..512 a power of two; other shapes use the cp.async kernels.
+// Periodic, uniform directions with n = 64..512 a power of two; other shapes use the cp.async kernels. Rank-split
+// directions (DIST) stage halo rows and neighbour carries with cp.async as transeq_m4.cu does; their inputs must be in
+// the direction's own layout (the halo pack and edge kernels read them), the outputs may go through a tensor map.
 // Measured at 512^3: tds_solve 0.395 -> 0.376 ms (87% of HBM peak) with 64-byte rows (L = 8, 256 threads); with
 // 32-byte rows (L = 4, 128 threads) the TMA version is slower (0.52 ms), so narrow tiles stay on the cp.async path.
 #include "m4_common.cuh"
@@ -20,18 +22,24 @@ struct TdsParams4 {
   CUtensorMap out_a, out_b;  // DUAL: two outputs; AXPY: out_a = y
   int tiles, nb;  // tile coordinates: (lane0, 0, 0, group % nb, group / nb)
   Op oa, ob;
+  // rank-split direction only: received halos (SZ, 4, NF, G) and carries (SZ, 3, NR, G)
+  const double *halo_s, *halo_e, *from_prev, *from_next;
 };
 
+// F: offset of the own rows' tile; om / op: base of the four rows before / after the own segment
 template <int NT, unsigned M>
-__device__ __forceinline__ void local_sweeps4(const int F, const Op& o, int bm, int b0, int bp, double (&z)[S],
-                                              double& ze) {
+__device__ __forceinline__ void local_sweeps4(const int F, const Op& o, const int om, const int b0, const int op,
+                                              double (&z)[S], double& ze) {
+  auto at = [&](int t) {  // window element t: row j0 - 4 + t
+    return smem4[t < 4 ? om + t * NT : (t < S + 4 ? F + b0 + (t - 4) * NT : op + (t - S - 4) * NT)];
+  };
   double wf[9];
 #pragma unroll
-  for (int t = 0; t < 8; ++t) wf[t] = smem4[F + woff4<NT>(t, bm, b0, bp)];
+  for (int t = 0; t < 8; ++t) wf[t] = at(t);
   double pz = 0.0;
 #pragma unroll
   for (int k = 0; k < S; ++k) {
-    wf[8] = smem4[F + woff4<NT>(k + 8, bm, b0, bp)];
+    wf[8] = at(k + 8);
     pz = fma(o.a, pz, sten<M>(o.cfw, wf));
     z[k] = pz;
 #pragma unroll
@@ -46,19 +54,33 @@ __device__ __forceinline__ void local_sweeps4(const int F, const Op& o, int bm, 
   }
 }
 
-// shared memory: [2 buffers][NSLOT tiles of 16 x NT] [NR x (ze, ys)[NT]] [2 mbarriers]
-template <int L, int NT, unsigned M, int MODE>
+template <int L, int NT, int MODE>
+struct Shape {
+  static constexpr int NSLOT = MODE == SINGLE ? 1 : 2;
+  static constexpr int NR = (MODE == SUM || MODE == DUAL) ? 2 : 1;     // recurrences
+  static constexpr int NLOAD = (MODE == SUM || MODE == AXPY) ? 2 : 1;  // tiles loaded
+  static constexpr int NF = MODE == SUM ? 2 : 1;                       // fields with halos
+  static constexpr int nseg = NT / L;
+  static constexpr int cz = 2 * NSLOT * S * NT;                        // carries
+  static constexpr int hs0 = cz + 2 * NR * NT + 2;                     // halo staging (after the two mbarriers)
+  static constexpr int stage = ((4 * NF + nseg - 1) / nseg) * 4 * NT;  // groups (buffer, field, side) of 4 rows x L
+  static constexpr int xb0 = hs0 + stage;                              // neighbour carries
+  static constexpr int xbuf = 2 * NR * EXP_ROWS * L;
+  static constexpr size_t smem(bool dist) { return sizeof(double) * (dist ? xb0 + 2 * xbuf : hs0); }
+  static __device__ __forceinline__ int stage_off(int j) { return hs0 + (j / nseg) * 4 * NT + (j % nseg) * L; }
+};
+
+// shared memory: [2 buffers][NSLOT tiles of 16 x NT] | NR x (ze, ys)[NT] | 2 mbarriers | DIST: halo staging, carries
+template <int L, int NT, unsigned M, int MODE, bool DIST>
 __global__ void __launch_bounds__(NT, 512 / NT) tds_m4_kernel(const __grid_constant__ TdsParams4 p) {
-  constexpr int nseg = NT / L, fd = S * NT, tpg = SZ / L;
-  constexpr int NSLOT = MODE == SINGLE ? 1 : 2;
-  constexpr int NR = (MODE == SUM || MODE == DUAL) ? 2 : 1;
-  constexpr int NLOAD = (MODE == SUM || MODE == AXPY) ? 2 : 1;
-  constexpr int cz = 2 * NSLOT * fd;
+  using Sh = Shape<L, NT, MODE>;
+  constexpr int nseg = Sh::nseg, fd = S * NT, tpg = SZ / L, cpr = L / 2;
+  constexpr int NSLOT = Sh::NSLOT, NR = Sh::NR, NLOAD = Sh::NLOAD, NF = Sh::NF, cz = Sh::cz;
   constexpr unsigned tile_bytes = fd * sizeof(double);
   const int tid = threadIdx.x, l = tid & (L - 1), q = tid / L;
   const int b0 = tid, bm = tid - L + (q == 0 ? NT : 0), bp = tid + L - (q == nseg - 1 ? NT : 0);
   const unsigned bar0 = saddr(smem4 + cz + 2 * NR * NT), bar1 = bar0 + 8;
-  auto issue_loads = [&](int buf, int tile) {
+  auto issue_loads = [&](int buf, int tile) {  // thread 0
     const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
     const unsigned bar = buf ? bar1 : bar0;
     mbar_expect_tx(bar, NLOAD * tile_bytes);
@@ -66,37 +88,70 @@ __global__ void __launch_bounds__(NT, 512 / NT) tds_m4_kernel(const __grid_const
     tma_load_5d(saddr(smem4 + buf * NSLOT * fd), &p.in_a, bar, l0, 0, 0, c3, c4);
     if (NLOAD == 2) tma_load_5d(saddr(smem4 + (buf * NSLOT + 1) * fd), &p.in_b, bar, l0, 0, 0, c3, c4);
   };
+  auto stage_neighbours = [&](int buf, int tile) {  // all threads
+    const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
+    for (int idx = tid; idx < (8 * NF + 2 * NR * EXP_ROWS) * cpr; idx += NT) {
+      const int row = idx / cpr, c = 2 * (idx - row * cpr);
+      if (row < 8 * NF) {
+        const int f = row >> 3, side = (row >> 2) & 1, r = row & 3;
+        const double* src = (side ? p.halo_e : p.halo_s) + ((size_t)(grp * NF + f) * 4 + r) * SZ + l0 + c;
+        cp_async16(smem4 + Sh::stage_off((buf * NF + f) * 2 + side) + r * NT + c, src);
+      } else {
+        const int e = row - 8 * NF, second = e >= NR * EXP_ROWS, rr = e - second * NR * EXP_ROWS;
+        const double* src = (second ? p.from_next : p.from_prev) + ((size_t)grp * NR * EXP_ROWS + rr) * SZ + l0 + c;
+        cp_async16(smem4 + Sh::xb0 + buf * Sh::xbuf + e * L + c, src);
+      }
+    }
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(buf ? bar1 : bar0) : "memory");
+  };
   if (tid == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar1, 1);
+    mbar_init(bar0, DIST ? 1 + NT : 1);
+    mbar_init(bar1, DIST ? 1 + NT : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid == 0) {
-    issue_loads(0, blockIdx.x);
-    if ((int)(blockIdx.x + gridDim.x) < p.tiles) issue_loads(1, blockIdx.x + gridDim.x);
+  {
+    const int t1 = blockIdx.x + gridDim.x;
+    if (tid == 0) {
+      issue_loads(0, blockIdx.x);
+      if (t1 < p.tiles) issue_loads(1, t1);
+    }
+    if (DIST) {
+      stage_neighbours(0, blockIdx.x);
+      if (t1 < p.tiles) stage_neighbours(1, t1);
+    }
   }
   int it = 0;
   for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
     const int buf = it & 1;
     mbar_wait(buf ? bar1 : bar0, (it >> 1) & 1);
     const int F0 = buf * NSLOT * fd, F1 = F0 + fd;
+    // rows before / after the own segment: the neighbouring segment or the staged halo rows (slot = field index)
+    auto before = [&](int F, int f) {
+      return (DIST && q == 0) ? Sh::stage_off((buf * NF + f) * 2) + l : F + bm + (S - 4) * NT;
+    };
+    auto after = [&](int F, int f) {
+      return (DIST && q == nseg - 1) ? Sh::stage_off((buf * NF + f) * 2 + 1) + l : F + bp;
+    };
     double za[S], zb[S], ze;
-    local_sweeps4<NT, M>(F0, p.oa, bm, b0, bp, za, ze);
+    local_sweeps4<NT, M>(F0, p.oa, before(F0, 0), b0, after(F0, 0), za, ze);
     smem4[cz + b0] = ze;
     smem4[cz + NT + b0] = za[0];
     if (NR == 2) {
-      local_sweeps4<NT, M>(MODE == SUM ? F1 : F0, p.ob, bm, b0, bp, zb, ze);
+      const int Fb = MODE == SUM ? F1 : F0, fb = MODE == SUM ? 1 : 0;
+      local_sweeps4<NT, M>(Fb, p.ob, before(Fb, fb), b0, after(Fb, fb), zb, ze);
       smem4[cz + 2 * NT + b0] = ze;
       smem4[cz + 3 * NT + b0] = zb[0];
     }
     __syncthreads();
+    const int xp = Sh::xb0 + buf * Sh::xbuf + l, xn = xp + NR * EXP_ROWS * L;
     double zin, yin;
-    carries<L, false>(cz + l, cz + NT + l, L, 0, 0, p.oa, q, nseg, zin, yin);
+    carries<L, DIST>(cz + l, cz + NT + l, L, xp, xn, p.oa, q, nseg, zin, yin);
 #pragma unroll
     for (int k = 0; k < S; ++k) za[k] = fma(p.oa.Cp[k], yin, fma(p.oa.W[k], zin, za[k]));
     if (NR == 2) {
-      carries<L, false>(cz + 2 * NT + l, cz + 3 * NT + l, L, 0, 0, p.ob, q, nseg, zin, yin);
+      carries<L, DIST>(cz + 2 * NT + l, cz + 3 * NT + l, L, xp + EXP_ROWS * L, xn + EXP_ROWS * L, p.ob, q, nseg, zin,
+                       yin);
 #pragma unroll
       for (int k = 0; k < S; ++k) zb[k] = fma(p.ob.Cp[k], yin, fma(p.ob.W[k], zin, zb[k]));
     }
@@ -115,13 +170,14 @@ __global__ void __launch_bounds__(NT, 512 / NT) tds_m4_kernel(const __grid_const
     }
     fence_async_smem();
     __syncthreads();
+    const int nn = tile + 2 * gridDim.x;
+    if (DIST && nn < p.tiles) stage_neighbours(buf, nn);  // the staging areas of this buffer are free
     if (tid == 0) {
       const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
       const int c4 = grp / p.nb, c3 = grp - c4 * p.nb;
       tma_store_5d(&p.out_a, saddr(smem4 + (MODE == AXPY ? F1 : F0)), l0, 0, 0, c3, c4);
       if (MODE == DUAL) tma_store_5d(&p.out_b, saddr(smem4 + F1), l0, 0, 0, c3, c4);
       tma_commit();
-      const int nn = tile + 2 * gridDim.x;
       if (nn < p.tiles) {
         tma_wait_read();  // the stores have read this buffer
         issue_loads(buf, nn);
@@ -132,32 +188,32 @@ __global__ void __launch_bounds__(NT, 512 / NT) tds_m4_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-template <int L, int NT, unsigned M, int MODE>
+template <int L, int NT, unsigned M, int MODE, bool DIST>
 int launch(x3d2c_ctx* ctx, const TdsParams4& p) {
-  constexpr int NSLOT = MODE == SINGLE ? 1 : 2, NR = (MODE == SUM || MODE == DUAL) ? 2 : 1;
-  constexpr size_t smem = sizeof(double) * (2 * NSLOT * S * NT + 2 * NR * NT) + 16;
+  constexpr size_t smem = Shape<L, NT, MODE>::smem(DIST);
   static int per_sm = 0;  // resident CTAs per SM (registers and shared memory), queried once
   if (!per_sm) {
-    X3D2C_CHECK_CUDA(cudaFuncSetAttribute(tds_m4_kernel<L, NT, M, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem));
-    X3D2C_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tds_m4_kernel<L, NT, M, MODE>, NT, smem));
+    X3D2C_CHECK_CUDA(cudaFuncSetAttribute(tds_m4_kernel<L, NT, M, MODE, DIST>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    X3D2C_CHECK_CUDA(
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tds_m4_kernel<L, NT, M, MODE, DIST>, NT, smem));
     if (per_sm < 1) per_sm = 1;
   }
   int grid = num_sms(ctx) * per_sm;
   if (grid > p.tiles) grid = p.tiles;
-  tds_m4_kernel<L, NT, M, MODE><<<grid, NT, smem, ctx->stream>>>(p);
+  tds_m4_kernel<L, NT, M, MODE, DIST><<<grid, NT, smem, ctx->stream>>>(p);
   X3D2C_CHECK_LAUNCH(ctx);
   return X3D2C_OK;
 }
 
-template <int L, int NT, int MODE>
+template <int L, int NT, int MODE, bool DIST>
 int dispatch_mask(x3d2c_ctx* ctx, const TdsParams4& p, unsigned mask) {
   switch (mask) {
-    case 0x78u: return launch<L, NT, 0x78u, MODE>(ctx, p);  // staggered derivative / interpolation v2p
-    case 0x3Cu: return launch<L, NT, 0x3Cu, MODE>(ctx, p);  // p2v
-    case 0x6Cu: if (MODE == SINGLE) return launch<L, NT, 0x6Cu, SINGLE>(ctx, p);  // first derivative
-    case 0x7Cu: if (MODE == SINGLE) return launch<L, NT, 0x7Cu, SINGLE>(ctx, p);  // second derivative
-    default: return launch<L, NT, 0x1FFu, MODE>(ctx, p);
+    case 0x78u: return launch<L, NT, 0x78u, MODE, DIST>(ctx, p);  // staggered derivative / interpolation v2p
+    case 0x3Cu: return launch<L, NT, 0x3Cu, MODE, DIST>(ctx, p);  // p2v
+    case 0x6Cu: if (MODE == SINGLE) return launch<L, NT, 0x6Cu, SINGLE, DIST>(ctx, p);  // first derivative
+    case 0x7Cu: if (MODE == SINGLE) return launch<L, NT, 0x7Cu, SINGLE, DIST>(ctx, p);  // second derivative
+    default: return launch<L, NT, 0x1FFu, MODE, DIST>(ctx, p);
   }
 }
 
@@ -172,13 +228,23 @@ bool tds_shape(int n, int* L, int* NT) {
   }
 }
 
-template <int MODE>
+template <int MODE, bool DIST>
 int dispatch_shape(x3d2c_ctx* ctx, const TdsParams4& p, int L, int NT, unsigned mask) {
-  if (NT == 128) return dispatch_mask<32, 128, MODE>(ctx, p, mask);
+  if (NT == 128) return dispatch_mask<32, 128, MODE, DIST>(ctx, p, mask);
   switch (L) {
-    case 8: return dispatch_mask<8, 256, MODE>(ctx, p, mask);
-    case 16: return dispatch_mask<16, 256, MODE>(ctx, p, mask);
-    default: return dispatch_mask<32, 256, MODE>(ctx, p, mask);
+    case 8: return dispatch_mask<8, 256, MODE, DIST>(ctx, p, mask);
+    case 16: return dispatch_mask<16, 256, MODE, DIST>(ctx, p, mask);
+    default: return dispatch_mask<32, 256, MODE, DIST>(ctx, p, mask);
+  }
+}
+
+template <bool DIST>
+int dispatch_mode(x3d2c_ctx* ctx, const TdsParams4& p, int mode, int L, int NT, unsigned mask) {
+  switch (mode) {
+    case SINGLE: return dispatch_shape<SINGLE, DIST>(ctx, p, L, NT, mask);
+    case SUM: return dispatch_shape<SUM, DIST>(ctx, p, L, NT, mask);
+    case DUAL: return dispatch_shape<DUAL, DIST>(ctx, p, L, NT, mask);
+    default: return dispatch_shape<AXPY, DIST>(ctx, p, L, NT, mask);
   }
 }
 
@@ -192,15 +258,17 @@ namespace x3d2c {
 int tds_m4(x3d2c_ctx* ctx, int dir, int mode, double* out_a, double* out_b, const double* in_a, const double* in_b,
            const x3d2c_tdsops* ta, const x3d2c_tdsops* tb, double scale_a, int lay_in, int lay_out) {
   static const bool disabled = std::getenv("X3D2C_NO_TMA") != nullptr;
-  if (disabled || ctx->cfg.nproc_dir[dir - 1] > 1 || ctx->force_dist) return X3D2C_EUNSUPPORTED;
+  if (disabled) return X3D2C_EUNSUPPORTED;
   const int n = ta->n_tds;
+  const bool split = ctx->cfg.nproc_dir[dir - 1] > 1 || ctx->force_dist;
+  if (split && (lay_in != dir || !dist_supported(ctx, dir, n))) return X3D2C_EUNSUPPORTED;
   int L = 0, NT = 0;
   if (!tds_shape(n, &L, &NT)) return X3D2C_EUNSUPPORTED;
   const bool two_ops = mode == SUM || mode == DUAL;
   if (two_ops && (tb->n_tds != n || tb->n_rhs != ta->n_rhs)) return X3D2C_EUNSUPPORTED;
   TdsParams4 p{};
-  if (!make_op(ta, mode == AXPY ? scale_a : 1.0, false, &p.oa)) return X3D2C_EUNSUPPORTED;
-  if (two_ops && !make_op(tb, 1.0, false, &p.ob)) return X3D2C_EUNSUPPORTED;
+  if (!make_op(ta, mode == AXPY ? scale_a : 1.0, split, &p.oa)) return X3D2C_EUNSUPPORTED;
+  if (two_ops && !make_op(tb, 1.0, split, &p.ob)) return X3D2C_EUNSUPPORTED;
   const int G = ctx->n_groups[dir], nseg = n / S;
   auto map = [&](CUtensorMap* m, const double* f, int layout) { return make_map5(m, f, layout, dir, L, nseg, ctx, &p.nb); };
   if (!map(&p.in_a, in_a, lay_in) || !map(&p.out_a, out_a, lay_out)) return X3D2C_EUNSUPPORTED;
@@ -209,12 +277,26 @@ int tds_m4(x3d2c_ctx* ctx, int dir, int mode, double* out_a, double* out_b, cons
   if (mode == DUAL && !map(&p.out_b, out_b, lay_out)) return X3D2C_EUNSUPPORTED;
   p.tiles = G * (SZ / L);
   const unsigned mask = two_ops ? (ta->tap_mask | tb->tap_mask) : ta->tap_mask;
-  switch (mode) {
-    case SINGLE: return dispatch_shape<SINGLE>(ctx, p, L, NT, mask);
-    case SUM: return dispatch_shape<SUM>(ctx, p, L, NT, mask);
-    case DUAL: return dispatch_shape<DUAL>(ctx, p, L, NT, mask);
-    default: return dispatch_shape<AXPY>(ctx, p, L, NT, mask);
-  }
+  if (!split) return dispatch_mode<false>(ctx, p, mode, L, NT, mask);
+  // rank-split direction: halos and boundary carries first (m3_edge.cu), then the main kernel
+  const DistBufs b = carve_dist(ctx);
+  EdgeParams ep{};
+  ep.n = n;
+  ep.n_pad = ctx->n_pad(dir);
+  ep.nseg = nseg;
+  ep.ns = two_ops ? 2 : 1;
+  ep.ops[0] = p.oa;
+  ep.ops[1] = p.ob;
+  ep.f[0] = in_a;
+  ep.f[1] = in_b;
+  const double* fields[2] = {in_a, in_b};
+  int rc = exchange_edges(ctx, dir, fields, mode == SUM ? 2 : 1, ep, b);
+  if (rc) return rc;
+  p.halo_s = b.halo_recv_s;
+  p.halo_e = b.halo_recv_e;
+  p.from_prev = b.carr_from_prev;
+  p.from_next = b.carr_from_next;
+  return dispatch_mode<true>(ctx, p, mode, L, NT, mask);
 }
 
 }  // namespace x3d2c

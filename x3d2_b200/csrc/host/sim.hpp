@@ -321,6 +321,11 @@ class Backend {  // cuda_c_backend_t: every method is one deferred procedure of 
     X3D2H_CALL(x3d2c_reorder(ctx, direction, u_.dev, u.dev));
     u_.data_loc = u.data_loc;
   }
+  void reorder_x2yz(Field& u_y, Field& u_z, const Field& u) {
+    if (u.dir != DIR_X || u_y.dir != DIR_Y || u_z.dir != DIR_Z) fail("reorder_x2yz: fields must be DIR_X -> DIR_Y, DIR_Z");
+    X3D2H_CALL(x3d2c_reorder_x2yz(ctx, u_y.dev, u_z.dev, u.dev));
+    u_y.data_loc = u.data_loc; u_z.data_loc = u.data_loc;
+  }
   void sum_yintox(Field& u, const Field& u_) { X3D2H_CALL(x3d2c_sum_yintox(ctx, u.dev, u_.dev)); }
   void sum_zintox(Field& u, const Field& u_) { X3D2H_CALL(x3d2c_sum_zintox(ctx, u.dev, u_.dev)); }
   void sum_yzintox(Field& u, const Field& u_y, const Field& u_z) { X3D2H_CALL(x3d2c_sum_yzintox(ctx, u.dev, u_y.dev, u_z.dev)); }
@@ -543,17 +548,17 @@ class Sim {
   void transeq_default(Field& du, Field& dv, Field& dw, const Field& uu, const Field& vv, const Field& ww) {
     Allocator& A = allocator;
     backend.transeq_x(du, dv, dw, uu, vv, ww, nu, xdirps);
-    Field *u_y = A.get_block(DIR_Y), *v_y = A.get_block(DIR_Y), *w_y = A.get_block(DIR_Y), *du_y = A.get_block(DIR_Y),
-          *dv_y = A.get_block(DIR_Y), *dw_y = A.get_block(DIR_Y);
-    backend.reorder(*u_y, uu, RDR_X2Y); backend.reorder(*v_y, vv, RDR_X2Y); backend.reorder(*w_y, ww, RDR_X2Y);
+    // u, v, w into both pencil layouts with one read each (reference: 3 x reorder X2Y here, 3 x reorder X2Z below)
+    Field *u_y = A.get_block(DIR_Y), *v_y = A.get_block(DIR_Y), *w_y = A.get_block(DIR_Y);
+    Field *u_z = A.get_block(DIR_Z), *v_z = A.get_block(DIR_Z), *w_z = A.get_block(DIR_Z);
+    backend.reorder_x2yz(*u_y, *u_z, uu); backend.reorder_x2yz(*v_y, *v_z, vv); backend.reorder_x2yz(*w_y, *w_z, ww);
+    Field *du_y = A.get_block(DIR_Y), *dv_y = A.get_block(DIR_Y), *dw_y = A.get_block(DIR_Y);
     backend.transeq_y(*du_y, *dv_y, *dw_y, *u_y, *v_y, *w_y, nu, ydirps);
     A.release_block(u_y); A.release_block(v_y); A.release_block(w_y);
-    // sum_yintox is deferred: one pass adds the y and the z contributions (in the reference's order)
-    Field *u_z = A.get_block(DIR_Z), *v_z = A.get_block(DIR_Z), *w_z = A.get_block(DIR_Z), *du_z = A.get_block(DIR_Z),
-          *dv_z = A.get_block(DIR_Z), *dw_z = A.get_block(DIR_Z);
-    backend.reorder(*u_z, uu, RDR_X2Z); backend.reorder(*v_z, vv, RDR_X2Z); backend.reorder(*w_z, ww, RDR_X2Z);
+    Field *du_z = A.get_block(DIR_Z), *dv_z = A.get_block(DIR_Z), *dw_z = A.get_block(DIR_Z);
     backend.transeq_z(*du_z, *dv_z, *dw_z, *u_z, *v_z, *w_z, nu, zdirps);
     A.release_block(u_z); A.release_block(v_z); A.release_block(w_z);
+    // one pass adds the y and the z contributions (sum_yintox then sum_zintox, in the reference's order)
     backend.sum_yzintox(du, *du_y, *du_z); backend.sum_yzintox(dv, *dv_y, *dv_z); backend.sum_yzintox(dw, *dw_y, *dw_z);
     A.release_block(du_y); A.release_block(dv_y); A.release_block(dw_y);
     A.release_block(du_z); A.release_block(dv_z); A.release_block(dw_z);
