@@ -119,6 +119,11 @@ struct x3d2c_poisson {
   double* waves = nullptr;                        // interleaved re/im in B's layout
   double *ax = nullptr, *bx = nullptr, *ay = nullptr, *by = nullptr, *az = nullptr, *bz = nullptr;
   double* compact = nullptr;  // un-padded real buffer when the DIR_C block is padded
+  // multi-rank: the slab exchange writes straight into the peers' buffers over NVLink (CUDA IPC mappings)
+  bool p2p = false;
+  cufftDoubleComplex* peerA[8] = {nullptr};
+  cufftDoubleComplex* peerB[8] = {nullptr};
+  double* bar_word = nullptr;  // device word of the all-reduce barriers
 };
 
 // internal launch helpers implemented across the .cu files

@@ -18,6 +18,7 @@
 
 namespace x3d2c {
 int alltoall(x3d2c_ctx* ctx, double* recv, const double* send, size_t block_doubles);  // nccl.cu
+int allreduce(x3d2c_ctx* ctx, double* dev, size_t count, int op);                        // nccl.cu
 }
 
 namespace {
@@ -72,6 +73,33 @@ slab_pack_kernel(double2* __restrict__ packed, double2* __restrict__ b, const in
     const size_t p = ((size_t)r * nz_loc * nxh + q) * ny_loc + jl;
     if (PACK) packed[p] = b[t];
     else b[t] = packed[p];
+  }
+}
+
+// The same exchange with the pack / unpack fused into the transfer: every element is written straight into the
+// destination rank's buffer through its CUDA-IPC mapping (NVLink peer stores; the own block is an ordinary store).
+//   FWD: local B(ny, nxh, nz_loc)  ->  rank r = j / ny_loc:  A_r[(rank * nz_loc * nxh + q) * ny_loc + jl]
+//   BWD: local A = C(j_loc, i, k)  ->  rank s = k / nz_loc:  B_s[(rank * ny_loc + jl) + ny * q]
+struct PeerPtrs { double2* p[8]; };
+template <bool FWD>
+__global__ void __launch_bounds__(256)
+slab_exchange_kernel(const PeerPtrs dst, const double2* __restrict__ src, const int ny, const int ny_loc, const int nxh,
+                     const int nz_loc, const int rank) {
+  const size_t n = (size_t)ny * nxh * nz_loc;
+  const size_t blk = (size_t)nz_loc * nxh;  // rows (i, k_loc) per rank block
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    if (FWD) {
+      const int j = (int)(t % ny);
+      const size_t q = t / ny;  // i + nxh * k_loc
+      const int r = j / ny_loc, jl = j - r * ny_loc;
+      dst.p[r][((size_t)rank * blk + q) * ny_loc + jl] = src[t];
+    } else {
+      const int jl = (int)(t % ny_loc);
+      const size_t row = t / ny_loc;  // q + blk * s
+      const int s = (int)(row / blk);
+      const size_t q = row - (size_t)s * blk;
+      dst.p[s][(size_t)rank * ny_loc + jl + (size_t)ny * q] = src[t];
+    }
   }
 }
 
@@ -173,6 +201,58 @@ int x3d2c_poisson_spec_layout(const x3d2c_ctx* ctx, int n_spec[3], int n_sp_st[3
   return X3D2C_OK;
 }
 
+// Maps every peer's A and B buffers into this process (CUDA IPC). All ranks agree on the outcome; when any mapping
+// fails the NCCL send/recv exchange stays in use.
+static int setup_peer_buffers(x3d2c_ctx* ctx, x3d2c_poisson* p) {
+  const int P = ctx->cfg.nproc, me = ctx->cfg.rank;
+  constexpr int HD = 2 * sizeof(cudaIpcMemHandle_t) / sizeof(double);  // doubles per rank: handles of A and B
+  static_assert(sizeof(cudaIpcMemHandle_t) % sizeof(double) == 0, "handle size");
+  std::vector<double> mine(HD), all((size_t)HD * P), rep((size_t)HD * P);
+  cudaIpcMemHandle_t h[2];
+  bool ok = cudaIpcGetMemHandle(&h[0], p->A) == cudaSuccess && cudaIpcGetMemHandle(&h[1], p->B) == cudaSuccess;
+  if (!ok) cudaGetLastError();
+  std::memcpy(mine.data(), h, sizeof h);
+  for (int r = 0; r < P; ++r) std::memcpy(&rep[(size_t)r * HD], mine.data(), sizeof h);
+  double *d_send = nullptr, *d_recv = nullptr;
+  X3D2C_CHECK_CUDA(cudaMalloc(&d_send, sizeof(double) * HD * P));
+  X3D2C_CHECK_CUDA(cudaMalloc(&d_recv, sizeof(double) * HD * P));
+  X3D2C_CHECK_CUDA(cudaMalloc(&p->bar_word, sizeof(double) * 2));
+  X3D2C_CHECK_CUDA(cudaMemsetAsync(p->bar_word, 0, sizeof(double) * 2, ctx->stream));
+  X3D2C_CHECK_CUDA(cudaMemcpyAsync(d_send, rep.data(), sizeof(double) * HD * P, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = alltoall(ctx, d_recv, d_send, HD);
+  if (rc) return rc;
+  X3D2C_CHECK_CUDA(cudaMemcpyAsync(all.data(), d_recv, sizeof(double) * HD * P, cudaMemcpyDeviceToHost, ctx->stream));
+  X3D2C_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int r = 0; r < P && ok; ++r) {
+    if (r == me) { p->peerA[r] = p->A; p->peerB[r] = p->B; continue; }
+    cudaIpcMemHandle_t hr[2];
+    std::memcpy(hr, &all[(size_t)r * HD], sizeof hr);
+    void *pa = nullptr, *pb = nullptr;
+    ok = cudaIpcOpenMemHandle(&pa, hr[0], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+         cudaIpcOpenMemHandle(&pb, hr[1], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    p->peerA[r] = (cufftDoubleComplex*)pa;
+    p->peerB[r] = (cufftDoubleComplex*)pb;
+  }
+  // agreement: minimum of the success flags
+  const double flag = ok ? 0.0 : 1.0;
+  X3D2C_CHECK_CUDA(cudaMemcpyAsync(p->bar_word, &flag, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = allreduce(ctx, p->bar_word, 1, 0))) return rc;
+  double failed = 1.0;
+  X3D2C_CHECK_CUDA(cudaMemcpyAsync(&failed, p->bar_word, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  X3D2C_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  p->p2p = failed == 0.0;
+  cudaFree(d_send);
+  cudaFree(d_recv);
+  if (std::getenv("X3D2C_TRACE"))
+    std::fprintf(stderr, "[x3d2c] rank %d poisson slab exchange: %s\n", me,
+                 p->p2p ? "peer stores over NVLink (CUDA IPC)" : "ncclSend/Recv");
+  return X3D2C_OK;
+}
+
+// barrier across ranks on the context's stream (tiny all-reduce)
+static int stream_barrier(x3d2c_ctx* ctx, x3d2c_poisson* p) { return allreduce(ctx, p->bar_word + 1, 1, 0); }
+
 int x3d2c_poisson_create(x3d2c_ctx* ctx, const double* waves, const double* ax, const double* bx,
                          const double* ay, const double* by, const double* az, const double* bz,
                          x3d2c_poisson** out) {
@@ -224,6 +304,10 @@ int x3d2c_poisson_create(x3d2c_ctx* ctx, const double* waves, const double* ax, 
   X3D2C_CHECK_CUFFT(cufftSetStream(p->plan_y, ctx->stream));
   X3D2C_CHECK_CUFFT(cufftSetStream(p->plan_z, ctx->stream));
   p->have_plans = true;
+  if (P > 1 && P <= 8 && !std::getenv("X3D2C_NO_P2P")) {
+    rc = setup_peer_buffers(ctx, p);
+    if (rc) return rc;
+  }
   *out = p;
   return X3D2C_OK;
 }
@@ -232,6 +316,12 @@ int x3d2c_poisson_destroy(x3d2c_ctx* ctx, x3d2c_poisson* p) {
   if (!p) return X3D2C_OK;
   cudaStreamSynchronize(ctx->stream);
   if (p->have_plans) { cufftDestroy(p->plan_r2c); cufftDestroy(p->plan_c2r); cufftDestroy(p->plan_y); cufftDestroy(p->plan_z); }
+  for (int r = 0; r < 8; ++r) {
+    if (r == ctx->cfg.rank) continue;
+    if (p->peerA[r]) cudaIpcCloseMemHandle(p->peerA[r]);
+    if (p->peerB[r]) cudaIpcCloseMemHandle(p->peerB[r]);
+  }
+  if (p->bar_word) cudaFree(p->bar_word);
   for (void* q : {(void*)p->A, (void*)p->B, (void*)p->waves, (void*)p->ax, (void*)p->bx, (void*)p->ay, (void*)p->by,
                   (void*)p->az, (void*)p->bz, (void*)p->compact})
     if (q) cudaFree(q);
@@ -239,8 +329,8 @@ int x3d2c_poisson_destroy(x3d2c_ctx* ctx, x3d2c_poisson* p) {
   return X3D2C_OK;
 }
 
-// the spectrum C(j_loc, i, k) always lives in p->B
-static cufftDoubleComplex* spec_buf(const x3d2c_ctx*, x3d2c_poisson* p) { return p->B; }
+// the spectrum C(j_loc, i, k) lives in p->B, or in p->A when the peers write it there directly
+static cufftDoubleComplex* spec_buf(const x3d2c_ctx*, x3d2c_poisson* p) { return p->p2p ? p->A : p->B; }
 
 int x3d2c_fft_forward(x3d2c_ctx* ctx, x3d2c_poisson* p, const double* f_c) {
   X3D2C_REQUIRE(ctx && p && f_c, "x3d2c_fft_forward: null argument");
@@ -259,7 +349,19 @@ int x3d2c_fft_forward(x3d2c_ctx* ctx, x3d2c_poisson* p, const double* f_c) {
   X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_y, p->B, p->B, CUFFT_FORWARD));
   ctx->launches++;
   cufftDoubleComplex* c = p->B;
-  if (ctx->cfg.nproc > 1) {
+  if (p->p2p) {
+    // every rank has finished reading its A (transpose above) -> A may be written by the peers; afterwards: all
+    // peer stores have landed
+    int rc = stream_barrier(ctx, p);
+    if (rc) return rc;
+    PeerPtrs dst;
+    for (int r = 0; r < 8; ++r) dst.p[r] = (double2*)p->peerA[r];
+    slab_exchange_kernel<true><<<1184, 256, 0, ctx->stream>>>(dst, (const double2*)p->B, p->ny, p->ny_loc, p->nxh,
+                                                              p->nz_loc, ctx->cfg.rank);
+    X3D2C_CHECK_LAUNCH(ctx);
+    if ((rc = stream_barrier(ctx, p))) return rc;
+    c = p->A;
+  } else if (ctx->cfg.nproc > 1) {
     slab_pack_kernel<true><<<1184, 256, 0, ctx->stream>>>((double2*)p->A, (double2*)p->B, p->ny, p->ny_loc, p->nxh, p->nz_loc);
     X3D2C_CHECK_LAUNCH(ctx);
     int rc = alltoall(ctx, (double*)p->B, (const double*)p->A, 2 * (size_t)p->ny_loc * p->nxh * p->nz_loc);
@@ -298,7 +400,16 @@ int x3d2c_fft_backward(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_c) {
   cufftDoubleComplex* c = spec_buf(ctx, p);
   X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_z, c, c, CUFFT_INVERSE));
   ctx->launches++;
-  if (ctx->cfg.nproc > 1) {
+  if (p->p2p) {
+    // B is free on every rank since the barrier that followed the forward exchange
+    PeerPtrs dst;
+    for (int r = 0; r < 8; ++r) dst.p[r] = (double2*)p->peerB[r];
+    slab_exchange_kernel<false><<<1184, 256, 0, ctx->stream>>>(dst, (const double2*)p->A, p->ny, p->ny_loc, p->nxh,
+                                                               p->nz_loc, ctx->cfg.rank);
+    X3D2C_CHECK_LAUNCH(ctx);
+    int rc = stream_barrier(ctx, p);
+    if (rc) return rc;
+  } else if (ctx->cfg.nproc > 1) {
     // y-slabs -> z-slabs: block s of C (k range of rank s) goes back to rank s
     int rc = alltoall(ctx, (double*)p->A, (const double*)p->B, 2 * (size_t)p->ny_loc * p->nxh * p->nz_loc);
     if (rc) return rc;
