@@ -27,7 +27,7 @@ class X3D2HConfig(C.Structure):  # include/x3d2h.h: x3d2h_config
 
 def build(verbose=False):
     """Compile both libraries for sm_100a (nvcc cross-compiles without a GPU)."""
-    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "all"]
+    cmd = ["make", "-j", str(min(16, os.cpu_count() or 4)), "-C", os.path.join(_HERE, "csrc"), "all"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("building x3d2_b200 failed:\n" + r.stdout)
