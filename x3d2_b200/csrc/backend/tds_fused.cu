@@ -48,7 +48,8 @@ int run(x3d2c_ctx* ctx, const char* what, int dir, int mode, double* out_a, doub
   auto report = [&](const char* how) {
     if (trace) std::fprintf(stderr, "[x3d2c] %s dir=%d rdr_in=%d rdr_out=%d -> %s\n", what, dir, rdr_in, rdr_out, how);
   };
-  if (!ctx->strict && (rdr_in || rdr_out)) {
+  static const bool no_rdr_in = std::getenv("X3D2C_NO_RDR_IN") != nullptr;  // tuning: explicit input reorders
+  if (!ctx->strict && (rdr_in || rdr_out) && !(no_rdr_in && rdr_in)) {
     rc = tds_m4(ctx, dir, mode, out_a, out_b, in_a, in_b, op_a, op_b, 1.0, lay_in, lay_out);
     if (rc != X3D2C_EUNSUPPORTED) {
       report("through the tensor maps");
