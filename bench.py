@@ -23,10 +23,10 @@ sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_PT = {"transeq": 48, "tds_solve": 16}  # per transeq_{x,y,z} / tds_solve call
 STEP_BYTES_PER_PT = 3888                                # whole RK3 step, the reference's operator graph
-# What this backend's operator graph moves per RK3 step (DESIGN.md "bytes per step"): per stage transeq 336
-# (3 x 48 kernels, 6 reorders, 3 fused y+z sums), divergence 160, Poisson 152, gradient + correction 184 (the y2z, z2c,
-# c2z, z2y reorders are done by the solves' tensor maps); RK3 updates 264
-STEP_BYTES_MOVED_PER_PT = 3 * (336 + 160 + 152 + 184) + 264
+# What this backend's operator graph moves per RK3 step (DESIGN.md "bytes per step"): per stage transeq 312
+# (3 x 48 kernels, 3 one-read x2y+x2z reorders, 3 fused y+z sums), divergence 160, Poisson 152, gradient + correction 200
+# (the y2z, z2c and z2y reorders are done by the solves' tensor maps); RK3 updates 264
+STEP_BYTES_MOVED_PER_PT = 3 * (312 + 160 + 152 + 200) + 264
 
 
 def grid_for(n_gpus, base):

@@ -130,5 +130,6 @@ struct x3d2c_poisson {
 namespace x3d2c {
 int launch_reorder(x3d2c_ctx* ctx, int dir_from, int dir_to, double* dst, const double* src, bool accumulate);
 int ensure_scratch(x3d2c_ctx* ctx, int count = 2);
+int ensure_scratch_slot(x3d2c_ctx* ctx, int i);
 int get_dims_dataloc(const x3d2c_ctx* ctx, int data_loc, int dims[3], bool global);
 }  // namespace x3d2c

@@ -30,6 +30,10 @@ int ensure_scratch(x3d2c_ctx* ctx, int count) {
     if (!ctx->scratch[i]) X3D2C_CHECK_CUDA(cudaMalloc(&ctx->scratch[i], sizeof(double) * ctx->ngrid));
   return X3D2C_OK;
 }
+int ensure_scratch_slot(x3d2c_ctx* ctx, int i) {
+  if (!ctx->scratch[i]) X3D2C_CHECK_CUDA(cudaMalloc(&ctx->scratch[i], sizeof(double) * ctx->ngrid));
+  return X3D2C_OK;
+}
 int nccl_init(x3d2c_ctx* ctx);      // nccl.cu
 void nccl_finalize(x3d2c_ctx* ctx);  // nccl.cu
 }  // namespace x3d2c

@@ -1,10 +1,10 @@
 // tds_solve combinations that read or write "through" a reorder (x3d2c_tds_solve_r / _sum_r / _dual_r).
 //
 // Each call equals: reorder the input(s) with rdr_in, apply the operator(s) in direction `dir`, reorder the output(s)
-// with rdr_out (rdr = 0: no reorder). On the fast path the TMA kernels of tds_m4.cu address the foreign layout
+// with rdr_out (rdr = 0: no reorder). On the fast path the TMA kernels of tds_m4.cu store into the foreign layout
 // directly through a 5-D tensor map (Y, Z and C layouts keep 32 consecutive x per row, so a Y- or Z-line tile is a
-// box in all three): the reorder passes (16 B per point each) disappear. Everywhere else the call runs as exactly the
-// sequence above through scratch fields, so the values are those of the reference's call sequence
+// box in all three): the output reorder passes (16 B per point each) disappear. Everywhere else the call runs as
+// exactly the sequence above through scratch fields, so the values are those of the reference's call sequence
 // (divergence_v2c / gradient_c2v, src/vector_calculus.f90:142-332; poisson_fft, src/solver.f90:741-775).
 #include "common.cuh"
 
@@ -48,22 +48,16 @@ int run(x3d2c_ctx* ctx, const char* what, int dir, int mode, double* out_a, doub
   auto report = [&](const char* how) {
     if (trace) std::fprintf(stderr, "[x3d2c] %s dir=%d rdr_in=%d rdr_out=%d -> %s\n", what, dir, rdr_in, rdr_out, how);
   };
-  static const bool no_rdr_in = std::getenv("X3D2C_NO_RDR_IN") != nullptr;  // tuning: explicit input reorders
-  if (!ctx->strict && (rdr_in || rdr_out) && !(no_rdr_in && rdr_in)) {
-    rc = tds_m4(ctx, dir, mode, out_a, out_b, in_a, in_b, op_a, op_b, 1.0, lay_in, lay_out);
-    if (rc != X3D2C_EUNSUPPORTED) {
-      report("through the tensor maps");
-      return rc;
-    }
-  }
-  // the sequence itself; the output side can still go through the tensor map (rank-split directions need their
-  // inputs in the direction's own layout)
-  if ((rc = ensure_scratch(ctx, 6))) return rc;
+  // Inputs are reordered explicitly: reading through a tensor map was measured slower than the separate pass (a
+  // c2z input has its rows one z-plane = 2 MB apart; pressure correction 12.15 ms against 12.02 ms), and rank-split
+  // directions need their inputs in the direction's own layout anyway. The outputs go through the tensor map.
   const double *a = in_a, *b = in_b;
   if (rdr_in) {
+    if ((rc = ensure_scratch_slot(ctx, 2))) return rc;
     if ((rc = x3d2c_reorder(ctx, rdr_in, ctx->scratch[2], in_a))) return rc;
     a = ctx->scratch[2];
     if (mode == 1) {
+      if ((rc = ensure_scratch_slot(ctx, 3))) return rc;
       if ((rc = x3d2c_reorder(ctx, rdr_in, ctx->scratch[3], in_b))) return rc;
       b = ctx->scratch[3];
     }
@@ -71,11 +65,12 @@ int run(x3d2c_ctx* ctx, const char* what, int dir, int mode, double* out_a, doub
   if (!ctx->strict && rdr_out) {
     rc = tds_m4(ctx, dir, mode, out_a, out_b, a, b, op_a, op_b, 1.0, dir, lay_out);
     if (rc != X3D2C_EUNSUPPORTED) {
-      report(rdr_in ? "input reorder, then output through the tensor map" : "output through the tensor map");
+      report(rdr_in ? "input reorder pass, output through the tensor map" : "output through the tensor map");
       return rc;
     }
   }
   if (rdr_in || rdr_out) report("reorder + operator sequence");
+  if (rdr_out && ((rc = ensure_scratch_slot(ctx, 4)) || (rc = ensure_scratch_slot(ctx, 5)))) return rc;
   double* oa = rdr_out ? ctx->scratch[4] : out_a;
   double* ob = rdr_out ? ctx->scratch[5] : out_b;
   if (mode == 0) rc = x3d2c_tds_solve(ctx, dir, oa, a, op_a);
