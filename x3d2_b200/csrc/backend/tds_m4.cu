@@ -4,7 +4,7 @@
 //   SUM   : out   = A(in_a) + B(in_b)      24 B/pt
 //   DUAL  : out_a = A(in), out_b = B(in)   24 B/pt
 //   AXPY  : y     = y + a A(in)            24 B/pt
-// Periodic, uniform directions with n = 64..512 a power of two; other shapes use the cp.async kernels. Rank-split
+// Periodic, uniform directions with n = 64..1024 a power of two; other shapes use the cp.async kernels. Rank-split
 // directions (DIST) stage halo rows and neighbour carries with cp.async as transeq_m4.cu does; their inputs must be in
 // the direction's own layout (the halo pack and edge kernels read them), the outputs may go through a tensor map.
 // Measured at 512^3: tds_solve 0.395 -> 0.376 ms (87% of HBM peak) with 64-byte rows (L = 8, 256 threads); with
@@ -224,7 +224,9 @@ bool tds_shape(int n, int* L, int* NT) {
     case 128: *L = 32; *NT = 256; return true;
     case 256: *L = 16; *NT = 256; return true;
     case 512: *L = 8; *NT = 256; return true;
-    default: return false;  // n = 1024 would need 32-byte rows: measured slower than the cp.async kernel
+    case 1024: *L = 4; *NT = 256; return true;  // 32-byte rows: no faster than the cp.async kernel (0.51 ms), but the
+                                                // output reorders can go through the tensor map
+    default: return false;
   }
 }
 
@@ -232,6 +234,7 @@ template <int MODE, bool DIST>
 int dispatch_shape(x3d2c_ctx* ctx, const TdsParams4& p, int L, int NT, unsigned mask) {
   if (NT == 128) return dispatch_mask<32, 128, MODE, DIST>(ctx, p, mask);
   switch (L) {
+    case 4: return dispatch_mask<4, 256, MODE, DIST>(ctx, p, mask);
     case 8: return dispatch_mask<8, 256, MODE, DIST>(ctx, p, mask);
     case 16: return dispatch_mask<16, 256, MODE, DIST>(ctx, p, mask);
     default: return dispatch_mask<32, 256, MODE, DIST>(ctx, p, mask);
