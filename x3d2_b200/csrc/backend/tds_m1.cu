@@ -8,8 +8,10 @@
 // In STRICT mode every product and sum is a separately rounded __dmul_rn/__dadd_rn in source order, so
 // the result is bit-identical to the strict-IEEE oracle. In the default mode the same statements are
 // evaluated with FMA contraction and exactly-zero stencil taps are skipped.
-// The intermediate sweeps live in the output arrays (as in the reference); the register-resident
-// segment-parallel kernels in tds_m3.cu are the fast path for single-rank directions.
+// The intermediate sweeps live in the output arrays (as in the reference). These kernels serve strict mode and
+// every operator the fast path does not cover (non-periodic boundaries, stretched meshes, short lines); periodic
+// uniform directions use the segment-parallel kernels of *_m4.cu (TMA tiles) and *_m3.cu (cp.async tiles).
+// This file also holds the C entry points x3d2c_tds_solve / _sum / _dual / _axpy / x3d2c_transeq and their dispatch.
 #include "common.cuh"
 
 namespace {
