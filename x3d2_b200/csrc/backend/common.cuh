@@ -121,8 +121,6 @@ struct x3d2c_poisson {
   double* compact = nullptr;  // un-padded real buffer when the DIR_C block is padded
   // multi-rank: the slab exchange writes straight into the peers' buffers over NVLink (CUDA IPC mappings)
   bool p2p = false;
-  // single rank: x and y transforms as one 2-D cuFFT plan, spectrum kept in the reference's (i, j, k) order in A
-  bool ijk = false;
   cufftDoubleComplex* peerA[8] = {nullptr};
   cufftDoubleComplex* peerB[8] = {nullptr};
   double* bar_word = nullptr;  // device word of the all-reduce barriers

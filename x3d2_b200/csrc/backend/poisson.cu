@@ -112,18 +112,16 @@ struct SpecParams {
 };
 
 // spectral_processing.f90:36-100, one thread per mode of C(j_loc, i, k)
-template <bool STRICT, bool IJK>
+template <bool STRICT>
 __global__ void __launch_bounds__(256)
 process_spectral_000_kernel(double2* __restrict__ c, const double2* __restrict__ waves,
                             const double* __restrict__ ax, const double* __restrict__ bx,
                             const double* __restrict__ ay, const double* __restrict__ by,
                             const double* __restrict__ az, const double* __restrict__ bz, const SpecParams p) {
-  // IJK: the spectrum is stored as (i, j, k), threads run along i; otherwise as C(j_loc, i, k), threads along j
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (IJK ? p.nxh : p.ny_loc)) return;
-  const int jl = IJK ? blockIdx.y : t, i = IJK ? t : blockIdx.y, k = blockIdx.z;
-  const size_t idx = IJK ? i + (size_t)p.nxh * (jl + (size_t)p.ny_loc * k)
-                         : jl + (size_t)p.ny_loc * (i + (size_t)p.nxh * k);
+  const int jl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (jl >= p.ny_loc) return;
+  const int i = blockIdx.y, k = blockIdx.z;
+  const size_t idx = jl + (size_t)p.ny_loc * (i + (size_t)p.nxh * k);
   const int ix = i, iy = jl + p.y_off, iz = k;  // 0-based
   double2 v = c[idx];
   double div_r, div_c;
@@ -273,11 +271,9 @@ int x3d2c_poisson_create(x3d2c_ctx* ctx, const double* waves, const double* ax, 
   const size_t n_spec = (size_t)p->nxh * p->ny_loc * p->nz;  // == nxh * ny * nz_loc
   X3D2C_CHECK_CUDA(cudaMalloc(&p->A, sizeof(cufftDoubleComplex) * n_spec));
   X3D2C_CHECK_CUDA(cudaMalloc(&p->B, sizeof(cufftDoubleComplex) * n_spec));
-  p->ijk = P == 1 && !std::getenv("X3D2C_POISSON_1D");
-  // waves(i, j, k) -> C order (j, i, k) (kept as is for the single-rank (i, j, k) spectrum)
+  // waves(i, j, k) -> C order (j, i, k)
   std::vector<double> wc(2 * n_spec);
-  if (p->ijk) std::memcpy(wc.data(), waves, sizeof(double) * 2 * n_spec);
-  for (int k = 0; k < (p->ijk ? 0 : p->nz); ++k)
+  for (int k = 0; k < p->nz; ++k)
     for (int j = 0; j < p->ny_loc; ++j)
       for (int i = 0; i < p->nxh; ++i) {
         const size_t s = i + (size_t)p->nxh * (j + (size_t)p->ny_loc * k);
@@ -298,14 +294,8 @@ int x3d2c_poisson_create(x3d2c_ctx* ctx, const double* waves, const double* ax, 
   if (padded) X3D2C_CHECK_CUDA(cudaMalloc(&p->compact, sizeof(double) * (size_t)p->nx * p->ny * p->nz_loc));
   // batched 1-D plans
   int n_x[1] = {p->nx}, n_y[1] = {p->ny}, n_z[1] = {p->nz};
-  if (p->ijk) {  // 2-D (y, x) transforms of every z-plane: no separate transposes
-    int n_yx[2] = {p->ny, p->nx};
-    X3D2C_CHECK_CUFFT(cufftPlanMany(&p->plan_r2c, 2, n_yx, nullptr, 1, 0, nullptr, 1, 0, CUFFT_D2Z, p->nz_loc));
-    X3D2C_CHECK_CUFFT(cufftPlanMany(&p->plan_c2r, 2, n_yx, nullptr, 1, 0, nullptr, 1, 0, CUFFT_Z2D, p->nz_loc));
-  } else {
-    X3D2C_CHECK_CUFFT(cufftPlanMany(&p->plan_r2c, 1, n_x, n_x, 1, p->nx, n_x, 1, p->nxh, CUFFT_D2Z, p->ny * p->nz_loc));
-    X3D2C_CHECK_CUFFT(cufftPlanMany(&p->plan_c2r, 1, n_x, n_x, 1, p->nxh, n_x, 1, p->nx, CUFFT_Z2D, p->ny * p->nz_loc));
-  }
+  X3D2C_CHECK_CUFFT(cufftPlanMany(&p->plan_r2c, 1, n_x, n_x, 1, p->nx, n_x, 1, p->nxh, CUFFT_D2Z, p->ny * p->nz_loc));
+  X3D2C_CHECK_CUFFT(cufftPlanMany(&p->plan_c2r, 1, n_x, n_x, 1, p->nxh, n_x, 1, p->nx, CUFFT_Z2D, p->ny * p->nz_loc));
   X3D2C_CHECK_CUFFT(cufftPlanMany(&p->plan_y, 1, n_y, n_y, 1, p->ny, n_y, 1, p->ny, CUFFT_Z2Z, p->nxh * p->nz_loc));
   const int zs = p->ny_loc * p->nxh;
   X3D2C_CHECK_CUFFT(cufftPlanMany(&p->plan_z, 1, n_z, n_z, zs, 1, n_z, zs, 1, CUFFT_Z2Z, zs));
@@ -340,7 +330,7 @@ int x3d2c_poisson_destroy(x3d2c_ctx* ctx, x3d2c_poisson* p) {
 }
 
 // the spectrum C(j_loc, i, k) lives in p->B, or in p->A when the peers write it there directly
-static cufftDoubleComplex* spec_buf(const x3d2c_ctx*, x3d2c_poisson* p) { return (p->p2p || p->ijk) ? p->A : p->B; }
+static cufftDoubleComplex* spec_buf(const x3d2c_ctx*, x3d2c_poisson* p) { return p->p2p ? p->A : p->B; }
 
 int x3d2c_fft_forward(x3d2c_ctx* ctx, x3d2c_poisson* p, const double* f_c) {
   X3D2C_REQUIRE(ctx && p && f_c, "x3d2c_fft_forward: null argument");
@@ -353,11 +343,6 @@ int x3d2c_fft_forward(x3d2c_ctx* ctx, x3d2c_poisson* p, const double* f_c) {
   }
   X3D2C_CHECK_CUFFT(cufftExecD2Z(p->plan_r2c, const_cast<double*>(in), p->A));
   ctx->launches++;
-  if (p->ijk) {
-    X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_z, p->A, p->A, CUFFT_FORWARD));
-    ctx->launches++;
-    return X3D2C_OK;
-  }
   const dim3 grid((p->nxh + 31) / 32, (p->ny + 31) / 32, p->nz_loc), block(32, 8);
   cplx_transpose_kernel<<<grid, block, 0, ctx->stream>>>((double2*)p->B, (const double2*)p->A, p->nxh, p->ny);
   X3D2C_CHECK_LAUNCH(ctx);
@@ -397,16 +382,15 @@ int x3d2c_fft_postprocess_000(x3d2c_ctx* ctx, x3d2c_poisson* p) {
   const long long N = (long long)p->nx * p->ny * p->nz;
   sp.pow2 = (N & (N - 1)) == 0;
   sp.inv_n = 1.0 / (double)N;
-  const int nfast = p->ijk ? p->nxh : p->ny_loc, nmid = p->ijk ? p->ny_loc : p->nxh;
-  const int bx_ = nfast >= 256 ? 256 : ((nfast + 31) / 32) * 32;
-  const dim3 grid((nfast + bx_ - 1) / bx_, nmid, p->nz), block(bx_);
+  const int bx_ = p->ny_loc >= 256 ? 256 : ((p->ny_loc + 31) / 32) * 32;
+  const dim3 grid((p->ny_loc + bx_ - 1) / bx_, p->nxh, p->nz), block(bx_);
   cufftDoubleComplex* c = spec_buf(ctx, p);
-  auto args = [&](auto kernel) {
-    kernel<<<grid, block, 0, ctx->stream>>>((double2*)c, (const double2*)p->waves, p->ax, p->bx, p->ay, p->by, p->az,
-                                            p->bz, sp);
-  };
-  if (ctx->strict) { if (p->ijk) args(process_spectral_000_kernel<true, true>); else args(process_spectral_000_kernel<true, false>); }
-  else { if (p->ijk) args(process_spectral_000_kernel<false, true>); else args(process_spectral_000_kernel<false, false>); }
+  if (ctx->strict)
+    process_spectral_000_kernel<true><<<grid, block, 0, ctx->stream>>>((double2*)c, (const double2*)p->waves, p->ax,
+                                                                      p->bx, p->ay, p->by, p->az, p->bz, sp);
+  else
+    process_spectral_000_kernel<false><<<grid, block, 0, ctx->stream>>>((double2*)c, (const double2*)p->waves, p->ax,
+                                                                       p->bx, p->ay, p->by, p->az, p->bz, sp);
   X3D2C_CHECK_LAUNCH(ctx);
   return X3D2C_OK;
 }
@@ -416,16 +400,6 @@ int x3d2c_fft_backward(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_c) {
   cufftDoubleComplex* c = spec_buf(ctx, p);
   X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_z, c, c, CUFFT_INVERSE));
   ctx->launches++;
-  if (p->ijk) {
-    double* outp = p->compact ? p->compact : f_c;
-    X3D2C_CHECK_CUFFT(cufftExecZ2D(p->plan_c2r, p->A, outp));
-    ctx->launches++;
-    if (p->compact) {
-      pad_copy_kernel<false><<<1184, 256, 0, ctx->stream>>>(p->compact, f_c, p->nx, p->ny, p->nz_loc, ctx->nx_pad, ctx->ny_pad);
-      X3D2C_CHECK_LAUNCH(ctx);
-    }
-    return X3D2C_OK;
-  }
   if (p->p2p) {
     // B is free on every rank since the barrier that followed the forward exchange
     PeerPtrs dst;
@@ -463,10 +437,6 @@ int x3d2c_poisson_get_spectrum(x3d2c_ctx* ctx, x3d2c_poisson* p, double* host_sp
   std::vector<double> tmp(2 * n);
   X3D2C_CHECK_CUDA(cudaMemcpyAsync(tmp.data(), spec_buf(ctx, p), sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
   X3D2C_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (p->ijk) {
-    std::memcpy(host_spec, tmp.data(), sizeof(double) * 2 * n);
-    return X3D2C_OK;
-  }
   for (int k = 0; k < p->nz; ++k)
     for (int j = 0; j < p->ny_loc; ++j)
       for (int i = 0; i < p->nxh; ++i) {
