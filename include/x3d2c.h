@@ -189,6 +189,14 @@ int x3d2c_scalar_product(x3d2c_ctx* ctx, int dir, int data_loc, const double* x,
 int x3d2c_field_max_mean(x3d2c_ctx* ctx, int dir, int data_loc, const double* f, double* max_val, double* mean_val);
 /* ---- field_volume_integral (src/backend/backend.f90:268-279): DIR_X only. Synchronous. */
 int x3d2c_field_volume_integral(x3d2c_ctx* ctx, int data_loc, const double* f, double* s);
+/* ---- field_set_face / field_set_face_from_field (src/backend/backend.f90:268-308, omp/backend.f90:903-1021): DIR_X
+ * fields only, `data_loc` gives the extents. set_face: Y_FACE sets the rows y = 1 and y = ny to c_start / c_end (X_FACE,
+ * Z_FACE: "not yet supported", as the reference; the top row is the one the reference's CUDA backend and the TODO at
+ * omp/backend.f90:939 intend). from_field: Y_FACE copies both rows from f_start; X_FACE copies the inlet column x = 1
+ * from f_start and applies the convective outflow f(nx) = f(nx) - c_end (f(nx) - f(nx-1)) + flow_rate_diff. */
+int x3d2c_field_set_face(x3d2c_ctx* ctx, double* f, int data_loc, double c_start, double c_end, int face);
+int x3d2c_field_set_face_from_field(x3d2c_ctx* ctx, double* f, const double* f_start, int data_loc, double c_end,
+                                    int face, double flow_rate_diff);
 
 /* ---- init_poisson_fft (src/backend/backend.f90:374-391) and the poisson_fft_t hooks
  * (src/poisson_fft.f90:45-62,72-116). The spectral buffer is hidden state of the handle between

@@ -333,3 +333,29 @@ class World:
         a = [np.zeros(nv) for _ in range(4)] + [np.zeros(nc) for _ in range(2)]
         _chk(lib().orc_world_geo(self.h, dir, *[_p(x) for x in a]))
         return dict(zip(("vert_coords", "vert_ds", "vert_ds2", "vert_d2s", "midp_coords", "midp_ds"), a))
+
+
+def field_set_face(f, c_start, c_end, face="y"):
+    """field_set_face_omp (omp/backend.f90:903-953) on a Cartesian [nz, ny, nx] array: Y_FACE sets the bottom row to
+    c_start and the top row to c_end (the row meant by the TODO at :939 and set by the CUDA backend)."""
+    if face != "y":
+        raise RuntimeError("Setting X_FACE / Z_FACE is not yet supported.")
+    g = np.array(f, dtype=np.float64, copy=True)
+    g[:, 0, :] = c_start
+    g[:, -1, :] = c_end
+    return g
+
+
+def field_set_face_from_field(f, f_start, c_end, face, flow_rate_diff=0.0):
+    """field_set_face_from_field_omp (omp/backend.f90:954-1021) on Cartesian [nz, ny, nx] arrays."""
+    g = np.array(f, dtype=np.float64, copy=True)
+    if face == "y":      # :1003-1014: both walls from f_start
+        g[:, 0, :] = f_start[:, 0, :]
+        g[:, -1, :] = f_start[:, -1, :]
+    elif face == "x":    # :981-1001: inlet from f_start, convective outflow
+        g[:, :, 0] = f_start[:, :, 0]
+        fd, fd1 = f[:, :, -1], f[:, :, -2]
+        g[:, :, -1] = (fd - c_end * (fd - fd1)) + flow_rate_diff
+    else:
+        raise RuntimeError("field_set_face_from_field: only X_FACE and Y_FACE supported.")
+    return g

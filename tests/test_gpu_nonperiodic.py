@@ -86,3 +86,22 @@ def test_veclincomb_matches_vecadd_chain(x3d2):
     fast = x3d2.Sim((33, 20, 24), bcs=((2, 2), (1, 1), (0, 0)))
     assert np.abs(fast.fieldop("lincomb", 1, x, y, a=a) - exp).max() < 1e-15
     fast.close()
+
+
+@pytest.mark.parametrize("dims,bcs", [((33, 41, 24), ((2, 2), (2, 2), (0, 0))), ((64, 64, 32), ((0, 0), (0, 0), (0, 0)))])
+def test_field_set_face(oracle, x3d2, dims, bcs):
+    """field_set_face / field_set_face_from_field (channel and inflow cases) against the Cartesian restatement."""
+    X_FACE, Y_FACE = 1100, 1010
+    sim = x3d2.Sim(dims, bcs=bcs)
+    rng = np.random.default_rng(8)
+    for loc in (0, 1110):
+        f, fs = rng.standard_normal(sim.shape(loc)), rng.standard_normal(sim.shape(loc))
+        got = sim.fieldop("set_face", 1, f, a=1.5, loc=loc, extra=(-2.5, Y_FACE))
+        assert np.array_equal(got, oracle.field_set_face(f, 1.5, -2.5))
+        got = sim.fieldop("set_face_from_field", 1, f, fs, a=0.0, loc=loc, extra=(0.0, Y_FACE))
+        assert np.array_equal(got, oracle.field_set_face_from_field(f, fs, 0.0, "y"))
+        got = sim.fieldop("set_face_from_field", 1, f, fs, a=0.37, loc=loc, extra=(0.01, X_FACE))
+        assert np.array_equal(got, oracle.field_set_face_from_field(f, fs, 0.37, "x", 0.01))
+    with pytest.raises(RuntimeError, match="not yet supported"):
+        sim.fieldop("set_face", 1, f, a=1.0, loc=loc, extra=(1.0, X_FACE))
+    sim.close()

@@ -302,12 +302,12 @@ class Sim:
         _chk(self._h.x3d2h_field_max_mean(self.h, dir, loc, _p(x), C.byref(mx), C.byref(mean)))
         return mx.value, mean.value
 
-    def fieldop(self, op, dir, x, y=None, a=0.0, loc=VERT):
-        """field_scale / field_shift / vecmult / veccopy / fill / volume_integral on host data."""
+    def fieldop(self, op, dir, x, y=None, a=0.0, loc=VERT, extra=None):
+        """field_scale / field_shift / vecmult / veccopy / fill / volume_integral / set_face / set_face_from_field."""
         x = _f(x)
         y = _f(y) if y is not None else None
         out = self._out(loc)
-        s = C.c_double(0)
+        s = (C.c_double * 2)(*(extra or (0.0, 0.0)))  # set_face*: (c_end | flow_rate_diff, face)
         _chk(self._h.x3d2h_fieldop(self.h, op.encode(), dir, loc, float(a), _p(x), _p(y) if y is not None else None,
-                                   _p(out), C.byref(s)))
-        return s.value if op == "volume_integral" else out
+                                   _p(out), s))
+        return s[0] if op == "volume_integral" else out

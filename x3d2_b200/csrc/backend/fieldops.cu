@@ -95,6 +95,37 @@ lincomb_kernel(double* out, const __grid_constant__ LinComb q, const long long n
   }
 }
 
+// field_set_face / field_set_face_from_field on DIR_X fields (omp/backend.f90:903-1021). One thread per face point.
+// Y faces: points (x, z), rows y = 0 and y = ny - 1; X faces: points (y, z), columns x = 0 and x = nx - 1.
+struct FaceGeom {
+  int nx, ny, nz;  // extents of the data location
+  int nx_pad, nyb;
+};
+__device__ __forceinline__ size_t dirx_index(const FaceGeom& g, int x, int y, int z) {
+  return (size_t)(y % SZ) + (size_t)SZ * (x + (size_t)g.nx_pad * ((y / SZ) + (size_t)g.nyb * z));
+}
+template <bool FROM_FIELD>
+__global__ void __launch_bounds__(256)
+set_yface_kernel(double* __restrict__ f, const double* __restrict__ f_start, const double c_start, const double c_end,
+                 const FaceGeom g) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+  if (x >= g.nx) return;
+  const size_t lo = dirx_index(g, x, 0, z), hi = dirx_index(g, x, g.ny - 1, z);
+  f[lo] = FROM_FIELD ? f_start[lo] : c_start;
+  f[hi] = FROM_FIELD ? f_start[hi] : c_end;
+}
+// inlet from f_start, convective outflow: f(nx-1) -= c_end (f(nx-1) - f(nx-2)) - flow_rate_diff
+__global__ void __launch_bounds__(256)
+set_xface_from_field_kernel(double* __restrict__ f, const double* __restrict__ f_start, const double c_end,
+                            const double flow_rate_diff, const FaceGeom g) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+  if (y >= g.ny) return;
+  const size_t i0 = dirx_index(g, 0, y, z), i1 = dirx_index(g, g.nx - 1, y, z), i2 = dirx_index(g, g.nx - 2, y, z);
+  f[i0] = f_start[i0];
+  const double fd = f[i1], fd1 = f[i2];
+  f[i1] = __dadd_rn(__dadd_rn(fd, -__dmul_rn(c_end, __dadd_rn(fd, -fd1))), flow_rate_diff);
+}
+
 struct RedGeom {
   int dir;
   int n_pad;        // padded line length
@@ -262,6 +293,46 @@ int x3d2c_field_scale(x3d2c_ctx* ctx, double* f, double a) {
 int x3d2c_field_shift(x3d2c_ctx* ctx, double* f, double a) {
   X3D2C_REQUIRE(ctx && f, "x3d2c_field_shift: null argument");
   return run_stream<OP_SHIFT>(ctx, f, nullptr, a, 0.0);
+}
+
+static int face_geom(const x3d2c_ctx* ctx, int data_loc, FaceGeom* g) {
+  int dims[3];
+  int rc = x3d2c::get_dims_dataloc(ctx, data_loc, dims, false);
+  if (rc) return rc;
+  g->nx = dims[0]; g->ny = dims[1]; g->nz = dims[2];
+  g->nx_pad = ctx->nx_pad;
+  g->nyb = ctx->ny_pad / SZ;
+  return X3D2C_OK;
+}
+
+int x3d2c_field_set_face(x3d2c_ctx* ctx, double* f, int data_loc, double c_start, double c_end, int face) {
+  X3D2C_REQUIRE(ctx && f, "x3d2c_field_set_face: null argument");
+  X3D2C_REQUIRE(face == X3D2C_X_FACE || face == X3D2C_Y_FACE || face == X3D2C_Z_FACE, "face is undefined.");
+  X3D2C_REQUIRE(face != X3D2C_X_FACE, "Setting X_FACE is not yet supported.");  // omp/backend.f90:930-931
+  X3D2C_REQUIRE(face != X3D2C_Z_FACE, "Setting Z_FACE is not yet supported.");  // :946-947
+  FaceGeom g;
+  int rc = face_geom(ctx, data_loc, &g);
+  if (rc) return rc;
+  set_yface_kernel<false><<<dim3((g.nx + 255) / 256, g.nz), 256, 0, ctx->stream>>>(f, nullptr, c_start, c_end, g);
+  X3D2C_CHECK_LAUNCH(ctx);
+  return X3D2C_OK;
+}
+
+int x3d2c_field_set_face_from_field(x3d2c_ctx* ctx, double* f, const double* f_start, int data_loc, double c_end,
+                                    int face, double flow_rate_diff) {
+  X3D2C_REQUIRE(ctx && f && f_start, "x3d2c_field_set_face_from_field: null argument");
+  X3D2C_REQUIRE(face == X3D2C_X_FACE || face == X3D2C_Y_FACE,
+                "field_set_face_from_field: only X_FACE and Y_FACE supported.");  // omp/backend.f90:1017-1018
+  FaceGeom g;
+  int rc = face_geom(ctx, data_loc, &g);
+  if (rc) return rc;
+  if (face == X3D2C_Y_FACE)
+    set_yface_kernel<true><<<dim3((g.nx + 255) / 256, g.nz), 256, 0, ctx->stream>>>(f, f_start, 0.0, 0.0, g);
+  else
+    set_xface_from_field_kernel<<<dim3((g.ny + 255) / 256, g.nz), 256, 0, ctx->stream>>>(f, f_start, c_end,
+                                                                                          flow_rate_diff, g);
+  X3D2C_CHECK_LAUNCH(ctx);
+  return X3D2C_OK;
 }
 
 int x3d2c_scalar_product(x3d2c_ctx* ctx, int dir, int data_loc, const double* x, const double* y, double* s) {

@@ -437,6 +437,11 @@ extern "C" int x3d2h_fieldop(x3d2h_sim* sim, const char* op_c, int dir, int data
   else if (op == "vecmult") { X3D2H_CALL(x3d2c_vecmult(S.ctx, fy->dev, fx->dev)); fx = fy; }
   else if (op == "veccopy") { S.backend.veccopy(*fy, *fx); fx = fy; }
   else if (op == "fill") X3D2H_CALL(x3d2c_field_fill(S.ctx, fx->dev, a));
+  else if (op == "set_face") {  // a = c_start; s[0] = c_end, s[1] = face
+    X3D2H_CALL(x3d2c_field_set_face(S.ctx, fx->dev, data_loc, a, s[0], (int)s[1]));
+  } else if (op == "set_face_from_field") {  // y = f_start; a = c_end; s[0] = flow_rate_diff, s[1] = face
+    X3D2H_CALL(x3d2c_field_set_face_from_field(S.ctx, fx->dev, fy->dev, data_loc, a, (int)s[1], s[0]));
+  }
   else if (op == "lincomb") {  // out = x; out = a y + out; out = (-a / 2) y + out, written over x (out aliases base)
     S.backend.veclincomb(*fx, *fx, {{a, fy}, {-a / 2, fy}});
   }
