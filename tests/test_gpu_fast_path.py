@@ -131,3 +131,29 @@ def test_tds_through_reorders(oracle, x3d2, dims, bcs, env, strict, monkeypatch)
     with pytest.raises(RuntimeError, match="rdr_out must be a reorder code that starts from dir"):
         sim.tds_fused_r("single", 2, "interpl_v2p", None, u, rdr_out=34)
     sim.close()
+
+
+def test_full_size_512_properties(x3d2):
+    """BASELINE.json configs[2] size (TGV 512^3, the benchmarked workload): the oracle would need minutes, so the
+    check is through size-independent properties of the same code paths."""
+    n = 512
+    sim = x3d2.Sim((n, n, n))
+    sim.init_tgv()
+    m0 = sim.monitor()
+    # TGV at t = 0: <u^2>/2 = 1/8 exactly, enstrophy 3/8 up to the O(dx^6) error of the compact derivative
+    assert abs(m0["ke"] - 0.125) < 1e-13 and abs(m0["enstrophy"] - 0.375) < 1e-9 and m0["div_u_max"] < 1e-11
+    sim.step(1)
+    m1 = sim.monitor()
+    # the corrected field is solenoidal to rounding, and the energy decays at the viscous rate dE/dt = -2 nu Omega
+    nu, dt = 1.0 / 1600.0, 1e-3
+    assert m1["div_u_max"] < 1e-11
+    assert abs((m0["ke"] - m1["ke"]) / dt - 2 * nu * 0.375) < 2e-3 * (2 * nu * 0.375)
+    # linearity of a distributed-tridiagonal operator and exact reorder round trip on full-size random fields
+    rng = np.random.default_rng(12)
+    a, b = rng.standard_normal(sim.shape()), rng.standard_normal(sim.shape())
+    da, db = sim.tds_solve(3, "der1st", a), sim.tds_solve(3, "der1st", b)
+    dc = sim.tds_solve(3, "der1st", 0.5 * a - 2.0 * b)
+    assert rel(dc, 0.5 * da - 2.0 * db) < TOL
+    assert abs(da.mean()) < 1e-10 * np.abs(da).max()  # the derivative of a periodic field has zero mean
+    assert np.array_equal(sim.reorder_chain(a, ["C2X", "X2Y", "Y2Z", "Z2C"]), a)
+    sim.close()
