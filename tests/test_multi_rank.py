@@ -79,10 +79,10 @@ def test_gloo_world2_exchange_patterns():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("nz,z_path", [(128, "m1 (reference order)"), (256, "m3 (fast path)")])
+@pytest.mark.parametrize("nz,z_path", [(128, "m1 (reference order)"), (256, "m4 (tma tiles)")])
 def test_two_gpus_vs_oracle(nz, z_path):
     """z-slabs on 2 GPUs against the oracle's 2-rank emulation: 64 planes per rank use the reference-order
-    DistD2 kernels with the 2x2 reduced systems, 128 planes per rank the distributed fast path (m3_edge.cu)."""
+    DistD2 kernels with the 2x2 reduced systems, 128 planes per rank the distributed fast path (m3_edge.cu + TMA kernels)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

@@ -400,10 +400,13 @@ HaloBufs carve(x3d2c_ctx* ctx) {
 }
 
 // X3D2C_TRACE=1: report on stderr which kernel family serves each call (used by tools/mgpu_check.py)
-void trace_path(const char* op, int dir, int P, bool fast) {
+// family: 4 = TMA tiles (*_m4.cu), 3 = cp.async tiles (*_m3.cu), 1 = reference-order kernels (this file)
+void trace_path(const char* op, int dir, int P, int family) {
   static int on = -1;
   if (on < 0) on = std::getenv("X3D2C_TRACE") ? 1 : 0;
-  if (on) std::fprintf(stderr, "[x3d2c] %s dir=%d ranks=%d -> %s\n", op, dir, P, fast ? "m3 (fast path)" : "m1 (reference order)");
+  if (on)
+    std::fprintf(stderr, "[x3d2c] %s dir=%d ranks=%d -> %s\n", op, dir, P,
+                 family == 4 ? "m4 (tma tiles)" : (family == 3 ? "m3 (cp.async tiles)" : "m1 (reference order)"));
 }
 }  // namespace
 
@@ -418,8 +421,9 @@ int x3d2c_tds_solve(x3d2c_ctx* ctx, int dir, double* du, const double* u, const 
   const int P = ctx->cfg.nproc_dir[dir - 1];
   if (!ctx->strict) {  // fast path: periodic uniform directions, single-rank or rank-split
     int rc = tds_m4(ctx, dir, 0, du, nullptr, u, nullptr, ops, ops, 1.0, dir, dir);
-    if (rc == X3D2C_EUNSUPPORTED) rc = tds_solve_m3(ctx, dir, du, u, ops);
-    trace_path("tds_solve", dir, P, rc != X3D2C_EUNSUPPORTED);
+    const bool tma = rc != X3D2C_EUNSUPPORTED;
+    if (!tma) rc = tds_solve_m3(ctx, dir, du, u, ops);
+    trace_path("tds_solve", dir, P, tma ? 4 : (rc != X3D2C_EUNSUPPORTED ? 3 : 1));
     if (rc != X3D2C_EUNSUPPORTED) return rc;
   }
   const dim3 block(128), grid((G + 3) / 4);
@@ -466,8 +470,9 @@ int x3d2c_tds_solve_sum(x3d2c_ctx* ctx, int dir, double* out, const double* in_a
   X3D2C_REQUIRE(out != in_a && out != in_b, "x3d2c_tds_solve_sum: out must differ from the inputs");
   if (!ctx->strict) {
     int rc = tds_m4(ctx, dir, 1, out, nullptr, in_a, in_b, op_a, op_b, 1.0, dir, dir);
-    if (rc == X3D2C_EUNSUPPORTED) rc = tds_pair_m3(ctx, dir, 0, out, nullptr, in_a, in_b, op_a, op_b, 1.0);
-    trace_path("tds_solve_sum", dir, ctx->cfg.nproc_dir[dir - 1], rc != X3D2C_EUNSUPPORTED);
+    const bool tma = rc != X3D2C_EUNSUPPORTED;
+    if (!tma) rc = tds_pair_m3(ctx, dir, 0, out, nullptr, in_a, in_b, op_a, op_b, 1.0);
+    trace_path("tds_solve_sum", dir, ctx->cfg.nproc_dir[dir - 1], tma ? 4 : (rc != X3D2C_EUNSUPPORTED ? 3 : 1));
     if (rc != X3D2C_EUNSUPPORTED) return rc;
   }
   int rc = ensure_scratch(ctx);
@@ -484,8 +489,9 @@ int x3d2c_tds_solve_dual(x3d2c_ctx* ctx, int dir, double* out_a, double* out_b, 
   X3D2C_REQUIRE(out_a != in && out_b != in && out_a != out_b, "x3d2c_tds_solve_dual: fields must be distinct");
   if (!ctx->strict) {
     int rc = tds_m4(ctx, dir, 2, out_a, out_b, in, nullptr, op_a, op_b, 1.0, dir, dir);
-    if (rc == X3D2C_EUNSUPPORTED) rc = tds_pair_m3(ctx, dir, 1, out_a, out_b, in, nullptr, op_a, op_b, 1.0);
-    trace_path("tds_solve_dual", dir, ctx->cfg.nproc_dir[dir - 1], rc != X3D2C_EUNSUPPORTED);
+    const bool tma = rc != X3D2C_EUNSUPPORTED;
+    if (!tma) rc = tds_pair_m3(ctx, dir, 1, out_a, out_b, in, nullptr, op_a, op_b, 1.0);
+    trace_path("tds_solve_dual", dir, ctx->cfg.nproc_dir[dir - 1], tma ? 4 : (rc != X3D2C_EUNSUPPORTED ? 3 : 1));
     if (rc != X3D2C_EUNSUPPORTED) return rc;
   }
   int rc = x3d2c_tds_solve(ctx, dir, out_a, in, op_a);
@@ -499,8 +505,9 @@ int x3d2c_tds_solve_axpy(x3d2c_ctx* ctx, int dir, double* y, double a, const dou
   X3D2C_REQUIRE(y != in, "x3d2c_tds_solve_axpy: y and in must be different fields");
   if (!ctx->strict) {
     int rc = tds_m4(ctx, dir, 3, y, nullptr, in, y, op, op, a, dir, dir);
-    if (rc == X3D2C_EUNSUPPORTED) rc = tds_pair_m3(ctx, dir, 2, y, nullptr, in, y, op, op, a);
-    trace_path("tds_solve_axpy", dir, ctx->cfg.nproc_dir[dir - 1], rc != X3D2C_EUNSUPPORTED);
+    const bool tma = rc != X3D2C_EUNSUPPORTED;
+    if (!tma) rc = tds_pair_m3(ctx, dir, 2, y, nullptr, in, y, op, op, a);
+    trace_path("tds_solve_axpy", dir, ctx->cfg.nproc_dir[dir - 1], tma ? 4 : (rc != X3D2C_EUNSUPPORTED ? 3 : 1));
     if (rc != X3D2C_EUNSUPPORTED) return rc;
   }
   int rc = ensure_scratch(ctx);
@@ -523,7 +530,7 @@ int x3d2c_transeq(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, c
     int rc = transeq_m4(ctx, dir, du, dv, dw, u, v, w, nu, der1st, der1st_sym, der2nd, der2nd_sym);  // TMA tiles
     const bool tma = rc != X3D2C_EUNSUPPORTED;
     if (!tma) rc = transeq_m3(ctx, dir, du, dv, dw, u, v, w, nu, der1st, der1st_sym, der2nd, der2nd_sym);
-    trace_path(tma ? "transeq[tma tiles]" : "transeq", dir, P, rc != X3D2C_EUNSUPPORTED);
+    trace_path("transeq", dir, P, tma ? 4 : (rc != X3D2C_EUNSUPPORTED ? 3 : 1));
     if (rc != X3D2C_EUNSUPPORTED) return rc;
   }
   // argument permutation of omp/backend.f90:154,168,182: component 0 is the line-aligned velocity
