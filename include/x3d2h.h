@@ -19,6 +19,12 @@ extern "C" {
 
 typedef struct x3d2h_sim x3d2h_sim;
 
+/* host-layer flag (same `flags` word as X3D2C_FLAG_*, bits >= 8 never reach the backend):
+ * issue the operator graph of the UNCHANGED reference solver (src/solver.f90:291-389,693-739,
+ * src/vector_calculus.f90:142-332, src/time_integrator.f90:166-300) call by call through the deferred procedures of
+ * base_backend_t only - no fused extension entry point. This is the drop-in path a Fortran cuda_c_backend_t gets. */
+#define X3D2H_FLAG_BASE_OPS 0x100
+
 /* keys of the reference's namelists domain_settings / solver_params (src/config.f90:104-205) */
 typedef struct {
   int dims_global[3];
@@ -33,7 +39,7 @@ typedef struct {
   const char* stagder_scheme; /* 'compact6' */
   int rank, nproc;            /* position in the job; one process per GPU */
   int device;                 /* CUDA device ordinal, -1 = current */
-  int flags;                  /* X3D2C_FLAG_* */
+  int flags;                  /* X3D2C_FLAG_* | X3D2H_FLAG_* */
   const void* nccl_unique_id; /* 128 bytes when nproc > 1 */
   const char* stretching[3];  /* 'uniform' | 'centred' | 'top-bottom' | 'bottom' per direction; NULL = uniform */
   double beta[3];             /* stretching parameter (src/config.f90 domain_settings) */

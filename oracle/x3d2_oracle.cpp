@@ -21,10 +21,24 @@ static thread_local std::string g_err;
     return ret;                           \
   }
 
+#include <omp.h>
+
 extern "C" {
 
 const char* orc_last_error() { return g_err.c_str(); }
 int orc_sz() { return SZ; }
+// OpenMP thread control: torchrun exports OMP_NUM_THREADS=1, so the timed legs set the count explicitly and report
+// the number of threads a parallel region really gets.
+void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int orc_num_threads() {
+  int n = 1;
+#pragma omp parallel
+  {
+#pragma omp single
+    n = omp_get_num_threads();
+  }
+  return n;
+}
 
 // ------------------------------------------------------------------------------------ tdsops
 void* orc_tdsops_create(int n_tds, double delta, const char* operation, const char* scheme, int bc_start,

@@ -31,6 +31,9 @@ def _load():
         build()
     lib = C.CDLL(_SO)
     lib.orc_last_error.restype = C.c_char_p
+    lib.orc_set_num_threads.argtypes = [C.c_int]
+    lib.orc_set_num_threads.restype = None
+    lib.orc_num_threads.restype = C.c_int
     lib.orc_tdsops_create.restype = C.c_void_p
     lib.orc_tdsops_create.argtypes = [C.c_int, C.c_double, C.c_char_p, C.c_char_p, C.c_int, C.c_int, _dp, _dp,
                                       C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_double]
@@ -82,6 +85,16 @@ def lib():
     if _lib is None:
         _lib = _load()
     return _lib
+
+
+def set_num_threads(n):
+    """omp_set_num_threads for the oracle (overrides OMP_NUM_THREADS, which torchrun sets to 1)."""
+    lib().orc_set_num_threads(int(n))
+
+
+def num_threads():
+    """Threads an OpenMP parallel region of the oracle really runs with."""
+    return int(lib().orc_num_threads())
 
 
 def _p(a):

@@ -15,11 +15,11 @@ import subprocess
 import numpy as np
 
 from . import lib as _libmod
-from .lib import (BC_DIRICHLET, BC_HALO, BC_NEUMANN, BC_PERIODIC, CELL, DIR_C, DIR_X, DIR_Y, DIR_Z, FLAG_STRICT, RDR,
+from .lib import (BC_DIRICHLET, BC_HALO, BC_NEUMANN, BC_PERIODIC, CELL, DIR_C, DIR_X, DIR_Y, DIR_Z, FLAG_BASE_OPS, FLAG_STRICT, RDR,
                   VERT, X3D2HConfig, build, load)
 
 __all__ = ["Sim", "build", "load", "tdsops_tables", "decompose", "geo", "waves_000", "DIR_X", "DIR_Y", "DIR_Z", "DIR_C", "VERT",
-           "CELL", "BC_PERIODIC", "BC_NEUMANN", "BC_DIRICHLET", "BC_HALO", "FLAG_STRICT", "RDR"]
+           "CELL", "BC_PERIODIC", "BC_NEUMANN", "BC_DIRICHLET", "BC_HALO", "FLAG_STRICT", "FLAG_BASE_OPS", "RDR"]
 
 _dp = C.POINTER(C.c_double)
 
@@ -121,13 +121,16 @@ class Sim:
 
     def __init__(self, dims, nproc_dir=(1, 1, 1), L=(2 * np.pi,) * 3, bcs=((0, 0), (0, 0), (0, 0)), Re=1600.0, dt=1e-3,
                  time_intg="RK3", der1st="compact6", der2nd="compact6", interpl="classic", stagder="compact6", rank=0,
-                 nproc=1, device=-1, strict=False, nccl_unique_id=None, stretching=None, beta=None):
+                 nproc=1, device=-1, strict=False, nccl_unique_id=None, stretching=None, beta=None, base_ops=False):
+        """base_ops=True: the host layer issues the unchanged reference solver's operator graph through the base_backend_t
+        entry points only (X3D2H_FLAG_BASE_OPS, the drop-in path); default: the fused extension entry points."""
         self._c, self._h = load()
         self.dims = tuple(int(d) for d in dims)
         self.periodic = [pair[0] == BC_PERIODIC for pair in bcs]
         self._nccl_id = nccl_unique_id  # keep the bytes alive
         cfg = _config(dims, nproc_dir, L, bcs, Re, dt, time_intg, der1st, der2nd, interpl, stagder, rank, nproc, device,
-                      FLAG_STRICT if strict else 0, nccl_unique_id, stretching, beta)
+                      (FLAG_STRICT if strict else 0) | (FLAG_BASE_OPS if base_ops else 0), nccl_unique_id, stretching,
+                      beta)
         self.h = C.c_void_p()
         rc = self._h.x3d2h_create(C.byref(cfg), C.byref(self.h))
         if rc != 0:

@@ -16,7 +16,7 @@
 #include <array>
 #include <complex>
 
-#include "../../../include/x3d2c.h"
+#include "../../../include/x3d2h.h"
 #include "tdsops.hpp"
 
 namespace x3d2h {
@@ -485,7 +485,7 @@ class Sim {
       bc.nproc_dir[q] = mesh.nproc_dir[q]; bc.nrank_dir[q] = mesh.nrank_dir[q]; bc.n_offset[q] = mesh.n_offset[q];
       bc.pprev[q] = mesh.pprev[q]; bc.pnext[q] = mesh.pnext[q]; bc.periodic[q] = mesh.periodic_BC[q];
     }
-    bc.sz = SZ; bc.rank = mesh.nrank; bc.nproc = mesh.nproc; bc.device = cfg.device; bc.flags = cfg.flags;
+    bc.sz = SZ; bc.rank = mesh.nrank; bc.nproc = mesh.nproc; bc.device = cfg.device; bc.flags = cfg.flags & 0xff;
     bc.nccl_unique_id = cfg.nccl_unique_id;
     X3D2H_CALL(x3d2c_create(&bc, &ctx));
     allocator.init(ctx);
@@ -544,8 +544,147 @@ class Sim {
                                     &pfft.ay[1], &pfft.by[1], &pfft.az[1], &pfft.bz[1], &backend.poisson));
   }
 
+  // ---- base-ops mode (X3D2H_FLAG_BASE_OPS): the operator graph of the UNCHANGED reference solver, issued call by
+  // call through the deferred procedures of base_backend_t only (no fused extension entry point). This is what a
+  // Fortran cuda_c_backend_t sees from solver.f90 / vector_calculus.f90 / time_integrator.f90 as they are.
+  bool base_ops() const { return (cfg.flags & X3D2H_FLAG_BASE_OPS) != 0; }
+
+  // solver.f90:291-389, statement by statement
+  void transeq_default_base(Field& du, Field& dv, Field& dw, const Field& uu, const Field& vv, const Field& ww) {
+    Allocator& A = allocator;
+    backend.transeq_x(du, dv, dw, uu, vv, ww, nu, xdirps);
+    Field* in[3] = {A.get_block(DIR_Y), A.get_block(DIR_Y), A.get_block(DIR_Y)};
+    Field* out[3] = {A.get_block(DIR_Y), A.get_block(DIR_Y), A.get_block(DIR_Y)};
+    const Field* vel[3] = {&uu, &vv, &ww};
+    Field* rhs[3] = {&du, &dv, &dw};
+    for (int i = 0; i < 3; ++i) backend.reorder(*in[i], *vel[i], RDR_X2Y);
+    backend.transeq_y(*out[0], *out[1], *out[2], *in[0], *in[1], *in[2], nu, ydirps);
+    for (int i = 0; i < 3; ++i) A.release_block(in[i]);
+    for (int i = 0; i < 3; ++i) backend.sum_yintox(*rhs[i], *out[i]);
+    for (int i = 0; i < 3; ++i) A.release_block(out[i]);
+    for (int i = 0; i < 3; ++i) in[i] = A.get_block(DIR_Z);
+    for (int i = 0; i < 3; ++i) out[i] = A.get_block(DIR_Z);
+    for (int i = 0; i < 3; ++i) backend.reorder(*in[i], *vel[i], RDR_X2Z);
+    backend.transeq_z(*out[0], *out[1], *out[2], *in[0], *in[1], *in[2], nu, zdirps);
+    for (int i = 0; i < 3; ++i) A.release_block(in[i]);
+    for (int i = 0; i < 3; ++i) backend.sum_zintox(*rhs[i], *out[i]);
+    for (int i = 0; i < 3; ++i) A.release_block(out[i]);
+  }
+
+  // vector_calculus.f90:142-246: 8 tds_solve, 5 reorder, 2 vecadd
+  void divergence_v2c_base(Field& div_u, const Field& uu, const Field& vv, const Field& ww) {
+    if (div_u.dir != DIR_Z || uu.dir != DIR_X || vv.dir != DIR_X || ww.dir != DIR_X)
+      fail("Error in divergence_v2c input/output field dirs: output must be in DIR_Z, inputs must be in DIR_X layout.");
+    Allocator& A = allocator;
+    Field* x[3] = {A.get_block(DIR_X), A.get_block(DIR_X), A.get_block(DIR_X)};
+    backend.tds_solve(*x[0], uu, xdirps.stagder_v2p);
+    backend.tds_solve(*x[1], vv, xdirps.interpl_v2p);
+    backend.tds_solve(*x[2], ww, xdirps.interpl_v2p);
+    Field* y[3] = {A.get_block(DIR_Y), A.get_block(DIR_Y), A.get_block(DIR_Y)};
+    for (int i = 0; i < 3; ++i) backend.reorder(*y[i], *x[i], RDR_X2Y);
+    for (int i = 0; i < 3; ++i) A.release_block(x[i]);
+    Field* dy[3] = {A.get_block(DIR_Y), A.get_block(DIR_Y), A.get_block(DIR_Y)};
+    backend.tds_solve(*dy[0], *y[0], ydirps.interpl_v2p);
+    backend.tds_solve(*dy[1], *y[1], ydirps.stagder_v2p);
+    backend.tds_solve(*dy[2], *y[2], ydirps.interpl_v2p);
+    for (int i = 0; i < 3; ++i) A.release_block(y[i]);
+    Field *u_z = A.get_block(DIR_Z), *w_z = A.get_block(DIR_Z);
+    backend.vecadd(1.0, *dy[1], 1.0, *dy[0]);
+    backend.reorder(*u_z, *dy[0], RDR_Y2Z);
+    backend.reorder(*w_z, *dy[2], RDR_Y2Z);
+    for (int i = 0; i < 3; ++i) A.release_block(dy[i]);
+    Field* dw_z = A.get_block(DIR_Z);
+    backend.tds_solve(div_u, *u_z, zdirps.interpl_v2p);
+    backend.tds_solve(*dw_z, *w_z, zdirps.stagder_v2p);
+    backend.vecadd(1.0, *dw_z, 1.0, div_u);
+    A.release_block(u_z); A.release_block(w_z); A.release_block(dw_z);
+  }
+
+  // vector_calculus.f90:248-332: 8 tds_solve, 5 reorder
+  void gradient_c2v_base(Field& dpdx, Field& dpdy, Field& dpdz, const Field& p) {
+    if (dpdx.dir != DIR_X || dpdy.dir != DIR_X || dpdz.dir != DIR_X || p.dir != DIR_Z)
+      fail("Error in gradient_c2v input/output field dirs: outputs must be in DIR_X, input must be in DIR_Z layout.");
+    Allocator& A = allocator;
+    Field *p_z = A.get_block(DIR_Z), *dz_z = A.get_block(DIR_Z);
+    backend.tds_solve(*p_z, p, zdirps.interpl_p2v);
+    backend.tds_solve(*dz_z, p, zdirps.stagder_p2v);
+    Field *p_y = A.get_block(DIR_Y), *dz_y = A.get_block(DIR_Y);
+    backend.reorder(*p_y, *p_z, RDR_Z2Y);
+    backend.reorder(*dz_y, *dz_z, RDR_Z2Y);
+    A.release_block(p_z); A.release_block(dz_z);
+    Field *q_y = A.get_block(DIR_Y), *dy_y = A.get_block(DIR_Y);
+    backend.tds_solve(*q_y, *p_y, ydirps.interpl_p2v);
+    backend.tds_solve(*dy_y, *p_y, ydirps.stagder_p2v);
+    A.release_block(p_y);
+    Field* dz2_y = A.get_block(DIR_Y);
+    backend.tds_solve(*dz2_y, *dz_y, ydirps.interpl_p2v);
+    A.release_block(dz_y);
+    Field* q_x = A.get_block(DIR_X);
+    backend.reorder(*q_x, *q_y, RDR_Y2X); A.release_block(q_y);
+    Field* dy_x = A.get_block(DIR_X);
+    backend.reorder(*dy_x, *dy_y, RDR_Y2X); A.release_block(dy_y);
+    Field* dz_x = A.get_block(DIR_X);
+    backend.reorder(*dz_x, *dz2_y, RDR_Y2X); A.release_block(dz2_y);
+    backend.tds_solve(dpdx, *q_x, xdirps.stagder_p2v);
+    backend.tds_solve(dpdy, *dy_x, xdirps.interpl_p2v);
+    backend.tds_solve(dpdz, *dz_x, xdirps.interpl_p2v);
+    A.release_block(q_x); A.release_block(dy_x); A.release_block(dz_x);
+  }
+
+  // solver.f90:693-739
+  void pressure_correction_base(Field& uu, Field& vv, Field& ww) {
+    Allocator& A = allocator;
+    Field* div_u = A.get_block(DIR_Z);
+    divergence_v2c_base(*div_u, uu, vv, ww);
+    Field* p = A.get_block(DIR_Z);
+    poisson_fft(*p, *div_u);  // reorder Z2C, solve_poisson, reorder C2Z (solver.f90:653-678)
+    A.release_block(div_u);
+    Field *dpdx = A.get_block(DIR_X), *dpdy = A.get_block(DIR_X), *dpdz = A.get_block(DIR_X);
+    gradient_c2v_base(*dpdx, *dpdy, *dpdz, *p);
+    A.release_block(p);
+    backend.vecadd(-1.0, *dpdx, 1.0, uu);
+    backend.vecadd(-1.0, *dpdy, 1.0, vv);
+    backend.vecadd(-1.0, *dpdz, 1.0, ww);
+    A.release_block(dpdx); A.release_block(dpdy); A.release_block(dpdz);
+  }
+
+  // time_integrator.f90:166-231 with veccopy / vecadd only
+  void runge_kutta_base(Field* curr[3], Field* deriv[3], double dt_) {
+    const int S = ti_nstage, s = ti_istage;
+    for (int i = 0; i < 3; ++i) {
+      if (s == S) {
+        if (S > 1) backend.veccopy(*curr[i], *olds[i][1]);
+        for (int j = 1; j <= S - 1; ++j) backend.vecadd(ti_rk_b[j][S] * dt_, *olds[i][j + 1], 1.0, *curr[i]);
+        backend.vecadd(ti_rk_b[S][S] * dt_, *deriv[i], 1.0, *curr[i]);
+      } else {
+        if (s == 1) backend.veccopy(*olds[i][1], *curr[i]);
+        backend.veccopy(*olds[i][s + 1], *deriv[i]);
+        if (s > 1) backend.veccopy(*curr[i], *olds[i][1]);
+        for (int j = 1; j <= s; ++j) backend.vecadd(ti_rk_a[j][s][S] * dt_, *olds[i][j + 1], 1.0, *curr[i]);
+      }
+    }
+    ti_istage = (s == S) ? 1 : s + 1;
+  }
+  // time_integrator.f90:233-300 with veccopy / vecadd only
+  void adams_bashforth_base(Field* curr[3], Field* deriv[3], double dt_) {
+    const int nstep = std::min(ti_istep, ti_nstep);
+    for (int i = 0; i < 3; ++i) {
+      backend.vecadd(ti_coeffs[1][nstep] * dt_, *deriv[i], 1.0, *curr[i]);
+      for (int j = 2; j <= nstep; ++j) backend.vecadd(ti_coeffs[j][nstep] * dt_, *olds[i][j - 1], 1.0, *curr[i]);
+      const int nrot = nstep < ti_nstep ? (ti_istep > 1 ? nstep : 0) : (ti_nstep > 2 ? nstep - 1 : 0);
+      if (nrot) {
+        Field* last = olds[i][nrot];
+        for (int q = nrot; q >= 2; --q) olds[i][q] = olds[i][q - 1];
+        olds[i][1] = last;
+      }
+      if (ti_nstep > 1) backend.veccopy(*olds[i][1], *deriv[i]);
+    }
+    ti_istep = ti_istep + 1;
+  }
+
   // solver.f90:291-389
   void transeq_default(Field& du, Field& dv, Field& dw, const Field& uu, const Field& vv, const Field& ww) {
+    if (base_ops()) return transeq_default_base(du, dv, dw, uu, vv, ww);
     Allocator& A = allocator;
     backend.transeq_x(du, dv, dw, uu, vv, ww, nu, xdirps);
     // u, v, w into both pencil layouts with one read each (reference: 3 x reorder X2Y here, 3 x reorder X2Z below)
@@ -566,6 +705,7 @@ class Sim {
 
   // vector_calculus.f90:142-246
   void divergence_v2c(Field& div_u, const Field& uu, const Field& vv, const Field& ww) {
+    if (base_ops()) return divergence_v2c_base(div_u, uu, vv, ww);
     // div_u in DIR_Z as in the reference, or in DIR_C (then the z2c reorder of poisson_fft is part of the last solve)
     if ((div_u.dir != DIR_Z && div_u.dir != DIR_C) || uu.dir != DIR_X || vv.dir != DIR_X || ww.dir != DIR_X)
       fail("Error in divergence_v2c input/output field dirs: output must be in DIR_Z, inputs must be in DIR_X layout.");
@@ -591,6 +731,7 @@ class Sim {
   // vector_calculus.f90:248-332. With sub != nullptr the x stage subtracts the gradient from (sub[0], sub[1],
   // sub[2]) instead of writing it (the vecadd(-1, dpdx, 1, u) calls of solver.f90:296-298 fused into the last solve).
   void gradient_c2v(Field& dpdx, Field& dpdy, Field& dpdz, const Field& p, Field* const* sub = nullptr) {
+    if (base_ops() && !sub) return gradient_c2v_base(dpdx, dpdy, dpdz, p);
     // p in DIR_Z as in the reference, or in DIR_C (then the c2z reorder of poisson_fft is part of the first solve)
     if (dpdx.dir != DIR_X || dpdy.dir != DIR_X || dpdz.dir != DIR_X || (p.dir != DIR_Z && p.dir != DIR_C))
       fail("Error in gradient_c2v input/output field dirs: outputs must be in DIR_X, input must be in DIR_Z layout.");
@@ -678,6 +819,7 @@ class Sim {
 
   // solver.f90:693-739
   void pressure_correction(Field& uu, Field& vv, Field& ww) {
+    if (base_ops()) return pressure_correction_base(uu, vv, ww);
     Allocator& A = allocator;
     // the Cartesian field of the FFT is written by the last solve of the divergence and read by the first solve of
     // the gradient: no z2c / c2z passes (same values as the reference's sequence)
@@ -779,7 +921,9 @@ class Sim {
     for (int sub = 1; sub <= ti_nstage; ++sub) {
       Field* deriv[3] = {allocator.get_block(DIR_X), allocator.get_block(DIR_X), allocator.get_block(DIR_X)};
       transeq_default(*deriv[0], *deriv[1], *deriv[2], *u, *v, *w);
-      if (ti_is_ab) adams_bashforth(curr, deriv, dt); else runge_kutta(curr, deriv, dt);
+      if (base_ops()) { if (ti_is_ab) adams_bashforth_base(curr, deriv, dt); else runge_kutta_base(curr, deriv, dt); }
+      else if (ti_is_ab) adams_bashforth(curr, deriv, dt);
+      else runge_kutta(curr, deriv, dt);
       u = curr[0]; v = curr[1]; w = curr[2];  // the integrators may continue in another block
       for (int i = 0; i < 3; ++i) allocator.release_block(deriv[i]);
       pressure_correction(*u, *v, *w);

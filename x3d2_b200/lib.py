@@ -11,6 +11,7 @@ DIR_X, DIR_Y, DIR_Z, DIR_C = 1, 2, 3, 4
 VERT, CELL = 0, 1110
 BC_PERIODIC, BC_NEUMANN, BC_DIRICHLET, BC_HALO = 0, 1, 2, -1
 FLAG_STRICT = 1
+FLAG_BASE_OPS = 0x100  # include/x3d2h.h: X3D2H_FLAG_BASE_OPS
 RDR = dict(X2Y=12, X2Z=13, Y2X=21, Y2Z=23, Z2X=31, Z2Y=32, C2X=41, C2Y=42, C2Z=43, X2C=14, Y2C=24, Z2C=34)
 
 _dp = C.POINTER(C.c_double)
