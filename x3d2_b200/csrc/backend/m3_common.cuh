@@ -28,7 +28,9 @@ constexpr int EXP_ROWS = DMAX;  // rows per recurrence in an exchange buffer: to
 constexpr int EXT_ROWS = 2 * EXP_ROWS;  // shared-memory rows per recurrence: EXP_ROWS from prev + EXP_ROWS from next
 
 struct Op {
-  double cfw[9];            // scale * fw * coeffs
+  double cfw[9];            // scale * fw * coeffs; exact operators: the plain coeffs of the tdsops table
+  double fs;                // exact operators: scale * fw, applied to the finished stencil sum (1 otherwise)
+  int exact;                // the stencil sum is evaluated as the reference writes it (sten_exact)
   double a, cb;             // forward / backward propagators: a = -fw*alpha, cb = -bw
   double zw[DMAX], yw[DMAX];
   double om[2 * DMAX - 1];  // index m + DMAX - 1, m = d - d'
@@ -50,6 +52,25 @@ __device__ __forceinline__ double sten(const double (&c)[9], const double (&w)[9
   for (int k = 0; k < 9; ++k)
     if (M & (1u << k)) {
       t = first ? c[k] * w[k] : fma(c[k], w[k], t);
+      first = false;
+    }
+  return t;
+}
+
+// The same sum in the reference's order and rounding (omp/kernels/distributed.f90:88-93: products rounded one by one,
+// added from tap -4 to tap +4, no FMA contraction; zero taps skipped, which does not change a bit). The second
+// derivative of a smooth field cancels to O(dx^2) of its terms, so at n = 512 / 1024 any other evaluation order
+// differs from the reference by more than the 1e-12 parity bar - with this one the right-hand
+// side is bit-identical and only the (well conditioned) sweeps round differently.
+template <unsigned M>
+__device__ __forceinline__ double sten_exact(const double (&c)[9], const double (&w)[9]) {
+  double t = 0.0;
+  bool first = true;
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+    if (M & (1u << k)) {
+      const double pr = __dmul_rn(c[k], w[k]);
+      t = first ? pr : __dadd_rn(t, pr);
       first = false;
     }
   return t;
@@ -205,7 +226,7 @@ __device__ __forceinline__ void segment_bases(int q, int l, int nseg, int& bm, i
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-bool make_op(const x3d2c_tdsops* t, double scale, bool dist, Op* o);
+bool make_op(const x3d2c_tdsops* t, double scale, bool dist, Op* o, bool exact = true);
 bool same_tables(const x3d2c_tdsops* a, const x3d2c_tdsops* b);
 int num_sms(const x3d2c_ctx* ctx);
 

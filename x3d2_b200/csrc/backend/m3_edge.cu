@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(32 * 2 * DMAX) edge_kernel(const __grid_consta
       double win[9];
 #pragma unroll
       for (int t = 0; t < 9; ++t) win[t] = src[i + t];
-      pz = fma(o.a, pz, sten<0x1FFu>(o.cfw, win));
+      pz = fma(o.a, pz, o.exact ? o.fs * sten_exact<0x1FFu>(o.cfw, win) : sten<0x1FFu>(o.cfw, win));
       z[i] = pz;
     }
     if (e >= DMAX) {  // ze of the last three segments, for the next rank
@@ -116,7 +116,7 @@ bool same_tables(const x3d2c_tdsops* a, const x3d2c_tdsops* b) {
 
 // constant set of one operator; false when the operator does not qualify for the fast path.
 // dist: the operator belongs to a rank-split periodic direction (halo boundary rows on both sides).
-bool make_op(const x3d2c_tdsops* t, double scale, bool dist, Op* o) {
+bool make_op(const x3d2c_tdsops* t, double scale, bool dist, Op* o, bool exact) {
   const int n = t->n_tds;
   if ((!t->periodic && !dist) || t->n_rhs != n || n < 4 * S || n % S) return false;
   if (dist && n < 2 * DMAX * S) return false;
@@ -129,7 +129,9 @@ bool make_op(const x3d2c_tdsops* t, double scale, bool dist, Op* o) {
         t->h_af[j] != al)
       return false;
   }
-  for (int k = 0; k < 9; ++k) o->cfw[k] = scale * fw * t->dev.coeffs[k];
+  for (int k = 0; k < 9; ++k) o->cfw[k] = exact ? t->dev.coeffs[k] : scale * fw * t->dev.coeffs[k];
+  o->fs = exact ? scale * fw : 1.0;
+  o->exact = exact ? 1 : 0;
   o->mask = t->tap_mask;
   o->a = -fw * al;
   o->cb = -bw;

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256, 3) tds_m3_kernel(const __grid_constant__ 
 #pragma unroll
       for (int k = 0; k < S; ++k) {
         wf[8] = F[woff<L>(k + 8, bm, b0, bp)];
-        pz = fma(p.o.a, pz, sten<M>(p.o.cfw, wf));
+        pz = fma(p.o.a, pz, p.o.fs * sten_exact<M>(p.o.cfw, wf));
         z[k] = pz;
 #pragma unroll
         for (int t = 0; t < 8; ++t) wf[t] = wf[t + 1];

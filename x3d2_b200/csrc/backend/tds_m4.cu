@@ -40,7 +40,7 @@ __device__ __forceinline__ void local_sweeps4(const int F, const Op& o, const in
 #pragma unroll
   for (int k = 0; k < S; ++k) {
     wf[8] = at(k + 8);
-    pz = fma(o.a, pz, sten<M>(o.cfw, wf));
+    pz = fma(o.a, pz, o.fs * sten_exact<M>(o.cfw, wf));
     z[k] = pz;
 #pragma unroll
     for (int t = 0; t < 8; ++t) wf[t] = wf[t + 1];

@@ -33,7 +33,7 @@ __device__ __forceinline__ void local_sweeps(const double* F, const Op& o, int b
 #pragma unroll
   for (int k = 0; k < S; ++k) {
     wf[8] = F[woff<L>(k + 8, bm, b0, bp)];
-    pz = fma(o.a, pz, sten<M>(o.cfw, wf));
+    pz = fma(o.a, pz, o.fs * sten_exact<M>(o.cfw, wf));
     z[k] = pz;
 #pragma unroll
     for (int t = 0; t < 8; ++t) wf[t] = wf[t + 1];

@@ -29,7 +29,8 @@ struct Params {
   const double* in[3];  // in[0] is the line-aligned velocity (conv)
   double* out[3];
   Geom g;
-  Op o_du, o_dud, o_d2u;  // scaled by -1/2, -1/2, nu
+  Op o_du, o_dud, o_d2u;  // du, dud scaled by -1/2; d2u unscaled (reference-order stencil)
+  double d2u_scale;       // nu * fw of the second derivative
   // rank-split direction only
   const double *halo_s, *halo_e, *from_prev, *from_next;
 };
@@ -59,7 +60,7 @@ __device__ __forceinline__ void component(const int fF, const int fC, const int 
       wp[8] = wf[8] * (SELF ? wf[8] : smem[fC + o]);
       p1 = fma(p.o_du.a, p1, sten<M1>(p.o_du.cfw, wf));
       p2 = fma(p.o_dud.a, p2, sten<M1>(p.o_dud.cfw, wp));
-      p3 = fma(p.o_d2u.a, p3, sten<M2>(p.o_d2u.cfw, wf));
+      p3 = fma(p.o_d2u.a, p3, sten_exact<M2>(p.o_d2u.cfw, wf));  // unscaled: nu * fw is applied below
       z1[k] = p1; z2[k] = p2; z3[k] = p3;
 #pragma unroll
       for (int t = 0; t < 8; ++t) { wf[t] = wf[t + 1]; wp[t] = wp[t + 1]; }
@@ -92,7 +93,7 @@ __device__ __forceinline__ void component(const int fF, const int fC, const int 
     for (int k = 0; k < S; ++k) z3[k] = fma(p.o_d2u.Cp[k], yi, fma(p.o_d2u.W[k], zi, z3[k]));
     carries<L, DIST>(cur + 1 * fd + pad0, oth + 1 * fd + pad0, st, xp + 1 * xs, xn + 1 * xs, p.o_dud, q, nseg, zi, yi);
 #pragma unroll
-    for (int k = 0; k < S; ++k) z2[k] = fma(p.o_dud.Cp[k], yi, fma(p.o_dud.W[k], zi, z2[k])) + z3[k];
+    for (int k = 0; k < S; ++k) z2[k] = fma(p.d2u_scale, z3[k], fma(p.o_dud.Cp[k], yi, fma(p.o_dud.W[k], zi, z2[k])));
   }
   {  // -1/2 d f, combined with conv
     double zi, yi;
@@ -208,9 +209,13 @@ int transeq_m3(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, cons
   const bool split = ctx->cfg.nproc_dir[dir - 1] > 1 || ctx->force_dist;
   if (split && !dist_supported(ctx, dir, n)) return X3D2C_EUNSUPPORTED;
   Params p{};
-  if (!make_op(der1st, -0.5, split, &p.o_du) || !make_op(der1st, -0.5, split, &p.o_dud) ||
-      !make_op(der2nd, nu, split, &p.o_d2u))
+  // du, d(u conv): FMA stencils with -1/2 and fw folded in; d2u: the reference's summation order (sten_exact), its
+  // recurrence runs unscaled (the edge kernel uses the same Op) and nu * fw multiplies the finished second derivative
+  if (!make_op(der1st, -0.5, split, &p.o_du, false) || !make_op(der1st, -0.5, split, &p.o_dud, false) ||
+      !make_op(der2nd, nu, split, &p.o_d2u, true))
     return X3D2C_EUNSUPPORTED;
+  p.d2u_scale = p.o_d2u.fs;
+  p.o_d2u.fs = 1.0;
   // Tile width L (lanes), threads = L * nseg per CTA: the choice that keeps most threads resident per SM (shared
   // memory and the 255-register budget both limit it), rows of at least one 32-byte DRAM sector (L >= 4) when
   // possible, and on a tie more CTAs per SM (their copy and FP64 phases interleave). X3D2C_TRANSEQ_THREADS

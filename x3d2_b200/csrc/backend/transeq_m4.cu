@@ -29,7 +29,8 @@ struct Params4 {
   CUtensorMap in[3];   // in[0] is the line-aligned velocity (conv)
   CUtensorMap out[3];
   int tiles;
-  Op o_du, o_dud, o_d2u;  // scaled by -1/2, -1/2, nu
+  Op o_du, o_dud, o_d2u;  // du, dud scaled by -1/2; d2u unscaled (reference-order stencil)
+  double d2u_scale;       // nu * fw of the second derivative
   // rank-split direction only: received halos (SZ, 4, 3, G) and carries (SZ, 3, 9, G)
   const double *halo_s, *halo_e, *from_prev, *from_next;
 };
@@ -68,7 +69,7 @@ __device__ __forceinline__ void component4(const int fF, const int fC, const int
       load(k + 8, wf[8], wp[8]);
       p1 = fma(p.o_du.a, p1, sten<0x6Cu>(p.o_du.cfw, wf));
       p2 = fma(p.o_dud.a, p2, sten<0x6Cu>(p.o_dud.cfw, wp));
-      p3 = fma(p.o_d2u.a, p3, sten<0x7Cu>(p.o_d2u.cfw, wf));
+      p3 = fma(p.o_d2u.a, p3, sten_exact<0x7Cu>(p.o_d2u.cfw, wf));  // unscaled: nu * fw is applied below
       z1[k] = p1; z2[k] = p2; z3[k] = p3;
 #pragma unroll
       for (int t = 0; t < 8; ++t) { wf[t] = wf[t + 1]; wp[t] = wp[t + 1]; }
@@ -100,7 +101,7 @@ __device__ __forceinline__ void component4(const int fF, const int fC, const int
     for (int k = 0; k < S; ++k) z3[k] = fma(p.o_d2u.Cp[k], yi, fma(p.o_d2u.W[k], zi, z3[k]));
     carries<L, DIST>(cz + 1 * NT + l, cz + 4 * NT + l, L, xp + 1 * xs, xn + 1 * xs, p.o_dud, q, nseg, zi, yi);
 #pragma unroll
-    for (int k = 0; k < S; ++k) z2[k] = fma(p.o_dud.Cp[k], yi, fma(p.o_dud.W[k], zi, z2[k])) + z3[k];
+    for (int k = 0; k < S; ++k) z2[k] = fma(p.d2u_scale, z3[k], fma(p.o_dud.Cp[k], yi, fma(p.o_dud.W[k], zi, z2[k])));
   }
   {
     double zi, yi;
@@ -259,9 +260,13 @@ int transeq_m4(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, cons
   int L = 0, NT = 0;
   if (!(split ? dist_shape(n, &L, &NT) : tile_shape(n, &L, &NT))) return X3D2C_EUNSUPPORTED;
   Params4 p{};
-  if (!make_op(der1st, -0.5, split, &p.o_du) || !make_op(der1st, -0.5, split, &p.o_dud) ||
-      !make_op(der2nd, nu, split, &p.o_d2u))
+  // du, d(u conv): FMA stencils with -1/2 and fw folded in; d2u: the reference's summation order (sten_exact), its
+  // recurrence runs unscaled (the edge kernel uses the same Op) and nu * fw multiplies the finished second derivative
+  if (!make_op(der1st, -0.5, split, &p.o_du, false) || !make_op(der1st, -0.5, split, &p.o_dud, false) ||
+      !make_op(der2nd, nu, split, &p.o_d2u, true))
     return X3D2C_EUNSUPPORTED;
+  p.d2u_scale = p.o_d2u.fs;
+  p.o_d2u.fs = 1.0;
   const double* in[3];
   double* out[3];
   if (dir == X3D2C_DIR_X) { out[0] = du; out[1] = dv; out[2] = dw; in[0] = u; in[1] = v; in[2] = w; }
