@@ -216,9 +216,25 @@ int x3d2c_fft_backward(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_c);
 /* debugging / tests: copy the spectral buffer (reference index order (i, j, k), interleaved re/im) to the host */
 int x3d2c_poisson_get_spectrum(x3d2c_ctx* ctx, x3d2c_poisson* p, double* host_spec);
 
-/* ---- not on the hot path of any BASELINE.json config: reported as unsupported
- * transeq_species (src/backend/backend.f90:88-106) */
-int x3d2c_transeq_species(x3d2c_ctx* ctx);
+/* ---- transeq_species (src/backend/backend.f90:88-106, omp/backend.f90:186-233): one scalar `spec` advected by the
+ * line-aligned velocity `uvw`; der1st / der1st_sym / der2nd of dirps; sync != 0 also exchanges the velocity halos */
+int x3d2c_transeq_species(x3d2c_ctx* ctx, int dir, double* dspec, const double* uvw, const double* spec, double nu,
+                          const x3d2c_tdsops* der1st, const x3d2c_tdsops* der1st_sym, const x3d2c_tdsops* der2nd,
+                          int sync);
+
+/* ---- slice_max_sum (src/backend/backend.f90:238-253, omp/backend.f90:816-881): signed max and signed sum of the
+ * plane i_slice (1-based) along the field's own direction; rank-local, the caller reduces across ranks. Synchronous. */
+int x3d2c_slice_max_sum(x3d2c_ctx* ctx, int dir, int data_loc, const double* f, int i_slice, double* max_val,
+                        double* sum_val);
+
+/* ---- compute_vorticity / compute_qcriterion (src/backend/backend.f90:310-325, omp/backend.f90:616-649): pointwise
+ * |curl u| and Q = -1/2 (dudx^2 + dvdy^2 + dwdz^2) - dudy dvdx - dudz dwdx - dvdz dwdy over whole padded blocks */
+int x3d2c_compute_vorticity(x3d2c_ctx* ctx, double* field_out, const double* dudx, const double* dudy,
+                            const double* dudz, const double* dvdx, const double* dvdy, const double* dvdz,
+                            const double* dwdx, const double* dwdy, const double* dwdz);
+int x3d2c_compute_qcriterion(x3d2c_ctx* ctx, double* field_out, const double* dudx, const double* dudy,
+                             const double* dudz, const double* dvdx, const double* dvdy, const double* dvdz,
+                             const double* dwdx, const double* dwdy, const double* dwdz);
 
 #ifdef __cplusplus
 }

@@ -84,6 +84,15 @@ int x3d2h_monitor(x3d2h_sim* sim, double out[4]);
 int x3d2h_transeq(x3d2h_sim* sim, const double* u, const double* v, const double* w, double* du, double* dv, double* dw);
 int x3d2h_transeq_dir(x3d2h_sim* sim, int dir, const double* u, const double* v, const double* w, double* du,
                       double* dv, double* dw);
+/* transeq_lowmem (src/solver.f90:391-505); u_back (may be NULL): u after its x -> y -> z -> x round trip */
+int x3d2h_transeq_lowmem(x3d2h_sim* sim, const double* u, const double* v, const double* w, double* du, double* dv,
+                         double* dw, double* u_back);
+/* transeq_species for one scalar (src/solver.f90:507-600) */
+int x3d2h_transeq_species(x3d2h_sim* sim, const double* u, const double* v, const double* w, const double* spec,
+                          double nu_s, double* dspec);
+/* compute_vorticity / compute_qcriterion: what = "vorticity" | "qcriterion"; grads = dudx dudy dudz dvdx ... dwdz */
+int x3d2h_derived(x3d2h_sim* sim, const char* what, const double* const* grads, double* out);
+int x3d2h_slice_max_sum(x3d2h_sim* sim, int dir, int data_loc, const double* x, int i_slice, double* mx, double* sum);
 int x3d2h_tds_solve(x3d2h_sim* sim, int dir, const char* opname, int in_loc, const double* in, double* out, int* out_loc);
 /* x3d2c_tds_solve_sum / _dual / _axpy on host data. mode "sum": out_a = A(in_a) + B(in_b); "dual": out_a = A(in_a),
  * out_b = B(in_a); "axpy": out_a = in_b + a A(in_a) (in_b has the output's extents) */

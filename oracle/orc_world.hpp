@@ -705,6 +705,60 @@ class World {
     release_block(du_z); release_block(dv_z); release_block(dw_z);
   }
 
+  // ---------------------------------------------------------------- solver.f90:391-505 (transeq_lowmem)
+  // u, v, w are released after the x2y reorders and come back from the z layout (reorder Z2X) in new blocks
+  void transeq_lowmem(WField& du, WField& dv, WField& dw, WField*& uu, WField*& vv, WField*& ww) {
+    transeq_x(du, dv, dw, *uu, *vv, *ww, nu);
+    WField *u_y = get_block(DIR_Y), *v_y = get_block(DIR_Y), *w_y = get_block(DIR_Y);
+    reorder(*u_y, *uu, RDR_X2Y); reorder(*v_y, *vv, RDR_X2Y); reorder(*w_y, *ww, RDR_X2Y);
+    release_block(uu); release_block(vv); release_block(ww);
+    WField *du_y = get_block(DIR_Y), *dv_y = get_block(DIR_Y), *dw_y = get_block(DIR_Y);
+    transeq_y(*du_y, *dv_y, *dw_y, *u_y, *v_y, *w_y, nu);
+    sum_yintox(du, *du_y); sum_yintox(dv, *dv_y); sum_yintox(dw, *dw_y);
+    release_block(du_y); release_block(dv_y); release_block(dw_y);
+    WField *u_z = get_block(DIR_Z), *v_z = get_block(DIR_Z), *w_z = get_block(DIR_Z);
+    reorder(*u_z, *u_y, RDR_Y2Z); reorder(*v_z, *v_y, RDR_Y2Z); reorder(*w_z, *w_y, RDR_Y2Z);
+    release_block(u_y); release_block(v_y); release_block(w_y);
+    WField *du_z = get_block(DIR_Z), *dv_z = get_block(DIR_Z), *dw_z = get_block(DIR_Z);
+    transeq_z(*du_z, *dv_z, *dw_z, *u_z, *v_z, *w_z, nu);
+    sum_zintox(du, *du_z); sum_zintox(dv, *dv_z); sum_zintox(dw, *dw_z);
+    release_block(du_z); release_block(dv_z); release_block(dw_z);
+    uu = get_block(DIR_X); vv = get_block(DIR_X); ww = get_block(DIR_X);
+    reorder(*uu, *u_z, RDR_Z2X); reorder(*vv, *v_z, RDR_Z2X); reorder(*ww, *w_z, RDR_Z2X);
+    release_block(u_z); release_block(v_z); release_block(w_z);
+  }
+
+  // ---------------------------------------------------------------- omp/backend.f90:186-233 (transeq_species_omp)
+  void transeq_species_dir(WField& dspec, const WField& uvw, const WField& spec, double nu_, const std::vector<Dirps>& dps,
+                           bool sync) {
+    const int dir = dps[0].dir, ng = n_groups(dir), npad = n_pad(dir);
+    for (int r = 0; r < P; ++r) {
+      const int n = dps[r].der1st.n_tds;
+      if (sync) copy_into_buffers(bufs[r].u_send_s, bufs[r].u_send_e, uvw.r[r].data(), npad, n, ng);
+      copy_into_buffers(bufs[r].v_send_s, bufs[r].v_send_e, spec.r[r].data(), npad, n, ng);
+    }
+    if (sync) exchange(dir, &RankBufs::u_recv_s, &RankBufs::u_recv_e, &RankBufs::u_send_s, &RankBufs::u_send_e);
+    exchange(dir, &RankBufs::v_recv_s, &RankBufs::v_recv_e, &RankBufs::v_send_s, &RankBufs::v_send_e);
+    transeq_dist_component(dspec, spec, uvw, nu_, HV, HU, op(dps, &Dirps::der1st), op(dps, &Dirps::der1st_sym),
+                           op(dps, &Dirps::der2nd), dir);
+  }
+  // solver.f90:507-600 for one species
+  void transeq_species(WField& rhs, const WField& uu, const WField& vv, const WField& ww, const WField& spec, double nu_s) {
+    transeq_species_dir(rhs, uu, spec, nu_s, xdirps, true);
+    WField *v_y = get_block(DIR_Y), *spec_y = get_block(DIR_Y), *dspec_y = get_block(DIR_Y);
+    reorder(*v_y, vv, RDR_X2Y);
+    reorder(*spec_y, spec, RDR_X2Y);
+    transeq_species_dir(*dspec_y, *v_y, *spec_y, nu_s, ydirps, true);
+    sum_yintox(rhs, *dspec_y);
+    release_block(v_y); release_block(spec_y); release_block(dspec_y);
+    WField *w_z = get_block(DIR_Z), *spec_z = get_block(DIR_Z), *dspec_z = get_block(DIR_Z);
+    reorder(*w_z, ww, RDR_X2Z);
+    reorder(*spec_z, spec, RDR_X2Z);
+    transeq_species_dir(*dspec_z, *w_z, *spec_z, nu_s, zdirps, true);
+    sum_zintox(rhs, *dspec_z);
+    release_block(w_z); release_block(spec_z); release_block(dspec_z);
+  }
+
   // ---------------------------------------------------------------- vector_calculus.f90:142-246
   void divergence_v2c(WField& div_u, const WField& uu, const WField& vv, const WField& ww) {
     if (div_u.dir != DIR_Z || uu.dir != DIR_X || vv.dir != DIR_X || ww.dir != DIR_X) fail("divergence_v2c dirs");

@@ -297,6 +297,39 @@ int orc_world_transeq(void* h, const double* u, const double* v, const double* w
   ORC_CATCH(1)
 }
 
+// transeq_lowmem (solver.f90:391-505): same right-hand side as transeq_default, velocities handed back in new blocks
+int orc_world_transeq_lowmem(void* h, const double* u, const double* v, const double* w, double* du, double* dv,
+                             double* dw, double* u_back) {
+  ORC_TRY
+  auto* W = (World*)h;
+  WField *fu = W->get_block(DIR_X), *fv = W->get_block(DIR_X), *fw = W->get_block(DIR_X);
+  WField *a = W->get_block(DIR_X), *b = W->get_block(DIR_X), *c = W->get_block(DIR_X);
+  W->set_field_from_global(*fu, u, VERT); W->set_field_from_global(*fv, v, VERT); W->set_field_from_global(*fw, w, VERT);
+  W->transeq_lowmem(*a, *b, *c, fu, fv, fw);
+  W->get_field_to_global(du, *a, VERT); W->get_field_to_global(dv, *b, VERT); W->get_field_to_global(dw, *c, VERT);
+  fu->data_loc = VERT;
+  if (u_back) W->get_field_to_global(u_back, *fu, VERT);
+  for (WField* f : {fu, fv, fw, a, b, c}) W->release_block(f);
+  return 0;
+  ORC_CATCH(1)
+}
+
+// transeq_species (solver.f90:507-600 with omp/backend.f90:186-233) for one scalar
+int orc_world_transeq_species(void* h, const double* u, const double* v, const double* w, const double* spec,
+                              double nu_s, double* dspec) {
+  ORC_TRY
+  auto* W = (World*)h;
+  WField *fu = W->get_block(DIR_X), *fv = W->get_block(DIR_X), *fw = W->get_block(DIR_X), *fs = W->get_block(DIR_X);
+  WField* a = W->get_block(DIR_X);
+  W->set_field_from_global(*fu, u, VERT); W->set_field_from_global(*fv, v, VERT); W->set_field_from_global(*fw, w, VERT);
+  W->set_field_from_global(*fs, spec, VERT);
+  W->transeq_species(*a, *fu, *fv, *fw, *fs, nu_s);
+  W->get_field_to_global(dspec, *a, VERT);
+  for (WField* f : {fu, fv, fw, fs, a}) W->release_block(f);
+  return 0;
+  ORC_CATCH(1)
+}
+
 // one directional transeq (backend%transeq_x/y/z) on vertex data given in Cartesian order
 int orc_world_transeq_dir(void* h, int dir, const double* u, const double* v, const double* w, double* du,
                           double* dv, double* dw) {

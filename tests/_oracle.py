@@ -55,6 +55,8 @@ def _load():
         orc_world_monitor=[C.c_void_p, _dp],
         orc_world_transeq=[C.c_void_p] + [_dp] * 6,
         orc_world_transeq_dir=[C.c_void_p, C.c_int] + [_dp] * 6,
+        orc_world_transeq_lowmem=[C.c_void_p] + [_dp] * 7,
+        orc_world_transeq_species=[C.c_void_p] + [_dp] * 4 + [C.c_double, _dp],
         orc_world_tds_solve=[C.c_void_p, C.c_int, C.c_char_p, C.c_int, _dp, _dp, _ip],
         orc_world_divergence=[C.c_void_p] + [_dp] * 4,
         orc_world_gradient=[C.c_void_p] + [_dp] * 4,
@@ -244,6 +246,19 @@ class World:
         _chk(lib().orc_world_transeq_dir(self.h, dir, _p(u), _p(v), _p(w), _p(a), _p(b), _p(c)))
         return a, b, c
 
+    def transeq_lowmem(self, u, v, w):
+        """solver.f90:391-505; returns (du, dv, dw, u after its round trip x -> y -> z -> x)."""
+        u, v, w = _f(u), _f(v), _f(w)
+        a, b, c, ub = self._out(), self._out(), self._out(), self._out()
+        _chk(lib().orc_world_transeq_lowmem(self.h, _p(u), _p(v), _p(w), _p(a), _p(b), _p(c), _p(ub)))
+        return a, b, c, ub
+
+    def transeq_species(self, u, v, w, spec, nu_s):
+        u, v, w, spec = _f(u), _f(v), _f(w), _f(spec)
+        d = self._out()
+        _chk(lib().orc_world_transeq_species(self.h, _p(u), _p(v), _p(w), _p(spec), float(nu_s), _p(d)))
+        return d
+
     def tds_solve(self, dir, opname, f, in_loc=VERT):
         f = _f(f)
         move = {"stagder_v2p": 1, "interpl_v2p": 1, "stagder_p2v": -1, "interpl_p2v": -1}.get(opname, 0)
@@ -372,3 +387,22 @@ def field_set_face_from_field(f, f_start, c_end, face, flow_rate_diff=0.0):
     else:
         raise RuntimeError("field_set_face_from_field: only X_FACE and Y_FACE supported.")
     return g
+
+
+def compute_vorticity(g):
+    """compute_vorticity_omp (omp/backend.f90:616-630); g = (dudx, dudy, dudz, dvdx, dvdy, dvdz, dwdx, dwdy, dwdz)."""
+    dudx, dudy, dudz, dvdx, dvdy, dvdz, dwdx, dwdy, dwdz = g
+    return np.sqrt((dwdy - dvdz) * (dwdy - dvdz) + (dudz - dwdx) * (dudz - dwdx) + (dvdx - dudy) * (dvdx - dudy))
+
+
+def compute_qcriterion(g):
+    """compute_qcriterion_omp (omp/backend.f90:632-649)."""
+    dudx, dudy, dudz, dvdx, dvdy, dvdz, dwdx, dwdy, dwdz = g
+    return -0.5 * (dudx * dudx + dvdy * dvdy + dwdz * dwdz) - dudy * dvdx - dudz * dwdx - dvdz * dwdy
+
+
+def slice_max_sum(f, dir, i_slice):
+    """slice_max_sum_omp (omp/backend.f90:816-881) on a Cartesian [nz, ny, nx] array: signed max and sum of the plane
+    i_slice (1-based) along `dir`."""
+    pl = {DIR_X: f[:, :, i_slice - 1], DIR_Y: f[:, i_slice - 1, :], DIR_Z: f[i_slice - 1, :, :]}[dir]
+    return float(pl.max()), float(pl.sum())

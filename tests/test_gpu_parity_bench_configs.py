@@ -118,15 +118,15 @@ def test_smooth_full_transeq_and_pressure_512_lines(oracle, x3d2):
 @pytest.mark.parametrize("time_intg,steps", [("RK3", 2), ("AB3", 4)])
 def test_base_ops_dropin_graph(oracle, x3d2, time_intg, steps):
     """X3D2H_FLAG_BASE_OPS: the unchanged reference solver's operator graph issued through the base_backend_t entry
-    points only (what a Fortran cuda_c_backend_t sees). Strict kernels: bit-exact against the oracle, which executes
-    the same statement sequence; fast kernels: 1e-12; and fused host layer == base-ops host layer to 1e-12."""
+    points only (what a Fortran cuda_c_backend_t sees): 1e-12 against the oracle with strict and fast kernels, and with
+    strict kernels bit-identical to the fused host layer."""
     n = 64
     ref = oracle.World((n, n, n), time_intg=time_intg)
     ref.init_tgv()
     ref.step(steps)
     exp = ref.get_uvw()
     scale = max(np.abs(b).max() for b in exp)
-    launches = {}
+    launches, fields = {}, {}
     for strict in (True, False):
         for base in (True, False):
             sim = x3d2.Sim((n, n, n), time_intg=time_intg, strict=strict, base_ops=base)
@@ -134,12 +134,12 @@ def test_base_ops_dropin_graph(oracle, x3d2, time_intg, steps):
             l0 = sim.launch_count()
             sim.step(steps)
             launches[(strict, base)] = sim.launch_count() - l0
-            got = sim.get_uvw()
-            if strict:
-                assert all(np.array_equal(a, b) for a, b in zip(got, exp)), (strict, base)
-            else:
-                assert max(np.abs(a - b).max() for a, b in zip(got, exp)) / scale < TOL, (strict, base)
+            got = fields[(strict, base)] = sim.get_uvw()
+            assert max(np.abs(a - b).max() for a, b in zip(got, exp)) / scale < TOL, (strict, base)
             sim.close()
+    # strict kernels: every fused extension runs as exactly the reference's call sequence, so the two host layers
+    # agree bit for bit (the oracle itself differs in the last bits: its FFT is not cuFFT)
+    assert all(np.array_equal(a, b) for a, b in zip(fields[(True, True)], fields[(True, False)]))
     # the base-ops graph really is the longer one: 3 transeq + 18 reorders + 6 sums + 16 solves + vecadd/veccopy per stage
     assert launches[(False, True)] > launches[(False, False)]
     print(time_intg, "launches per", steps, "steps (strict, base_ops):", launches)

@@ -208,6 +208,33 @@ class Sim:
         _chk(self._h.x3d2h_transeq_dir(self.h, dir, _p(u), _p(v), _p(w), _p(a), _p(b), _p(c)))
         return a, b, c
 
+    def transeq_lowmem(self, u, v, w):
+        """solver.f90:391-505: (du, dv, dw, u after its x -> y -> z -> x round trip)."""
+        u, v, w = _f(u), _f(v), _f(w)
+        a, b, c, ub = self._out(), self._out(), self._out(), self._out()
+        _chk(self._h.x3d2h_transeq_lowmem(self.h, _p(u), _p(v), _p(w), _p(a), _p(b), _p(c), _p(ub)))
+        return a, b, c, ub
+
+    def transeq_species(self, u, v, w, spec, nu_s):
+        u, v, w, spec = _f(u), _f(v), _f(w), _f(spec)
+        d = self._out()
+        _chk(self._h.x3d2h_transeq_species(self.h, _p(u), _p(v), _p(w), _p(spec), float(nu_s), _p(d)))
+        return d
+
+    def derived(self, what, grads):
+        """compute_vorticity / compute_qcriterion from the nine velocity gradients (dudx, dudy, ..., dwdz)."""
+        g = [_f(a) for a in grads]
+        arr = (_dp * 9)(*[_p(a) for a in g])
+        out = self._out()
+        _chk(self._h.x3d2h_derived(self.h, what.encode(), arr, _p(out)))
+        return out
+
+    def slice_max_sum(self, dir, x, i_slice, loc=VERT):
+        x = _f(x)
+        mx, sm = C.c_double(0), C.c_double(0)
+        _chk(self._h.x3d2h_slice_max_sum(self.h, dir, loc, _p(x), i_slice, C.byref(mx), C.byref(sm)))
+        return mx.value, sm.value
+
     def tds_solve(self, dir, opname, f, in_loc=VERT):
         f = _f(f)
         move = {"stagder_v2p": 1, "interpl_v2p": 1, "stagder_p2v": -1, "interpl_p2v": -1}.get(opname, 0)

@@ -209,9 +209,4 @@ int x3d2c_tdsops_destroy(x3d2c_ctx* ctx, x3d2c_tdsops* ops) {
   return X3D2C_OK;
 }
 
-int x3d2c_transeq_species(x3d2c_ctx*) {
-  set_error("transeq_species is not implemented by the cuda_c backend (n_species = 0 in every supported case)");
-  return X3D2C_EUNSUPPORTED;
-}
-
 }  // extern "C"

@@ -4,6 +4,8 @@
 // CUDA-Fortran kernels of src/backend/cuda/kernels/fieldops.f90.
 // Streaming ops move 128-bit vectors with a grid of 148 SMs x 8 CTAs; reductions are a deterministic
 // two-stage tree (per-CTA partials in a fixed order, then one CTA), not per-thread atomics.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace x3d2c {
@@ -199,6 +201,78 @@ reduce_stage2(const double* __restrict__ part_sum, const double* __restrict__ pa
   if (threadIdx.x == 0) { out[0] = sh_s[0]; out[1] = sh_m[0]; }
 }
 
+// slice_max_sum (omp/backend.f90:816-881): signed maximum and signed sum over the plane j = i_slice of a directional
+// field, rank-local. One warp per group row; same two-stage deterministic tree as the other reductions.
+__global__ void __launch_bounds__(kThreads)
+slice_stage1(const double* __restrict__ x, const RedGeom q, const int j, double* __restrict__ part_sum,
+             double* __restrict__ part_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warps_total = gridDim.x * (kThreads / 32);
+  double s = 0.0, m = -1.7976931348623157e308;  // -huge(1._dp)
+  for (int g = blockIdx.x * (kThreads / 32) + warp; g < q.n_groups; g += warps_total) {
+    const int blk = g % q.nblk, pl = g / q.nblk;
+    if ((blk * SZ + lane) < q.n_lane_dim && pl < q.n_plane_dim) {
+      const double v = x[((size_t)g * q.n_pad + j) * SZ + lane];
+      s += v;
+      m = fmax(m, v);
+    }
+  }
+  __shared__ double sh_s[kThreads / 32], sh_m[kThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  }
+  if (lane == 0) { sh_s[warp] = s; sh_m[warp] = m; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tm = -1.7976931348623157e308;
+    for (int w = 0; w < kThreads / 32; ++w) { ts += sh_s[w]; tm = fmax(tm, sh_m[w]); }
+    part_sum[blockIdx.x] = ts;
+    part_max[blockIdx.x] = tm;
+  }
+}
+__global__ void __launch_bounds__(256)
+slice_stage2(const double* __restrict__ part_sum, const double* __restrict__ part_max, const int n,
+             double* __restrict__ out) {
+  __shared__ double sh_s[256], sh_m[256];
+  double s = 0.0, m = -1.7976931348623157e308;
+  for (int i = threadIdx.x; i < n; i += 256) { s += part_sum[i]; m = fmax(m, part_max[i]); }
+  sh_s[threadIdx.x] = s; sh_m[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sh_s[threadIdx.x] += sh_s[threadIdx.x + o];
+      sh_m[threadIdx.x] = fmax(sh_m[threadIdx.x], sh_m[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = sh_s[0]; out[1] = sh_m[0]; }
+}
+
+// compute_vorticity / compute_qcriterion (omp/backend.f90:616-649): pointwise over the whole padded block, the
+// expressions in the reference's order with separately rounded operations
+struct Grad9 { const double* g[9]; };  // dudx dudy dudz dvdx dvdy dvdz dwdx dwdy dwdz
+template <bool QCRIT>
+__global__ void __launch_bounds__(kThreads)
+derive_kernel(double* __restrict__ out, const __grid_constant__ Grad9 q, const long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double dudx = q.g[0][i], dudy = q.g[1][i], dudz = q.g[2][i], dvdx = q.g[3][i], dvdy = q.g[4][i],
+                 dvdz = q.g[5][i], dwdx = q.g[6][i], dwdy = q.g[7][i], dwdz = q.g[8][i];
+    double r;
+    if (QCRIT) {
+      const double tr = __dadd_rn(__dadd_rn(__dmul_rn(dudx, dudx), __dmul_rn(dvdy, dvdy)), __dmul_rn(dwdz, dwdz));
+      r = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(-0.5, tr), -__dmul_rn(dudy, dvdx)), -__dmul_rn(dudz, dwdx)),
+                    -__dmul_rn(dvdz, dwdy));
+    } else {
+      const double a = __dadd_rn(dwdy, -dvdz), b = __dadd_rn(dudz, -dwdx), c = __dadd_rn(dvdx, -dudy);
+      r = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(c, c)));
+    }
+    out[i] = r;
+  }
+}
+
 int red_geom(const x3d2c_ctx* ctx, int dir, int data_loc, RedGeom* q) {
   int dims[3];
   int rc = x3d2c::get_dims_dataloc(ctx, data_loc, dims, false);
@@ -368,6 +442,50 @@ int x3d2c_field_max_mean(x3d2c_ctx* ctx, int dir, int data_loc, const double* f,
   *max_val = m;
   *mean_val = s / ((double)g[0] * g[1] * g[2]);  // omp/backend.f90:802
   return X3D2C_OK;
+}
+
+int x3d2c_slice_max_sum(x3d2c_ctx* ctx, int dir, int data_loc, const double* f, int i_slice, double* max_val,
+                        double* sum_val) {
+  X3D2C_REQUIRE(ctx && f && max_val && sum_val, "x3d2c_slice_max_sum: null argument");
+  X3D2C_REQUIRE(dir != X3D2C_DIR_C, "slice_max_sum does not support DIR_C fields!");
+  RedGeom q;
+  int rc = red_geom(ctx, dir, data_loc, &q);
+  if (rc) return rc;
+  X3D2C_REQUIRE(i_slice >= 1 && i_slice <= q.n_line, "slice_max_sum: i_slice out of range");
+  double* ps = ctx->red;
+  double* pm = ctx->red + ctx->red_blocks;
+  double* out = ctx->red + 2 * ctx->red_blocks;
+  const int blocks = std::min(ctx->red_blocks, (q.n_groups + kThreads / 32 - 1) / (kThreads / 32));
+  slice_stage1<<<blocks, kThreads, 0, ctx->stream>>>(f, q, i_slice - 1, ps, pm);
+  X3D2C_CHECK_LAUNCH(ctx);
+  slice_stage2<<<1, 256, 0, ctx->stream>>>(ps, pm, blocks, out);
+  X3D2C_CHECK_LAUNCH(ctx);
+  return fetch2(ctx, sum_val, max_val);  // rank-local: the caller reduces across ranks (omp/backend.f90:877-879)
+}
+
+static int derive(x3d2c_ctx* ctx, bool qcrit, double* out, const double* const* grads) {
+  X3D2C_REQUIRE(ctx && out && grads, "compute_vorticity / compute_qcriterion: null argument");
+  Grad9 q;
+  for (int k = 0; k < 9; ++k) {
+    X3D2C_REQUIRE(grads[k], "compute_vorticity / compute_qcriterion: null gradient field");
+    q.g[k] = grads[k];
+  }
+  if (qcrit) derive_kernel<true><<<kBlocks, kThreads, 0, ctx->stream>>>(out, q, ctx->ngrid);
+  else derive_kernel<false><<<kBlocks, kThreads, 0, ctx->stream>>>(out, q, ctx->ngrid);
+  X3D2C_CHECK_LAUNCH(ctx);
+  return X3D2C_OK;
+}
+int x3d2c_compute_vorticity(x3d2c_ctx* ctx, double* field_out, const double* dudx, const double* dudy,
+                            const double* dudz, const double* dvdx, const double* dvdy, const double* dvdz,
+                            const double* dwdx, const double* dwdy, const double* dwdz) {
+  const double* g[9] = {dudx, dudy, dudz, dvdx, dvdy, dvdz, dwdx, dwdy, dwdz};
+  return derive(ctx, false, field_out, g);
+}
+int x3d2c_compute_qcriterion(x3d2c_ctx* ctx, double* field_out, const double* dudx, const double* dudy,
+                             const double* dudz, const double* dvdx, const double* dvdy, const double* dvdz,
+                             const double* dwdx, const double* dwdy, const double* dwdz) {
+  const double* g[9] = {dudx, dudy, dudz, dvdx, dvdy, dvdz, dwdx, dwdy, dwdz};
+  return derive(ctx, true, field_out, g);
 }
 
 int x3d2c_field_volume_integral(x3d2c_ctx* ctx, int data_loc, const double* f, double* s) {

@@ -76,6 +76,23 @@ __device__ __forceinline__ double sten_exact(const double (&c)[9], const double 
   return t;
 }
 
+// sten_exact for a symmetric stencil (c[8 - k] == c[k], checked by the host): both mirror taps use the SAME coefficient
+// register, so in the fully unrolled sweeps the product c[k] * u_i needed by row i - (k - 4) and again by row
+// i + (k - 4) is one instruction (common sub-expression): 3 multiplications + 4 additions per point for compact6.
+template <unsigned M>
+__device__ __forceinline__ double sten_exact_sym(const double (&c)[9], const double (&w)[9]) {
+  double t = 0.0;
+  bool first = true;
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+    if (M & (1u << k)) {
+      const double pr = __dmul_rn(c[k <= 4 ? k : 8 - k], w[k]);
+      t = first ? pr : __dadd_rn(t, pr);
+      first = false;
+    }
+  return t;
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));

@@ -590,4 +590,63 @@ int x3d2c_transeq(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, c
   return X3D2C_OK;
 }
 
+// transeq_species (src/backend/omp/backend.f90:186-233): convection + diffusion of one scalar `spec` advected by the
+// line-aligned velocity `uvw`: rhs = -1/2 (uvw d(spec) + d(spec uvw)) + nu d2(spec) with (der1st, der1st_sym, der2nd) in
+// the roles (du, dud, d2u) of transeq_dist_component (:299-338). `sync`: exchange the velocity halos too (the first
+// species of a direction); otherwise the halos received by the previous call are reused, as in the reference.
+// Reference-order kernels (one scalar per call has a third of the arithmetic intensity of the fused momentum kernel).
+int x3d2c_transeq_species(x3d2c_ctx* ctx, int dir, double* dspec, const double* uvw, const double* spec, double nu,
+                          const x3d2c_tdsops* der1st, const x3d2c_tdsops* der1st_sym, const x3d2c_tdsops* der2nd,
+                          int sync) {
+  X3D2C_REQUIRE(ctx && dspec && uvw && spec && der1st && der1st_sym && der2nd, "x3d2c_transeq_species: null argument");
+  X3D2C_REQUIRE(dir >= 1 && dir <= 3, "x3d2c_transeq_species: dir must be DIR_X/Y/Z");
+  X3D2C_REQUIRE(der1st->n_rhs == der1st->n_tds && der2nd->n_rhs == der2nd->n_tds && der1st->n_tds == der2nd->n_tds &&
+                    der1st_sym->n_tds == der1st->n_tds, "x3d2c_transeq_species: operators must share n_tds == n_rhs");
+  X3D2C_REQUIRE(dspec != spec && dspec != uvw, "x3d2c_transeq_species: dspec must differ from the inputs");
+  const int P = ctx->cfg.nproc_dir[dir - 1];
+  int rc = ensure_scratch(ctx);
+  if (rc) return rc;
+  const int n_pad = ctx->n_pad(dir), G = ctx->n_groups[dir];
+  const dim3 block(128), grid((G + 3) / 4);
+  HaloBufs h = carve(ctx);
+  if (P > 1) {
+    if (sync) {  // velocity halos into the u buffers
+      halo_pack_kernel<<<G, 128, 0, ctx->stream>>>(h.send_s[0], h.send_e[0], uvw, der1st->n_tds, n_pad, G);
+      X3D2C_CHECK_LAUNCH(ctx);
+      if ((rc = sendrecv_fields(ctx, dir, h.recv_s[0], h.recv_e[0], h.send_s[0], h.send_e[0], (size_t)SZ * 4 * G))) return rc;
+    }
+    halo_pack_kernel<<<G, 128, 0, ctx->stream>>>(h.send_s[1], h.send_e[1], spec, der1st->n_tds, n_pad, G);  // v buffers
+    X3D2C_CHECK_LAUNCH(ctx);
+    if ((rc = sendrecv_fields(ctx, dir, h.recv_s[1], h.recv_e[1], h.send_s[1], h.send_e[1], (size_t)SZ * 4 * G))) return rc;
+  }
+  const double *shs = nullptr, *she = nullptr, *chs = nullptr, *che = nullptr;
+  if (P > 1) { shs = h.recv_s[1]; she = h.recv_e[1]; chs = h.recv_s[0]; che = h.recv_e[0]; }
+  double *send = h.rsend, *recv = h.rrecv;
+  auto launch = [&](int phase) {
+    if (ctx->strict)
+      transeq_m1_kernel<true><<<grid, block, 0, ctx->stream>>>(
+          dspec, ctx->scratch[0], ctx->scratch[1], spec, uvw, shs, she, chs, che, send, recv, h.row, der1st->dev,
+          der1st_sym->dev, der2nd->dev, der1st->tap_mask, der1st_sym->tap_mask, der2nd->tap_mask, nu, n_pad, G, phase);
+    else
+      transeq_m1_kernel<false><<<grid, block, 0, ctx->stream>>>(
+          dspec, ctx->scratch[0], ctx->scratch[1], spec, uvw, shs, she, chs, che, send, recv, h.row, der1st->dev,
+          der1st_sym->dev, der2nd->dev, der1st->tap_mask, der1st_sym->tap_mask, der2nd->tap_mask, nu, n_pad, G, phase);
+  };
+  if (P == 1) {
+    launch(PH_ALL);
+    X3D2C_CHECK_LAUNCH(ctx);
+    return X3D2C_OK;
+  }
+  launch(PH_DIST);
+  X3D2C_CHECK_LAUNCH(ctx);
+  for (int q = 0; q < 3; ++q) {
+    rc = sendrecv_fields(ctx, dir, recv + (2 * q) * h.row, recv + (2 * q + 1) * h.row, send + (2 * q) * h.row,
+                         send + (2 * q + 1) * h.row, (size_t)SZ * G);
+    if (rc) return rc;
+  }
+  launch(PH_SUBS);
+  X3D2C_CHECK_LAUNCH(ctx);
+  return X3D2C_OK;
+}
+
 }  // extern "C"

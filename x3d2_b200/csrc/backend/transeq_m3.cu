@@ -60,7 +60,7 @@ __device__ __forceinline__ void component(const int fF, const int fC, const int 
       wp[8] = wf[8] * (SELF ? wf[8] : smem[fC + o]);
       p1 = fma(p.o_du.a, p1, sten<M1>(p.o_du.cfw, wf));
       p2 = fma(p.o_dud.a, p2, sten<M1>(p.o_dud.cfw, wp));
-      p3 = fma(p.o_d2u.a, p3, sten_exact<M2>(p.o_d2u.cfw, wf));  // unscaled: nu * fw is applied below
+      p3 = fma(p.o_d2u.a, p3, sten_exact_sym<M2>(p.o_d2u.cfw, wf));  // unscaled: nu * fw is applied below
       z1[k] = p1; z2[k] = p2; z3[k] = p3;
 #pragma unroll
       for (int t = 0; t < 8; ++t) { wf[t] = wf[t + 1]; wp[t] = wp[t + 1]; }
@@ -214,6 +214,8 @@ int transeq_m3(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, cons
   if (!make_op(der1st, -0.5, split, &p.o_du, false) || !make_op(der1st, -0.5, split, &p.o_dud, false) ||
       !make_op(der2nd, nu, split, &p.o_d2u, true))
     return X3D2C_EUNSUPPORTED;
+  for (int k = 0; k < 4; ++k)  // sten_exact_sym shares the products of mirror taps
+    if (p.o_d2u.cfw[k] != p.o_d2u.cfw[8 - k]) return X3D2C_EUNSUPPORTED;
   p.d2u_scale = p.o_d2u.fs;
   p.o_d2u.fs = 1.0;
   // Tile width L (lanes), threads = L * nseg per CTA: the choice that keeps most threads resident per SM (shared

@@ -181,6 +181,56 @@ int x3d2h_transeq(x3d2h_sim* sim, const double* u, const double* v, const double
   S.get_field(du, *a, VERT); S.get_field(dv, *b, VERT); S.get_field(dw, *c, VERT);
   H_CATCH
 }
+int x3d2h_transeq_lowmem(x3d2h_sim* sim, const double* u, const double* v, const double* w, double* du, double* dv,
+                         double* dw, double* u_back) {
+  H_TRY
+  Sim& S = *sim->s;
+  Allocator& A = S.allocator;
+  Field *fu = A.get_block(DIR_X), *fv = A.get_block(DIR_X), *fw = A.get_block(DIR_X);
+  Tmp t(A);
+  Field *a = t.get(DIR_X), *b = t.get(DIR_X), *c = t.get(DIR_X);
+  S.set_field(*fu, u, VERT); S.set_field(*fv, v, VERT); S.set_field(*fw, w, VERT);
+  S.transeq_lowmem(*a, *b, *c, fu, fv, fw);  // fu, fv, fw now point at the blocks that came back from the z layout
+  S.get_field(du, *a, VERT); S.get_field(dv, *b, VERT); S.get_field(dw, *c, VERT);
+  if (u_back) S.get_field(u_back, *fu, VERT);
+  A.release_block(fu); A.release_block(fv); A.release_block(fw);
+  H_CATCH
+}
+int x3d2h_transeq_species(x3d2h_sim* sim, const double* u, const double* v, const double* w, const double* spec,
+                          double nu_s, double* dspec) {
+  H_TRY
+  Sim& S = *sim->s;
+  Tmp t(S.allocator);
+  Field *fu = t.get(DIR_X), *fv = t.get(DIR_X), *fw = t.get(DIR_X), *fs = t.get(DIR_X), *a = t.get(DIR_X);
+  S.set_field(*fu, u, VERT); S.set_field(*fv, v, VERT); S.set_field(*fw, w, VERT); S.set_field(*fs, spec, VERT);
+  Field* rhs[1] = {a};
+  Field* sp[1] = {fs};
+  S.transeq_species(rhs, 1, *fu, *fv, *fw, sp, &nu_s);
+  S.get_field(dspec, *a, VERT);
+  H_CATCH
+}
+int x3d2h_derived(x3d2h_sim* sim, const char* what, const double* const* grads, double* out) {
+  H_TRY
+  Sim& S = *sim->s;
+  Tmp t(S.allocator);
+  Field* g[9];
+  for (int k = 0; k < 9; ++k) { g[k] = t.get(DIR_X); S.set_field(*g[k], grads[k], VERT); }
+  Field* o = t.get(DIR_X, VERT);
+  if (std::string(what) == "vorticity") S.backend.compute_vorticity(*o, g);
+  else if (std::string(what) == "qcriterion") S.backend.compute_qcriterion(*o, g);
+  else fail("x3d2h_derived: unknown quantity");
+  S.get_field(out, *o, VERT);
+  H_CATCH
+}
+int x3d2h_slice_max_sum(x3d2h_sim* sim, int dir, int data_loc, const double* x, int i_slice, double* mx, double* sum) {
+  H_TRY
+  Sim& S = *sim->s;
+  Tmp t(S.allocator);
+  Field* f = t.get(dir, data_loc);
+  S.set_field(*f, x, data_loc);
+  S.backend.slice_max_sum(*mx, *sum, *f, i_slice);
+  H_CATCH
+}
 int x3d2h_transeq_dir(x3d2h_sim* sim, int dir, const double* u, const double* v, const double* w, double* du,
                       double* dv, double* dw) {
   H_TRY

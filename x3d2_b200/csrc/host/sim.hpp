@@ -267,6 +267,28 @@ class Backend {  // cuda_c_backend_t: every method is one deferred procedure of 
   void transeq_x(Field& du, Field& dv, Field& dw, const Field& u, const Field& v, const Field& w, double nu, const DevDirps& dp) { transeq(DIR_X, du, dv, dw, u, v, w, nu, dp); }
   void transeq_y(Field& du, Field& dv, Field& dw, const Field& u, const Field& v, const Field& w, double nu, const DevDirps& dp) { transeq(DIR_Y, du, dv, dw, u, v, w, nu, dp); }
   void transeq_z(Field& du, Field& dv, Field& dw, const Field& u, const Field& v, const Field& w, double nu, const DevDirps& dp) { transeq(DIR_Z, du, dv, dw, u, v, w, nu, dp); }
+  // omp/backend.f90:186-233
+  void transeq_species(Field& dspec, const Field& uvw, const Field& spec, double nu_s, const DevDirps& dp, bool sync) {
+    if (dspec.dir != dp.dir || uvw.dir != dp.dir || spec.dir != dp.dir) fail("DIR mismatch between fields in transeq_species.");
+    X3D2H_CALL(x3d2c_transeq_species(ctx, dp.dir, dspec.dev, uvw.dev, spec.dev, nu_s, dp.der1st.h, dp.der1st_sym.h,
+                                     dp.der2nd.h, sync ? 1 : 0));
+    dspec.data_loc = spec.data_loc;
+  }
+  // omp/backend.f90:816-881: rank-local signed max and sum of one plane
+  void slice_max_sum(double& mx, double& sum, const Field& f, int i_slice, int enforced_data_loc = -999) {
+    if (f.data_loc == NULL_LOC && enforced_data_loc == -999) fail("slice_max_sum: the field has no valid data_loc");
+    if (f.dir == DIR_C) fail("slice_max_sum does not support DIR_C fields!");
+    X3D2H_CALL(x3d2c_slice_max_sum(ctx, f.dir, enforced_data_loc != -999 ? enforced_data_loc : f.data_loc, f.dev, i_slice, &mx, &sum));
+  }
+  // omp/backend.f90:616-649
+  void compute_vorticity(Field& out, const Field* const g[9]) {
+    X3D2H_CALL(x3d2c_compute_vorticity(ctx, out.dev, g[0]->dev, g[1]->dev, g[2]->dev, g[3]->dev, g[4]->dev, g[5]->dev,
+                                       g[6]->dev, g[7]->dev, g[8]->dev));
+  }
+  void compute_qcriterion(Field& out, const Field* const g[9]) {
+    X3D2H_CALL(x3d2c_compute_qcriterion(ctx, out.dev, g[0]->dev, g[1]->dev, g[2]->dev, g[3]->dev, g[4]->dev, g[5]->dev,
+                                        g[6]->dev, g[7]->dev, g[8]->dev));
+  }
   void tds_solve(Field& du, const Field& u, const DevTdsops& ops) {  // cuda/backend.f90:449-470
     if (u.dir != du.dir) fail("DIR mismatch between fields in tds_solve.");
     if (u.data_loc != NULL_LOC) du.data_loc = move_data_loc(u.data_loc, u.dir, ops.t.move);
@@ -680,6 +702,63 @@ class Sim {
       if (ti_nstep > 1) backend.veccopy(*olds[i][1], *deriv[i]);
     }
     ti_istep = ti_istep + 1;
+  }
+
+  // solver.f90:391-505: the low-memory variant. The velocity blocks are given back to the pool once they exist in the
+  // y layout and return from the z layout (reorder Z2X) in fresh blocks: uu, vv, ww are re-pointed.
+  void transeq_lowmem(Field& du, Field& dv, Field& dw, Field*& uu, Field*& vv, Field*& ww) {
+    Allocator& A = allocator;
+    backend.transeq_x(du, dv, dw, *uu, *vv, *ww, nu, xdirps);
+    Field* vel[3] = {uu, vv, ww};
+    Field* rhs[3] = {&du, &dv, &dw};
+    Field* y[3];
+    for (int i = 0; i < 3; ++i) y[i] = A.get_block(DIR_Y);
+    for (int i = 0; i < 3; ++i) backend.reorder(*y[i], *vel[i], RDR_X2Y);
+    for (int i = 0; i < 3; ++i) A.release_block(vel[i]);
+    Field* d[3];
+    for (int i = 0; i < 3; ++i) d[i] = A.get_block(DIR_Y);
+    backend.transeq_y(*d[0], *d[1], *d[2], *y[0], *y[1], *y[2], nu, ydirps);
+    for (int i = 0; i < 3; ++i) backend.sum_yintox(*rhs[i], *d[i]);
+    for (int i = 0; i < 3; ++i) A.release_block(d[i]);
+    Field* z[3];
+    for (int i = 0; i < 3; ++i) z[i] = A.get_block(DIR_Z);
+    for (int i = 0; i < 3; ++i) backend.reorder(*z[i], *y[i], RDR_Y2Z);
+    for (int i = 0; i < 3; ++i) A.release_block(y[i]);
+    for (int i = 0; i < 3; ++i) d[i] = A.get_block(DIR_Z);
+    backend.transeq_z(*d[0], *d[1], *d[2], *z[0], *z[1], *z[2], nu, zdirps);
+    for (int i = 0; i < 3; ++i) backend.sum_zintox(*rhs[i], *d[i]);
+    for (int i = 0; i < 3; ++i) A.release_block(d[i]);
+    for (int i = 0; i < 3; ++i) vel[i] = A.get_block(DIR_X);
+    for (int i = 0; i < 3; ++i) backend.reorder(*vel[i], *z[i], RDR_Z2X);
+    for (int i = 0; i < 3; ++i) A.release_block(z[i]);
+    uu = vel[0]; vv = vel[1]; ww = vel[2];
+  }
+
+  // solver.f90:507-600: convection-diffusion of the species fields spec[0..n) with diffusivities nu_s[i]
+  void transeq_species(Field* const* rhs, int n, const Field& uu, const Field& vv, const Field& ww, Field* const* spec,
+                       const double* nu_s) {
+    Allocator& A = allocator;
+    for (int i = 0; i < n; ++i) backend.transeq_species(*rhs[i], uu, *spec[i], nu_s[i], xdirps, i <= 0);
+    {
+      Field *v_y = A.get_block(DIR_Y), *spec_y = A.get_block(DIR_Y), *dspec_y = A.get_block(DIR_Y);
+      backend.reorder(*v_y, vv, RDR_X2Y);
+      for (int i = 0; i < n; ++i) {
+        backend.reorder(*spec_y, *spec[i], RDR_X2Y);
+        backend.transeq_species(*dspec_y, *v_y, *spec_y, nu_s[i], ydirps, i <= 0);
+        backend.sum_yintox(*rhs[i], *dspec_y);
+      }
+      A.release_block(v_y); A.release_block(spec_y); A.release_block(dspec_y);
+    }
+    {
+      Field *w_z = A.get_block(DIR_Z), *spec_z = A.get_block(DIR_Z), *dspec_z = A.get_block(DIR_Z);
+      backend.reorder(*w_z, ww, RDR_X2Z);
+      for (int i = 0; i < n; ++i) {
+        backend.reorder(*spec_z, *spec[i], RDR_X2Z);
+        backend.transeq_species(*dspec_z, *w_z, *spec_z, nu_s[i], zdirps, i <= 0);
+        backend.sum_zintox(*rhs[i], *dspec_z);
+      }
+      A.release_block(w_z); A.release_block(spec_z); A.release_block(dspec_z);
+    }
   }
 
   // solver.f90:291-389

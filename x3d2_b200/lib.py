@@ -76,6 +76,10 @@ def load():
         x3d2h_monitor=[C.c_void_p, _dp],
         x3d2h_transeq=[C.c_void_p] + [_dp] * 6,
         x3d2h_transeq_dir=[C.c_void_p, C.c_int] + [_dp] * 6,
+        x3d2h_transeq_lowmem=[C.c_void_p] + [_dp] * 7,
+        x3d2h_transeq_species=[C.c_void_p] + [_dp] * 4 + [C.c_double, _dp],
+        x3d2h_derived=[C.c_void_p, C.c_char_p, C.POINTER(_dp), _dp],
+        x3d2h_slice_max_sum=[C.c_void_p, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp],
         x3d2h_tds_solve=[C.c_void_p, C.c_int, C.c_char_p, C.c_int, _dp, _dp, _ip],
         x3d2h_tds_fused=[C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int, _dp, _dp, C.c_double,
                          _dp, _dp],
