@@ -225,6 +225,10 @@ class World {
   std::vector<cplx> waves, c_x;
   std::vector<double> ax, bx, ay, by, az, bz;
   std::vector<cplx> kx, ky, kz, exs, eys, ezs, k2x, k2y, k2z;
+  // 010 (non-periodic y): poisson_fft.f90:29-37
+  bool is_010 = false, stretched_y = false, stretched_y_sym = false;
+  std::vector<double> trans_x, trans_y, trans_z;        // trans_?_re (== trans_?_im), 1-based
+  std::vector<double> a_odd, a_even, a_full;            // (nx_spec, ny_spec/2 | ny_spec, nz_spec, 5); re == im
 
   // ---------------------------------------------------------------- construction (mesh.f90:37-194)
   World(const int dims_global[3], const int nproc_dir[3], const double L[3], const int bcs[3][2],
@@ -875,7 +879,12 @@ class World {
   // The emulation keeps the whole spectral pencil (nx/2+1, ny, nz) in one array (sp_st = 0): 2DECOMP's
   // distributed transform of the gathered field equals the global transform.
   void init_poisson() {
-    if (!(gm.periodic_BC[0] && gm.periodic_BC[1] && gm.periodic_BC[2])) return;  // 010 etc: not in the OMP oracle
+    const bool p000 = gm.periodic_BC[0] && gm.periodic_BC[1] && gm.periodic_BC[2];
+    is_010 = gm.periodic_BC[0] && !gm.periodic_BC[1] && gm.periodic_BC[2];
+    if (!p000 && !is_010) return;  // 100 / 110: no config uses non-periodic x
+    if (is_010 && P > 1) fail("Multiple ranks are not yet supported for non-periodic BCs!");  // poisson_fft.f90:178-180
+    if (rm[0].geo.stretched[0] || rm[0].geo.stretched[2])
+      fail("FFT based Poisson solver does not support stretching in x- or z-directions!");
     int nx = gm.global_cell_dims[0], ny = gm.global_cell_dims[1], nz = gm.global_cell_dims[2];
     nx_spec = nx / 2 + 1; ny_spec = ny; nz_spec = nz;
     const Tdsops &sx = xdirps[0].stagder_v2p, &sy = ydirps[0].stagder_v2p, &sz_ = zdirps[0].stagder_v2p;
@@ -899,6 +908,285 @@ class World {
           cplx xt2 = k2x[i] * (fx * fx), yt2 = k2y[j] * (fy * fy), zt2 = k2z[k] * (fz * fz);
           waves[(i - 1) + (size_t)nx_spec * ((j - 1) + (size_t)ny_spec * (k - 1))] = xt2 + yt2 + zt2;
         }
+    if (is_010 && rm[0].geo.stretched[1]) {
+      stretched_y = true;
+      stretching_matrix();
+    }
+  }
+
+  // ---------------------------------------------------------------- poisson_fft.f90:275-652 (stretching_matrix)
+  // Every complex quantity of the reference is cmplx(1, 1) * x, so its real and imaginary parts are the same number;
+  // one real array stands for a_*_re and a_*_im (the expressions for _im are the _re ones with get_imag for get_real).
+  double km(int i, int j, int k) const { return trans_x[i] * ky[j].real() * trans_z[k]; }  // get_km(_re), :893-903
+  double& A5(std::vector<double>& a, int nrow, int i, int j, int k, int d) {
+    return a[(size_t)(i - 1) + (size_t)nx_spec * ((j - 1) + (size_t)nrow * ((k - 1) + (size_t)nz_spec * (d - 1)))];
+  }
+  void stretching_matrix() {
+    const Geo& geo = rm[0].geo;
+    const Tdsops &ix = xdirps[0].interpl_v2p, &iy = ydirps[0].interpl_v2p, &iz = zdirps[0].interpl_v2p;
+    auto trans = [](const Tdsops& t, double temp) {
+      return 2 * (t.a * std::cos(temp * 0.5) + t.b * std::cos(temp * 1.5) + t.c * std::cos(temp * 2.5) +
+                  t.d * std::cos(temp * 3.5)) / (1.0 + 2 * t.alpha * std::cos(temp));
+    };
+    trans_x.assign(nx_spec + 1, 0); trans_y.assign(ny_spec + 1, 0); trans_z.assign(nz_spec + 1, 0);
+    for (int i = 1; i <= nx_spec; ++i) trans_x[i] = trans(ix, exs[i].real() * geo.d[0]);
+    for (int j = 1; j <= ny_spec; ++j) trans_y[j] = trans(iy, eys[j].real() * geo.d[1]);
+    for (int k = 1; k <= nz_spec; ++k) trans_z[k] = trans(iz, ezs[k].real() * geo.d[2]);
+    const double a0 = (geo.alpha[1] / pi + 1.0 / (2 * pi * geo.beta[1])) * geo.L[1];
+    auto sq = [](double x) { return x * x; };
+    if (geo.stretching[1] == "bottom") {  // :320-422
+      stretched_y_sym = false;
+      const int n = ny_spec;
+      a_full.assign((size_t)nx_spec * n * nz_spec * 5, 0.0);
+      const double a1 = -1.0 / (4 * pi * geo.beta[1]) * geo.L[1];
+      for (int k = 1; k <= nz_spec; ++k)
+        for (int j = 1; j <= n; ++j)
+          for (int i = 1; i <= nx_spec; ++i) {
+            double km_a1;
+            if (j == 1) km_a1 = km(i, 2, k);
+            else if (j == n) km_a1 = km(i, n - 1, k);
+            else km_a1 = km(i, j - 1, k) + km(i, j + 1, k);
+            A5(a_full, n, i, j, k, 3) = -sq(kx[i].real() * trans_y[j] * trans_z[k]) - sq(kz[k].real() * trans_y[j] * trans_x[i]) -
+                                        a0 * a0 * sq(km(i, j, k)) - a1 * a1 * km(i, j, k) * km_a1;
+            // the reference evaluates get_km at iy + 1 = ny_spec + 1 for the last row (out of bounds in ky); that
+            // entry is never used by the solve. Guarded here.
+            if (j + 1 <= n) A5(a_full, n, i, j, k, 4) = a0 * a1 * km(i, j + 1, k) * (km(i, j, k) + km(i, j + 1, k));
+            if (j <= n - 2) A5(a_full, n, i, j, k, 5) = -a1 * a1 * km(i, j + 1, k) * km(i, j + 2, k);
+            if (j >= 2) A5(a_full, n, i, j, k, 2) = a0 * a1 * km(i, j - 1, k) * (km(i, j, k) + km(i, j - 1, k));
+            if (j >= 3) A5(a_full, n, i, j, k, 1) = -a1 * a1 * km(i, j - 1, k) * km(i, j - 2, k);
+          }
+      A5(a_full, n, 1, 1, 1, 3) = 1.0; A5(a_full, n, 1, 1, 1, 4) = 0; A5(a_full, n, 1, 1, 1, 5) = 0;
+      return;
+    }
+    // 'centred' / 'top-bottom': odd and even modes decouple (:423-650)
+    stretched_y_sym = true;
+    const int n = ny_spec / 2;
+    a_odd.assign((size_t)nx_spec * n * nz_spec * 5, 0.0);
+    a_even.assign((size_t)nx_spec * n * nz_spec * 5, 0.0);
+    double a1 = 0.0;
+    if (geo.stretching[1] == "centred") a1 = 1.0 / (4 * pi * geo.beta[1]) * geo.L[1];
+    else if (geo.stretching[1] == "top-bottom") a1 = -1.0 / (4 * pi * geo.beta[1]) * geo.L[1];
+    for (int k = 1; k <= nz_spec; ++k)
+      for (int j = 1; j <= n; ++j)
+        for (int i = 1; i <= nx_spec; ++i) {
+          const int od = 2 * j - 1, ev = 2 * j;
+          {  // diagonal (:444-497)
+            double c1_od = a0 * a0, c2_od = a1 * a1, c1_ev = a0 * a0, c2_ev = a1 * a1, km_od, km_ev;
+            if (j == 1) { c1_ev = a0 * a0 - a1 * a1; km_od = km(i, 3, k); km_ev = km(i, 4, k); }
+            else if (j == n) { c1_ev = (a0 + a1) * (a0 + a1); km_od = km(i, od - 2, k); km_ev = km(i, ev - 2, k); }
+            else { km_od = km(i, od - 2, k) + km(i, od + 2, k); km_ev = km(i, ev - 2, k) + km(i, ev + 2, k); }
+            A5(a_odd, n, i, j, k, 3) = -sq(kx[i].real() * trans_y[od] * trans_z[k]) - sq(kz[k].real() * trans_y[od] * trans_x[i]) -
+                                       c1_od * sq(km(i, od, k)) - c2_od * km(i, od, k) * km_od;
+            A5(a_even, n, i, j, k, 3) = -sq(kx[i].real() * trans_y[ev] * trans_z[k]) - sq(kz[k].real() * trans_y[ev] * trans_x[i]) -
+                                        c1_ev * sq(km(i, ev, k)) - c2_ev * km(i, ev, k) * km_ev;
+          }
+          if (j <= n - 1) {  // diagonal + 1 (:500-538); for j == n the reference reads ky beyond its end with
+                             // c1_ev = c2_ev = 0 (even) and a non-zero factor (odd): neither entry is used by the solve
+            double c1_od = a0 * a1, c2_od = a0 * a1, c1_ev = a0 * a1, c2_ev = a0 * a1;
+            if (j == 1) { c1_od = 2 * a0 * a1; c2_od = 2 * a0 * a1; c1_ev = a0 * a1 - a1 * a1; c2_ev = a0 * a1; }
+            else if (j == n - 1) { c1_ev = a0 * a1; c2_ev = (a0 + a1) * a1; }
+            A5(a_odd, n, i, j, k, 4) = c1_od * (km(i, od, k) * km(i, od + 2, k)) + c2_od * sq(km(i, od + 2, k));
+            A5(a_even, n, i, j, k, 4) = c1_ev * (km(i, ev, k) * km(i, ev + 2, k)) + c2_ev * sq(km(i, ev + 2, k));
+          }
+          if (j <= n - 2) {  // diagonal + 2 (:541-567)
+            double c1_od = a1 * a1, c1_ev = a1 * a1;
+            if (j == 1) c1_od = 2 * a1 * a1;
+            A5(a_odd, n, i, j, k, 5) = -(c1_od * km(i, od + 2, k) * km(i, od + 4, k));
+            A5(a_even, n, i, j, k, 5) = -(c1_ev * km(i, ev + 2, k) * km(i, ev + 4, k));
+          }
+          if (j >= 2) {  // diagonal - 1 (:570-608)
+            double c1_od = a0 * a1, c2_od = a0 * a1, c1_ev = a0 * a1, c2_ev = a0 * a1;
+            if (j == 2) { c1_ev = a0 * a1; c2_ev = (a0 + a1) * a1; }
+            else if (j == n) { c1_ev = (a0 + a1) * a1; c2_ev = a0 * a1; }
+            A5(a_odd, n, i, j, k, 2) = c1_od * (km(i, od, k) * km(i, od - 2, k)) + c2_od * sq(km(i, od - 2, k));
+            A5(a_even, n, i, j, k, 2) = c1_ev * (km(i, ev, k) * km(i, ev - 2, k)) + c2_ev * sq(km(i, ev - 2, k));
+          }
+          if (j >= 3) {  // diagonal - 2 (:611-631)
+            A5(a_odd, n, i, j, k, 1) = -(a1 * a1 * km(i, od - 2, k) * km(i, od - 4, k));
+            A5(a_even, n, i, j, k, 1) = -(a1 * a1 * km(i, ev - 2, k) * km(i, ev - 4, k));
+          }
+        }
+    for (int k = 1; k <= nz_spec; ++k)  // :633-648: make the mean mode regular
+      for (int i = 1; i <= nx_spec; ++i)
+        if (k2x[i].real() < 1e-15 && k2z[k].real() < 1e-15) {
+          A5(a_odd, n, i, 1, k, 3) = 1.0; A5(a_odd, n, i, 1, k, 4) = 0; A5(a_odd, n, i, 1, k, 5) = 0;
+        }
+  }
+
+  // ---------------------------------------------------------------- omp/poisson_fft.f90:237-285 (single rank)
+  void enforce_periodicity_y(WField& f_out, const WField& f_in) {
+    const int nx = gm.global_cell_dims[0], ny = gm.global_cell_dims[1], nz = gm.global_cell_dims[2];
+    const int* cp = alloc.padded(DIR_C);
+    auto at = [&](std::vector<double>& v, int i, int j, int k) -> double& { return v[(i - 1) + (size_t)cp[0] * ((j - 1) + (size_t)cp[1] * (k - 1))]; };
+    std::vector<double>& o = f_out.r[0];
+    std::vector<double>& in = const_cast<std::vector<double>&>(f_in.r[0]);
+    for (int k = 1; k <= nz; ++k) {
+      for (int j = 1; j <= ny / 2; ++j)
+        for (int i = 1; i <= nx; ++i) at(o, i, j, k) = at(in, i, 2 * (j - 1) + 1, k);
+      for (int j = ny / 2 + 1; j <= ny; ++j)
+        for (int i = 1; i <= nx; ++i) at(o, i, j, k) = at(in, i, 2 * ny - 2 * j + 2, k);
+    }
+  }
+  void undo_periodicity_y(WField& f_out, const WField& f_in) {
+    const int nx = gm.global_cell_dims[0], ny = gm.global_cell_dims[1], nz = gm.global_cell_dims[2];
+    const int* cp = alloc.padded(DIR_C);
+    auto at = [&](std::vector<double>& v, int i, int j, int k) -> double& { return v[(i - 1) + (size_t)cp[0] * ((j - 1) + (size_t)cp[1] * (k - 1))]; };
+    std::vector<double>& o = f_out.r[0];
+    std::vector<double>& in = const_cast<std::vector<double>&>(f_in.r[0]);
+    for (int k = 1; k <= nz; ++k)
+      for (int i = 1; i <= nx; ++i) {
+        for (int j = 1; j <= ny / 2; ++j) at(o, i, 2 * j - 1, k) = at(in, i, j, k);
+        for (int j = 1; j <= ny / 2; ++j) at(o, i, 2 * j, k) = at(in, i, ny - j + 1, k);
+      }
+  }
+
+  // ---------------------------------------------------------------- omp/kernels/spectral_processing.f90:108-283 and,
+  // for the stretched mesh (which only the CUDA-Fortran backend implements),
+  // cuda/kernels/spectral_processing.f90:385-702: _fw = first two blocks, _bw = last two blocks of process_spectral_010
+  cplx& CX(int i, int j, int k) { return c_x[(size_t)(i - 1) + (size_t)nx_spec * ((j - 1) + (size_t)ny_spec * (k - 1))]; }
+  void spectral_010_fw() {
+    const int nx = gm.global_cell_dims[0], ny = gm.global_cell_dims[1], nz = gm.global_cell_dims[2];
+#pragma omp parallel for collapse(2)
+    for (int k = 1; k <= nz_spec; ++k)
+      for (int j = 1; j <= ny_spec; ++j)
+        for (int i = 1; i <= nx_spec; ++i) {
+          const int ix = i, iz = k;
+          double div_r = CX(i, j, k).real() / nx / ny / nz, div_c = CX(i, j, k).imag() / nx / ny / nz;
+          double tmp_r = div_r, tmp_c = div_c;
+          div_r = tmp_r * bz[iz] + tmp_c * az[iz];
+          div_c = tmp_c * bz[iz] - tmp_r * az[iz];
+          if (iz > nz / 2 + 1) div_r = -div_r;
+          if (iz > nz / 2 + 1) div_c = -div_c;
+          tmp_r = div_r; tmp_c = div_c;
+          div_r = tmp_r * bx[ix] + tmp_c * ax[ix];
+          div_c = tmp_c * bx[ix] - tmp_r * ax[ix];
+          if (ix > nx / 2 + 1) div_r = -div_r;
+          if (ix > nx / 2 + 1) div_c = -div_c;
+          CX(i, j, k) = cplx(div_r, div_c);
+        }
+#pragma omp parallel for collapse(2)
+    for (int k = 1; k <= nz_spec; ++k)
+      for (int j = 2; j <= ny_spec / 2 + 1; ++j)
+        for (int i = 1; i <= nx_spec; ++i) {
+          const int iy = j, iy_r = ny_spec - j + 2;
+          const double l_r = CX(i, j, k).real(), l_c = CX(i, j, k).imag();
+          const double r_r = CX(i, iy_r, k).real(), r_c = CX(i, iy_r, k).imag();
+          CX(i, j, k) = 0.5 * cplx(l_r * by[iy] + l_c * ay[iy] + r_r * by[iy] - r_c * ay[iy],
+                                   -l_r * ay[iy] + l_c * by[iy] + r_r * ay[iy] + r_c * by[iy]);
+          CX(i, iy_r, k) = 0.5 * cplx(r_r * by[iy_r] + r_c * ay[iy_r] + l_r * by[iy_r] - l_c * ay[iy_r],
+                                      -r_r * ay[iy_r] + r_c * by[iy_r] + l_r * ay[iy_r] + l_c * by[iy_r]);
+        }
+  }
+  void spectral_010_solve_uniform() {
+    const int nx = gm.global_cell_dims[0], nz = gm.global_cell_dims[2];
+#pragma omp parallel for collapse(2)
+    for (int k = 1; k <= nz_spec; ++k)
+      for (int j = 1; j <= ny_spec; ++j)
+        for (int i = 1; i <= nx_spec; ++i) {
+          double div_r = CX(i, j, k).real(), div_c = CX(i, j, k).imag();
+          const cplx wv = waves[(size_t)(i - 1) + (size_t)nx_spec * ((j - 1) + (size_t)ny_spec * (k - 1))];
+          const double tmp_r = wv.real(), tmp_c = wv.imag();
+          if (std::fabs(tmp_r) < 1.e-16) div_r = 0.0; else div_r = -div_r / tmp_r;
+          if (std::fabs(tmp_c) < 1.e-16) div_c = 0.0; else div_c = -div_c / tmp_c;
+          CX(i, j, k) = cplx(div_r, div_c);
+          if (i == nx / 2 + 1 && k == nz / 2 + 1) CX(i, j, k) = 0.0;
+        }
+  }
+  void spectral_010_bw() {
+    const int nx = gm.global_cell_dims[0], nz = gm.global_cell_dims[2];
+#pragma omp parallel for collapse(2)
+    for (int k = 1; k <= nz_spec; ++k)
+      for (int j = 2; j <= ny_spec / 2 + 1; ++j)
+        for (int i = 1; i <= nx_spec; ++i) {
+          const int iy = j, iy_r = ny_spec - j + 2;
+          const double l_r = CX(i, j, k).real(), l_c = CX(i, j, k).imag();
+          const double r_r = CX(i, iy_r, k).real(), r_c = CX(i, iy_r, k).imag();
+          CX(i, j, k) = cplx(l_r * by[iy] - l_c * ay[iy] + r_r * ay[iy] + r_c * by[iy],
+                             l_r * ay[iy] + l_c * by[iy] - r_r * by[iy] + r_c * ay[iy]);
+          CX(i, iy_r, k) = cplx(r_r * by[iy_r] - r_c * ay[iy_r] + l_r * ay[iy_r] + l_c * by[iy_r],
+                                r_r * ay[iy_r] + r_c * by[iy_r] - l_r * by[iy_r] + l_c * ay[iy_r]);
+        }
+#pragma omp parallel for collapse(2)
+    for (int k = 1; k <= nz_spec; ++k)
+      for (int j = 1; j <= ny_spec; ++j)
+        for (int i = 1; i <= nx_spec; ++i) {
+          const int ix = i, iz = k;
+          double div_r = CX(i, j, k).real(), div_c = CX(i, j, k).imag();
+          double tmp_r = div_r, tmp_c = div_c;
+          div_r = tmp_r * bz[iz] - tmp_c * az[iz];
+          div_c = tmp_c * bz[iz] + tmp_r * az[iz];
+          if (iz > nz / 2 + 1) div_r = -div_r;
+          if (iz > nz / 2 + 1) div_c = -div_c;
+          tmp_r = div_r; tmp_c = div_c;
+          div_r = tmp_r * bx[ix] - tmp_c * ax[ix];
+          div_c = tmp_c * bx[ix] + tmp_r * ax[ix];
+          if (ix > nx / 2 + 1) div_r = -div_r;
+          if (ix > nx / 2 + 1) div_c = -div_c;
+          CX(i, j, k) = cplx(div_r, div_c);
+        }
+  }
+  // cuda/kernels/spectral_processing.f90:465-622 (process_spectral_010_poisson): in-place pentadiagonal elimination
+  // along y for one mode family (off, inc); `a` is a working copy of the coefficient tensor (the kernel mutates it;
+  // cuda/poisson_fft.f90:870-895 re-copies it before every call). Real and imaginary parts use the same coefficients.
+  void spectral_010_penta(std::vector<double> a, int off, int inc, int n) {
+    const int nx = gm.global_cell_dims[0], nz = gm.global_cell_dims[2];
+    const double epsilon = 1.e-16;
+#pragma omp parallel for collapse(2)
+    for (int k = 1; k <= nz_spec; ++k)
+      for (int i = 1; i <= nx_spec; ++i) {
+        auto A = [&](int j, int d) -> double& { return A5(a, n, i, j, k, d); };
+        for (int j = 1; j <= n - 2; ++j) {
+          const int jm = inc * j + off - inc / 2;
+          double t = 0.0;
+          if (std::fabs(A(j, 3)) > epsilon) t = A(j + 1, 2) / A(j, 3);
+          CX(i, jm + inc, k) = cplx(CX(i, jm + inc, k).real() - t * CX(i, jm, k).real(),
+                                    CX(i, jm + inc, k).imag() - t * CX(i, jm, k).imag());
+          A(j + 1, 3) = A(j + 1, 3) - t * A(j, 4);
+          A(j + 1, 4) = A(j + 1, 4) - t * A(j, 5);
+          t = 0.0;
+          if (std::fabs(A(j, 3)) > epsilon) t = A(j + 2, 1) / A(j, 3);
+          CX(i, jm + 2 * inc, k) = cplx(CX(i, jm + 2 * inc, k).real() - t * CX(i, jm, k).real(),
+                                        CX(i, jm + 2 * inc, k).imag() - t * CX(i, jm, k).imag());
+          A(j + 2, 2) = A(j + 2, 2) - t * A(j, 4);
+          A(j + 2, 3) = A(j + 2, 3) - t * A(j, 5);
+        }
+        double t = std::fabs(A(n - 1, 3)) > epsilon ? A(n, 2) / A(n - 1, 3) : 0.0;
+        const double d = A(n, 3) - t * A(n - 1, 4);
+        const int nm = inc * n + off - inc / 2;
+        double div_r, div_c;
+        if (std::fabs(d) > epsilon) {
+          t = t / d;
+          div_r = CX(i, nm, k).real() / d - t * CX(i, nm - inc, k).real();
+          div_c = CX(i, nm, k).imag() / d - t * CX(i, nm - inc, k).imag();
+        } else {
+          div_r = 0.0; div_c = 0.0;
+        }
+        CX(i, nm, k) = cplx(div_r, div_c);
+        const double ti = std::fabs(A(n - 1, 3)) > epsilon ? 1.0 / A(n - 1, 3) : 0.0;
+        const double dd = A(n - 1, 4) * ti;
+        CX(i, nm - inc, k) = cplx(CX(i, nm - inc, k).real() * ti - CX(i, nm, k).real() * dd,
+                                  CX(i, nm - inc, k).imag() * ti - CX(i, nm, k).imag() * dd);
+        if (i == nx / 2 + 1 && k == nz / 2 + 1) { CX(i, nm, k) = 0.0; CX(i, nm - inc, k) = 0.0; }
+        for (int j = n - 2; j >= 1; --j) {
+          const int jm = inc * j + off - inc / 2;
+          const double tj = std::fabs(A(j, 3)) > epsilon ? 1.0 / A(j, 3) : 0.0;
+          CX(i, jm, k) = cplx(tj * (CX(i, jm, k).real() - A(j, 4) * CX(i, jm + inc, k).real() - A(j, 5) * CX(i, jm + 2 * inc, k).real()),
+                              tj * (CX(i, jm, k).imag() - A(j, 4) * CX(i, jm + inc, k).imag() - A(j, 5) * CX(i, jm + 2 * inc, k).imag()));
+          if (i == nx / 2 + 1 && k == nz / 2 + 1) CX(i, jm, k) = 0.0;
+        }
+      }
+  }
+  // cuda/poisson_fft.f90:822-924 (fft_postprocess_010)
+  void fft_postprocess_010() {
+    spectral_010_fw();
+    if (!stretched_y) spectral_010_solve_uniform();
+    else if (stretched_y_sym) {
+      spectral_010_penta(a_odd, 0, 2, ny_spec / 2);
+      spectral_010_penta(a_even, 1, 2, ny_spec / 2);
+    } else {
+      spectral_010_penta(a_full, 0, 1, ny_spec);
+    }
+    spectral_010_bw();
   }
 
   // omp/kernels/spectral_processing.f90:7-106
@@ -987,9 +1275,17 @@ class World {
     WField* p_temp = get_block(DIR_C);
     reorder(*p_temp, div_u, RDR_Z2C);
     WField* temp = get_block(DIR_C);
-    fft_forward(*p_temp);
-    process_spectral_000();
-    fft_backward(*p_temp);
+    if (is_010) {  // poisson_fft.f90:228-242 (poisson_010)
+      enforce_periodicity_y(*temp, *p_temp);
+      fft_forward(*temp);
+      fft_postprocess_010();
+      fft_backward(*temp);
+      undo_periodicity_y(*p_temp, *temp);
+    } else {
+      fft_forward(*p_temp);
+      process_spectral_000();
+      fft_backward(*p_temp);
+    }
     release_block(temp);
     reorder(pressure, *p_temp, RDR_C2Z);
     release_block(p_temp);

@@ -196,3 +196,68 @@ def test_tgv_invariants(oracle):
     W1.step(1)
     a, b = W.get_uvw(), W1.get_uvw()
     assert max(np.abs(x - y).max() for x, y in zip(a, b)) < 1e-12  # DistD2 truncation alpha^32
+
+
+TEST_COS = {"COS_X": (1, 0, 0), "COS_Y": (0, 1, 0), "COS_XY": (1, 1, 0), "COS_XYZ": (1, 1, 1)}
+
+
+def _cos_family(W, n_wave, mask, L=(1.0, 1.0, 1.0)):
+    """create_cosine_field / create_analytical_solution of tests/verification/test_poisson_bc.f90:383-463 at the cell
+    centres of W (uniform mesh)."""
+    nz, ny, nx = W.shape(1110)
+    c = [(np.arange(n) + 0.5) * (Lq / n) for n, Lq in zip((nx, ny, nz), L)]
+    f = np.ones((nz, ny, nx))
+    if mask[0]:
+        f = f * np.cos(n_wave * np.pi * c[0])[None, None, :]
+    if mask[1]:
+        f = f * np.cos(n_wave * np.pi * c[1])[None, :, None]
+    if mask[2]:
+        f = f * np.cos(n_wave * np.pi * c[2])[:, None, None]
+    return f, -f / (sum(mask) * (n_wave * np.pi) ** 2)
+
+
+@pytest.mark.parametrize("dims", [(128, 65, 32), (64, 129, 32)])
+@pytest.mark.parametrize("name", ["COS_X", "COS_Y", "COS_XY", "COS_XYZ"])
+@pytest.mark.parametrize("n_wave", [2, 3])
+def test_poisson_010_known_answers(oracle, dims, name, n_wave):
+    """The 010 row of tests/verification/test_poisson_bc.f90:478-618 (grid 128 x 65 x 32, L = 1, walls in y): check 1
+    solution vs analytic, check 2 div(grad p) == f, both <= 1e-11 in the reference's norm2 / N; n = 3 along a periodic
+    direction is the reference's XFAIL (:357-382)."""
+    W = oracle.World(dims, L=(1.0, 1.0, 1.0), bcs=((0, 0), (2, 2), (0, 0)))
+    mask = TEST_COS[name]
+    f, pa = _cos_family(W, n_wave, mask)
+    xfail = n_wave == 3 and (mask[0] or mask[2])
+    p = W.poisson(f)
+    e1 = np.linalg.norm((p - p[0, 0, 0]) - (pa - pa[0, 0, 0])) / p.size
+    gx, gy, gz = W.gradient(p)
+    e2 = np.linalg.norm(W.divergence(gx, gy, gz) - f) / f.size
+    if xfail:
+        assert e1 > 1e-11 or e2 > 1e-11  # the reference expects these to fail (cos(3 pi x) is not periodic on L = 1)
+    else:
+        assert e1 <= 1e-11 and e2 <= 1e-11, (e1, e2)
+
+
+@pytest.mark.parametrize("stretching,beta", [("uniform", 1.0), ("top-bottom", 0.259065151), ("centred", 0.8)])
+def test_poisson_010_stretched_inverts_the_discrete_operator(oracle, stretching, beta):
+    """Stretched y (examples/channel: 'top-bottom', beta = 0.259065151): the reference has no analytic test for the
+    pentadiagonal spectral solve (test_poisson_bc runs the uniform mesh only), so the pin is the property that check 2
+    of that test relies on: for a right-hand side in the range of the solver's own staggered operators (f = div grad p0
+    with the stretching factors), the solve returns p0 up to a constant and div(grad p) == f to round-off.
+    ('bottom' stretching is restated too, but the reference's matrix for it has no special rows for the mean mode
+    and inverts the operator only to ~1e-3; it is used by no configuration and is compared GPU-vs-oracle only.)"""
+    dims = (64, 65, 32)
+    st = ("uniform", stretching, "uniform")
+    W = oracle.World(dims, L=(1.0, 2.0, 1.0), bcs=((0, 0), (2, 2), (0, 0)), stretching=st, beta=(1.0, beta, 1.0))
+    nz, ny, nx = W.shape(1110)
+    z = ((np.arange(nz) + 0.5) / nz)[:, None, None]
+    y = ((np.arange(ny) + 0.5) / ny)[None, :, None]
+    x = ((np.arange(nx) + 0.5) / nx)[None, None, :]
+    p0 = (np.cos(2 * np.pi * x) * np.cos(np.pi * y) * np.cos(2 * np.pi * z) + 0.3 * np.cos(2 * np.pi * y) * np.sin(2 * np.pi * x) +
+          0.2 * np.cos(4 * np.pi * y) + 0.1 * np.cos(3 * np.pi * y))
+    f = W.divergence(*W.gradient(p0))
+    p = W.poisson(f)
+    d = W.divergence(*W.gradient(p))
+    assert np.linalg.norm(d - f) / f.size <= 1e-11           # the reference's check 2 and tolerance
+    assert np.abs(d - f).max() <= 1e-11 * np.abs(f).max()    # and pointwise
+    dp = p - p0
+    assert np.abs(dp - dp.mean()).max() <= 1e-12
