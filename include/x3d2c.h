@@ -213,6 +213,35 @@ int x3d2c_poisson_destroy(x3d2c_ctx* ctx, x3d2c_poisson* p);
 int x3d2c_fft_forward(x3d2c_ctx* ctx, x3d2c_poisson* p, const double* f_c);  /* f_c: DIR_C block */
 int x3d2c_fft_postprocess_000(x3d2c_ctx* ctx, x3d2c_poisson* p);
 int x3d2c_fft_backward(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_c);
+/* ---- non-periodic y (poisson_010, src/poisson_fft.f90:228-242; single rank, as the reference requires :178-180).
+ * fft_forward_010 / fft_backward_010 are x3d2c_fft_forward / x3d2c_fft_backward (as in cuda/poisson_fft.f90:78-83).
+ * stretched: 0 uniform mesh (waves table), 1 'centred' / 'top-bottom' (a_odd_*, a_even_*: (nx_spec, ny_spec / 2, nz_spec, 5)
+ * Fortran order, src/poisson_fft.f90:423-650), 2 'bottom' (a_odd_* = a_re / a_im: (nx_spec, ny_spec, nz_spec, 5)).
+ * The tensors are factorised ONCE here; fft_postprocess_010 never modifies or re-copies them (the reference's kernels
+ * eliminate in place and cuda/poisson_fft.f90:870-895 restores the tensors before every solve). */
+int x3d2c_poisson_create_010(x3d2c_ctx* ctx, const double* waves, const double* ax, const double* bx, const double* ay,
+                             const double* by, const double* az, const double* bz, int stretched,
+                             const double* a_odd_re, const double* a_odd_im, const double* a_even_re,
+                             const double* a_even_im, x3d2c_poisson** out);
+/* fft_postprocess_010 (cuda/poisson_fft.f90:822-924; omp/kernels/spectral_processing.f90:108-283 on a uniform mesh) */
+int x3d2c_fft_postprocess_010(x3d2c_ctx* ctx, x3d2c_poisson* p);
+/* enforce_periodicity_y / undo_periodicity_y (src/poisson_fft.f90:57-58; omp/poisson_fft.f90:237-285): the even / odd
+ * reshuffle in y that turns the cosine transform into an FFT of the same length. DIR_C blocks, f_out != f_in. */
+int x3d2c_enforce_periodicity_y(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_out, const double* f_in);
+int x3d2c_undo_periodicity_y(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_out, const double* f_in);
+/* ---- non-periodic x (100 / 110; src/poisson_fft.f90:47-62): no BASELINE.json configuration has walls in x; the
+ * reference's own OMP backend stops with 'does not support ...' for these hooks (omp/poisson_fft.f90:99-127,183-235).
+ * Exported so that a Fortran extends(poisson_fft_t) can bind every deferred procedure; they return X3D2C_EUNSUPPORTED. */
+int x3d2c_fft_forward_100(x3d2c_ctx* ctx, x3d2c_poisson* p, const double* f_c);
+int x3d2c_fft_forward_110(x3d2c_ctx* ctx, x3d2c_poisson* p, const double* f_c);
+int x3d2c_fft_backward_100(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_c);
+int x3d2c_fft_backward_110(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_c);
+int x3d2c_fft_postprocess_100(x3d2c_ctx* ctx, x3d2c_poisson* p);
+int x3d2c_fft_postprocess_110(x3d2c_ctx* ctx, x3d2c_poisson* p);
+int x3d2c_enforce_periodicity_x(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_out, const double* f_in);
+int x3d2c_undo_periodicity_x(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_out, const double* f_in);
+int x3d2c_enforce_periodicity_xy(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_out, const double* f_in);
+int x3d2c_undo_periodicity_xy(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_out, const double* f_in);
 /* debugging / tests: copy the spectral buffer (reference index order (i, j, k), interleaved re/im) to the host */
 int x3d2c_poisson_get_spectrum(x3d2c_ctx* ctx, x3d2c_poisson* p, double* host_spec);
 

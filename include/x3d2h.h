@@ -64,6 +64,10 @@ int x3d2h_tdsops_tables(int n_tds, double delta, const char* operation, const ch
  * (src/poisson_fft.f90:654-882); waves: (nx/2+1, ny, nz) interleaved re/im */
 int x3d2h_waves_000(const x3d2h_config* cfg, double* waves);
 
+/* same for walls in y (010): waves (nx/2+1, ny_cell, nz) and, on a stretched mesh, the pentadiagonal spectral operators
+ * a_odd / a_even (nx/2+1, rows, nz, 5) of src/poisson_fft.f90:275-652; info = {stretched (0 | 1 | 2), rows} */
+int x3d2h_poisson_tables_010(const x3d2h_config* cfg, int* info, double* waves, double* a_odd, double* a_even);
+
 /* ---- simulation object: xcompact.f90:48-131 + solver init (src/solver.f90:111-212) */
 int x3d2h_create(const x3d2h_config* cfg, x3d2h_sim** out);
 int x3d2h_destroy(x3d2h_sim* sim);

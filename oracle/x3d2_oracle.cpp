@@ -445,6 +445,19 @@ int orc_world_waves(void* h, double* re_im) {
   for (size_t i = 0; i < W->waves.size(); ++i) { re_im[2 * i] = W->waves[i].real(); re_im[2 * i + 1] = W->waves[i].imag(); }
   return 0;
 }
+// stretching_matrix (poisson_fft.f90:275-652): info = {stretched (0 | 1 sym | 2 bottom), rows}; tensors may be null
+int orc_world_stretching_matrix(void* h, int* info, double* a_odd, double* a_even) {
+  ORC_TRY
+  auto* W = (World*)h;
+  info[0] = !W->stretched_y ? 0 : (W->stretched_y_sym ? 1 : 2);
+  info[1] = W->stretched_y_sym ? W->ny_spec / 2 : W->ny_spec;
+  const std::vector<double>& o = W->stretched_y_sym ? W->a_odd : W->a_full;
+  if (a_odd && !o.empty()) std::memcpy(a_odd, o.data(), sizeof(double) * o.size());
+  if (a_even && !W->a_even.empty()) std::memcpy(a_even, W->a_even.data(), sizeof(double) * W->a_even.size());
+  return 0;
+  ORC_CATCH(1)
+}
+
 int orc_world_pressure_correction(void* h) {
   ORC_TRY
   auto* W = (World*)h;

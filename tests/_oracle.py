@@ -65,6 +65,7 @@ def _load():
         orc_world_fft_roundtrip=[C.c_void_p, _dp, _dp, _dp],
         orc_world_spec_dims=[C.c_void_p, _ip],
         orc_world_waves=[C.c_void_p, _dp],
+        orc_world_stretching_matrix=[C.c_void_p, _ip, _dp, _dp],
         orc_world_pressure_correction=[C.c_void_p],
         orc_world_reorder_chain=[C.c_void_p, _dp, _ip, C.c_int, _dp],
         orc_world_sum_intox=[C.c_void_p, C.c_int, _dp, _dp, _dp],
@@ -303,6 +304,16 @@ class World:
         w = np.zeros((nz, ny, nx, 2))
         lib().orc_world_waves(self.h, _p(w))
         return w[..., 0] + 1j * w[..., 1]
+
+    def stretching_matrix(self):
+        """a_odd / a_even (or a_re in a_odd for 'bottom') of poisson_fft.f90:275-652 as [5, nz, rows, nx_spec]."""
+        nx, ny, nz = self.spec_dims()
+        info = (C.c_int * 2)()
+        _chk(lib().orc_world_stretching_matrix(self.h, info, None, None))
+        rows = info[1]
+        ao, ae = np.zeros((5, nz, rows, nx)), np.zeros((5, nz, rows, nx))
+        _chk(lib().orc_world_stretching_matrix(self.h, info, _p(ao), _p(ae)))
+        return dict(stretched=info[0], rows=rows, a_odd=ao, a_even=ae)
 
     def fft_roundtrip(self, f, want_spec=False):
         f = _f(f)

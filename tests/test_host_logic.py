@@ -139,3 +139,20 @@ def test_bench_grid_and_reference_arm():
     j = json.loads(out.strip().splitlines()[-1])
     assert j["impl"] == "reference" and j["cpu_baseline"]["kind"] == "port" and j["value"] > 0
     assert j["e2e"]["h2d_bytes_per_step"] == 0
+
+
+@pytest.mark.parametrize("stretching,beta", [("uniform", 1.0), ("top-bottom", 0.259065151), ("centred", 0.8), ("bottom", 1.3)])
+def test_poisson_010_tables_match_oracle(x3d2, oracle, stretching, beta):
+    """Host layer's base_init for walls in y: the wave-number table and the pentadiagonal spectral operators of a
+    stretched mesh (src/poisson_fft.f90:275-652) against the oracle's transcription, bit for bit."""
+    dims, L = (32, 33, 16), (1.0, 2.0, 3.0)
+    t = x3d2.poisson_tables_010(dims, L, stretching, beta)
+    W = oracle.World(dims, L=L, bcs=((0, 0), (2, 2), (0, 0)), stretching=("uniform", stretching, "uniform"),
+                     beta=(1.0, beta, 1.0))
+    assert np.array_equal(t["waves"], W.waves())
+    m = W.stretching_matrix()
+    assert t["stretched"] == m["stretched"]
+    if stretching != "uniform":
+        assert t["rows"] == m["rows"]
+        assert np.array_equal(t["a_odd"], m["a_odd"]) and np.abs(m["a_odd"]).max() > 0
+        assert np.array_equal(t["a_even"], m["a_even"])

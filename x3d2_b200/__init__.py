@@ -18,7 +18,7 @@ from . import lib as _libmod
 from .lib import (BC_DIRICHLET, BC_HALO, BC_NEUMANN, BC_PERIODIC, CELL, DIR_C, DIR_X, DIR_Y, DIR_Z, FLAG_BASE_OPS, FLAG_STRICT, RDR,
                   VERT, X3D2HConfig, build, load)
 
-__all__ = ["Sim", "build", "load", "tdsops_tables", "decompose", "geo", "waves_000", "DIR_X", "DIR_Y", "DIR_Z", "DIR_C", "VERT",
+__all__ = ["Sim", "build", "load", "tdsops_tables", "poisson_tables_010", "decompose", "geo", "waves_000", "DIR_X", "DIR_Y", "DIR_Z", "DIR_C", "VERT",
            "CELL", "BC_PERIODIC", "BC_NEUMANN", "BC_DIRICHLET", "BC_HALO", "FLAG_STRICT", "FLAG_BASE_OPS", "RDR"]
 
 _dp = C.POINTER(C.c_double)
@@ -111,6 +111,20 @@ def waves_000(dims, L=(2 * np.pi,) * 3, interpl="classic", stagder="compact6"):
     w = np.zeros((nz, ny, nx // 2 + 1, 2))
     _chk(load()[1].x3d2h_waves_000(C.byref(cfg), _p(w)))
     return w[..., 0] + 1j * w[..., 1]
+
+
+def poisson_tables_010(dims, L, stretching="uniform", beta=1.0, interpl="classic", stagder="compact6"):
+    """Host-layer tables of the Poisson solver with walls in y (no GPU needed): waves and the pentadiagonal operators."""
+    cfg = _config(dims, (1, 1, 1), L, ((0, 0), (2, 2), (0, 0)), 1600.0, 1e-3, "RK3", "compact6", "compact6", interpl,
+                  stagder, 0, 1, -1, 0, None, ("uniform", stretching, "uniform"), (1.0, beta, 1.0))
+    nx, ny, nz = dims[0], dims[1] - 1, dims[2]
+    nxh = nx // 2 + 1
+    w = np.zeros((nz, ny, nxh, 2))
+    rows = ny if stretching == "bottom" else ny // 2
+    ao, ae = np.zeros((5, nz, rows, nxh)), np.zeros((5, nz, rows, nxh))
+    info = (C.c_int * 2)()
+    _chk(load()[1].x3d2h_poisson_tables_010(C.byref(cfg), info, _p(w), _p(ao), _p(ae)))
+    return dict(stretched=info[0], rows=info[1], waves=w[..., 0] + 1j * w[..., 1], a_odd=ao, a_even=ae)
 
 
 class Sim:

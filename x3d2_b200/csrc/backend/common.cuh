@@ -124,6 +124,11 @@ struct x3d2c_poisson {
   cufftDoubleComplex* peerA[8] = {nullptr};
   cufftDoubleComplex* peerB[8] = {nullptr};
   double* bar_word = nullptr;  // device word of the all-reduce barriers
+  // non-periodic y (poisson010.cu)
+  int bc_case = 0;      // 0: 000, 10: 010
+  int stretched = 0;    // 0 uniform, 1 odd / even families, 2 one family ('bottom')
+  int penta_rows = 0;   // rows per family
+  double *fac_re = nullptr, *fac_im = nullptr;  // factorised pentadiagonal systems [line][family][row][5]; may alias
 };
 
 // internal launch helpers implemented across the .cu files
@@ -132,4 +137,7 @@ int launch_reorder(x3d2c_ctx* ctx, int dir_from, int dir_to, double* dst, const 
 int ensure_scratch(x3d2c_ctx* ctx, int count = 2);
 int ensure_scratch_slot(x3d2c_ctx* ctx, int i);
 int get_dims_dataloc(const x3d2c_ctx* ctx, int data_loc, int dims[3], bool global);
+// shared part of x3d2c_poisson_create / x3d2c_poisson_create_010 (poisson.cu)
+int poisson_create_common(x3d2c_ctx* ctx, int bc_case, const double* waves, const double* ax, const double* bx,
+                          const double* ay, const double* by, const double* az, const double* bz, x3d2c_poisson** out);
 }  // namespace x3d2c

@@ -258,9 +258,18 @@ int x3d2c_poisson_create(x3d2c_ctx* ctx, const double* waves, const double* ax, 
                          x3d2c_poisson** out) {
   X3D2C_REQUIRE(ctx && waves && ax && bx && ay && by && az && bz && out, "x3d2c_poisson_create: null argument");
   X3D2C_REQUIRE(ctx->cfg.periodic[0] && ctx->cfg.periodic[1] && ctx->cfg.periodic[2],
-                "x3d2c_poisson_create: only the fully periodic (000) solver is implemented");
+                "x3d2c_poisson_create: the fully periodic (000) solver; walls in y: x3d2c_poisson_create_010");
+  return x3d2c::poisson_create_common(ctx, 0, waves, ax, bx, ay, by, az, bz, out);
+}
+
+}  // extern "C"
+
+int x3d2c::poisson_create_common(x3d2c_ctx* ctx, int bc_case, const double* waves, const double* ax, const double* bx,
+                                 const double* ay, const double* by, const double* az, const double* bz,
+                                 x3d2c_poisson** out) {
   X3D2C_REQUIRE(slab_z(ctx), "x3d2c_poisson_create: needs nproc_dir = (1, 1, P)");
   auto* p = new x3d2c_poisson;
+  p->bc_case = bc_case;
   const int P = ctx->cfg.nproc;
   p->nx = ctx->cfg.dims_cell_global[0]; p->ny = ctx->cfg.dims_cell_global[1]; p->nz = ctx->cfg.dims_cell_global[2];
   p->nxh = p->nx / 2 + 1;
@@ -312,6 +321,8 @@ int x3d2c_poisson_create(x3d2c_ctx* ctx, const double* waves, const double* ax, 
   return X3D2C_OK;
 }
 
+extern "C" {
+
 int x3d2c_poisson_destroy(x3d2c_ctx* ctx, x3d2c_poisson* p) {
   if (!p) return X3D2C_OK;
   cudaStreamSynchronize(ctx->stream);
@@ -322,6 +333,8 @@ int x3d2c_poisson_destroy(x3d2c_ctx* ctx, x3d2c_poisson* p) {
     if (p->peerB[r]) cudaIpcCloseMemHandle(p->peerB[r]);
   }
   if (p->bar_word) cudaFree(p->bar_word);
+  if (p->fac_im && p->fac_im != p->fac_re) cudaFree(p->fac_im);
+  if (p->fac_re) cudaFree(p->fac_re);
   for (void* q : {(void*)p->A, (void*)p->B, (void*)p->waves, (void*)p->ax, (void*)p->bx, (void*)p->ay, (void*)p->by,
                   (void*)p->az, (void*)p->bz, (void*)p->compact})
     if (q) cudaFree(q);

@@ -122,6 +122,31 @@ int x3d2h_waves_000(const x3d2h_config* cfg, double* waves) {
   H_CATCH
 }
 
+// base_init of the Poisson solver for a whole (single-rank) domain with walls in y: the wave-number table and, on a
+// stretched mesh, the pentadiagonal spectral operators (src/poisson_fft.f90:275-652). info = {stretched, rows}
+int x3d2h_poisson_tables_010(const x3d2h_config* cfg, int* info, double* waves, double* a_odd, double* a_even) {
+  H_TRY
+  Config k = to_config(cfg);
+  k.rank = 0; k.nproc = 1; k.nproc_dir[0] = k.nproc_dir[1] = k.nproc_dir[2] = 1;
+  Mesh m;
+  m.init(k);
+  DevDirps d[3];
+  for (int q = 0; q < 3; ++q) {
+    const int n_cell = m.get_n(q + 1, CELL);
+    const int b0 = m.BCs[q][0] == BC_DIRICHLET ? BC_NEUMANN : m.BCs[q][0], b1 = m.BCs[q][1] == BC_DIRICHLET ? BC_NEUMANN : m.BCs[q][1];
+    d[q].stagder_v2p.t = tdsops_init(n_cell, m.d[q], "stag-deriv", k.stagder, b0, b1, m.midp_ds[q].data(), nullptr, 4, "v2p");
+    d[q].interpl_v2p.t = tdsops_init(n_cell, m.d[q], "interpolate", k.interpl, b0, b1, nullptr, nullptr, 4, "v2p");
+  }
+  PoissonFFT p;
+  int n_spec[3] = {m.global_cell_dims[0] / 2 + 1, m.global_cell_dims[1], m.global_cell_dims[2]}, st[3] = {0, 0, 0};
+  p.base_init(m, d[0], d[1], d[2], n_spec, st);
+  info[0] = p.stretched; info[1] = p.penta_rows;
+  if (waves) std::memcpy(waves, p.waves.data(), sizeof(cplx) * p.waves.size());
+  if (a_odd && !p.a_odd.empty()) std::memcpy(a_odd, p.a_odd.data(), sizeof(double) * p.a_odd.size());
+  if (a_even && !p.a_even.empty()) std::memcpy(a_even, p.a_even.data(), sizeof(double) * p.a_even.size());
+  H_CATCH
+}
+
 int x3d2h_create(const x3d2h_config* cfg, x3d2h_sim** out) {
   H_TRY
   auto* h = new x3d2h_sim;

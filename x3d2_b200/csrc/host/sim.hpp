@@ -418,6 +418,12 @@ struct PoissonFFT {
   std::vector<double> ax, bx, ay, by, az, bz;  // 1-based
   std::vector<cplx> kx, ky, kz, exs, eys, ezs, k2x, k2y, k2z;
   std::vector<cplx> waves;
+  // non-periodic y (poisson_fft.f90:29-37,176-190): bc_case 10; stretched y adds the pentadiagonal spectral operator
+  int bc_case = 0;       // 0: 000, 10: 010
+  int stretched = 0;     // 0 uniform, 1 'centred' / 'top-bottom' (odd and even modes decouple), 2 'bottom'
+  std::vector<double> trans[3];                    // trans_x/y/z_re (== _im), 1-based
+  std::vector<double> a_odd, a_even;               // (nx_spec, rows, nz_spec, 5) Fortran order; 'bottom': a_odd = a_re
+  int penta_rows = 0;                              // ny_spec / 2 (decoupled families) or ny_spec ('bottom')
 
   // poisson_fft.f90:833-882
   static void wave_numbers(std::vector<double>& a, std::vector<double>& b, std::vector<cplx>& k, std::vector<cplx>& e,
@@ -452,8 +458,13 @@ struct PoissonFFT {
     nx_glob = mesh.global_cell_dims[0]; ny_glob = mesh.global_cell_dims[1]; nz_glob = mesh.global_cell_dims[2];
     nx_spec = n_spec[0]; ny_spec = n_spec[1]; nz_spec = n_spec[2];
     for (int q = 0; q < 3; ++q) sp_st[q] = n_sp_st[q];
-    if (!(mesh.periodic_BC[0] && mesh.periodic_BC[1] && mesh.periodic_BC[2]))
-      fail("Requested BCs are not supported in the cuda_c FFT-based Poisson solver (000 only)");
+    const bool p000 = mesh.periodic_BC[0] && mesh.periodic_BC[1] && mesh.periodic_BC[2];
+    const bool p010 = mesh.periodic_BC[0] && !mesh.periodic_BC[1] && mesh.periodic_BC[2];
+    if (!p000 && !p010) fail("Requested BCs are not supported in the cuda_c FFT-based Poisson solver (000 and 010 only)");
+    if (p010 && mesh.nproc > 1) fail("Multiple ranks are not yet supported for non-periodic BCs!");  // poisson_fft.f90:178-180
+    if (mesh.stretched[0] || mesh.stretched[2])
+      fail("FFT based Poisson solver does not support stretching in x- or z-directions!");
+    bc_case = p010 ? 10 : 0;
     const Tdsops &sx = xd.stagder_v2p.t, &sy = yd.stagder_v2p.t, &sz_ = zd.stagder_v2p.t;
     const Tdsops &ix = xd.interpl_v2p.t, &iy = yd.interpl_v2p.t, &iz = zd.interpl_v2p.t;
     wave_numbers(ax, bx, kx, exs, k2x, nx_glob, mesh.L[0], mesh.d[0], mesh.periodic_BC[0], sx.a, sx.b, sx.alpha);
@@ -475,6 +486,94 @@ struct PoissonFFT {
           const cplx xt2 = k2x[ixx] * (fx * fx), yt2 = k2y[iyy] * (fy * fy), zt2 = k2z[izz] * (fz * fz);
           waves[(i - 1) + (size_t)nx_spec * ((j - 1) + (size_t)ny_spec * (k - 1))] = xt2 + yt2 + zt2;
         }
+    if (p010 && mesh.stretched[1]) stretching_matrix(mesh, xd, yd, zd);
+  }
+
+  // stretching_matrix (poisson_fft.f90:275-652; JCP 228 (2009) 5989, sec. 5). The metric of the stretched mesh is
+  // a0 + 2 a1 cos(2 pi eta), so multiplying by it couples cosine mode m with m +- 2 ('bottom': m +- 1): one
+  // pentadiagonal system per (kx, kz) and mode family. Every complex number of the reference is (1 + i) x, so one
+  // real tensor stands for a_*_re and a_*_im. A row is assembled from the band description below instead of the
+  // reference's five separate triple loops; each entry is the reference's expression, evaluated in its order.
+  double km(int i, int j, int k) const { return trans[0][i] * ky[j].real() * trans[2][k]; }  // get_km, :893-903
+  static double sq(double x) { return x * x; }
+  void stretching_matrix(const Mesh& mesh, const DevDirps& xd, const DevDirps& yd, const DevDirps& zd) {
+    const Tdsops* ip[3] = {&xd.interpl_v2p.t, &yd.interpl_v2p.t, &zd.interpl_v2p.t};
+    const std::vector<cplx>* es[3] = {&exs, &eys, &ezs};
+    const int ns[3] = {nx_spec, ny_spec, nz_spec};
+    for (int q = 0; q < 3; ++q) {
+      trans[q].assign(ns[q] + 1, 0.0);
+      const Tdsops& t = *ip[q];
+      for (int m = 1; m <= ns[q]; ++m) {
+        const double temp = (*es[q])[m].real() * mesh.d[q];
+        trans[q][m] = 2 * (t.a * std::cos(temp * 0.5) + t.b * std::cos(temp * 1.5) + t.c * std::cos(temp * 2.5) +
+                           t.d * std::cos(temp * 3.5)) / (1.0 + 2 * t.alpha * std::cos(temp));
+      }
+    }
+    const std::string& st = mesh.stretching[1];
+    const double a0 = (mesh.alpha[1] / pi + 1.0 / (2 * pi * mesh.beta[1])) * mesh.L[1];
+    const double a1 = (st == "centred" ? 1.0 : (st == "top-bottom" || st == "bottom" ? -1.0 : 0.0)) / (4 * pi * mesh.beta[1]) * mesh.L[1];
+    const bool bottom = st == "bottom";
+    stretched = bottom ? 2 : 1;
+    const int n = penta_rows = bottom ? ny_spec : ny_spec / 2;
+    const int hop = bottom ? 1 : 2;  // distance in y between neighbouring rows of one family
+    a_odd.assign((size_t)nx_spec * n * nz_spec * 5, 0.0);
+    if (!bottom) a_even.assign(a_odd.size(), 0.0);
+    auto at = [&](std::vector<double>& a, int i, int j, int k, int d) -> double& {
+      return a[(size_t)(i - 1) + (size_t)nx_spec * ((j - 1) + (size_t)n * ((k - 1) + (size_t)nz_spec * (d - 1)))];
+    };
+    for (int fam = 0; fam < (bottom ? 1 : 2); ++fam) {
+      std::vector<double>& a = fam == 0 ? a_odd : a_even;
+      const bool even = fam == 1;
+      for (int k = 1; k <= nz_spec; ++k)
+        for (int j = 1; j <= n; ++j)
+          for (int i = 1; i <= nx_spec; ++i) {
+            const int y = bottom ? j : 2 * j - 1 + fam;  // the y mode of row j
+            // main diagonal: the coefficients of km(y)^2 and of km(y) (km(y - hop) + km(y + hop)); the first and last
+            // rows of a family see their neighbour once (mirror) and the even family has modified end rows
+            double c1 = a0 * a0, c2 = a1 * a1, nb;
+            if (j == 1) { nb = km(i, y + hop, k); if (even) c1 = a0 * a0 - a1 * a1; }
+            else if (j == n) { nb = km(i, y - hop, k); if (even) c1 = (a0 + a1) * (a0 + a1); }
+            else nb = km(i, y - hop, k) + km(i, y + hop, k);
+            at(a, i, j, k, 3) = -sq(kx[i].real() * trans[1][y] * trans[2][k]) - sq(kz[k].real() * trans[1][y] * trans[0][i]) -
+                                c1 * sq(km(i, y, k)) - c2 * km(i, y, k) * nb;
+            if (bottom) {  // :368-420
+              if (j + 1 <= n) at(a, i, j, k, 4) = a0 * a1 * km(i, y + 1, k) * (km(i, y, k) + km(i, y + 1, k));
+              if (j + 2 <= n) at(a, i, j, k, 5) = -a1 * a1 * km(i, y + 1, k) * km(i, y + 2, k);
+              if (j >= 2) at(a, i, j, k, 2) = a0 * a1 * km(i, y - 1, k) * (km(i, y, k) + km(i, y - 1, k));
+              if (j >= 3) at(a, i, j, k, 1) = -a1 * a1 * km(i, y - 1, k) * km(i, y - 2, k);
+              continue;
+            }
+            if (j + 1 <= n) {  // first super-diagonal (:500-538); entries of the last row are never used
+              double u1 = a0 * a1, u2 = a0 * a1;
+              if (j == 1 && !even) { u1 = 2 * a0 * a1; u2 = 2 * a0 * a1; }
+              if (j == 1 && even) { u1 = a0 * a1 - a1 * a1; u2 = a0 * a1; }
+              if (j == n - 1 && j != 1 && even) { u1 = a0 * a1; u2 = (a0 + a1) * a1; }
+              at(a, i, j, k, 4) = u1 * (km(i, y, k) * km(i, y + 2, k)) + u2 * sq(km(i, y + 2, k));
+            }
+            if (j + 2 <= n) {  // second super-diagonal (:541-567)
+              const double w = (j == 1 && !even) ? 2 * a1 * a1 : a1 * a1;
+              at(a, i, j, k, 5) = -(w * km(i, y + 2, k) * km(i, y + 4, k));
+            }
+            if (j >= 2) {      // first sub-diagonal (:570-608)
+              double l1 = a0 * a1, l2 = a0 * a1;
+              if (j == 2 && even) { l1 = a0 * a1; l2 = (a0 + a1) * a1; }
+              else if (j == n && even) { l1 = (a0 + a1) * a1; l2 = a0 * a1; }
+              at(a, i, j, k, 2) = l1 * (km(i, y, k) * km(i, y - 2, k)) + l2 * sq(km(i, y - 2, k));
+            }
+            if (j >= 3)        // second sub-diagonal (:611-631)
+              at(a, i, j, k, 1) = -(a1 * a1 * km(i, y - 2, k) * km(i, y - 4, k));
+          }
+    }
+    // the mean mode: the operator is singular there, the first row becomes the identity
+    if (bottom) {  // :418-422
+      at(a_odd, 1, 1, 1, 3) = 1.0; at(a_odd, 1, 1, 1, 4) = 0.0; at(a_odd, 1, 1, 1, 5) = 0.0;
+    } else {       // :633-648
+      for (int k = 1; k <= nz_spec; ++k)
+        for (int i = 1; i <= nx_spec; ++i)
+          if (k2x[i + sp_st[0]].real() < 1e-15 && k2z[k + sp_st[2]].real() < 1e-15) {
+            at(a_odd, i, 1, k, 3) = 1.0; at(a_odd, i, 1, k, 4) = 0.0; at(a_odd, i, 1, k, 5) = 0.0;
+          }
+    }
   }
 };
 
@@ -558,12 +657,22 @@ class Sim {
 
   // init_poisson_fft (cuda/poisson_fft.f90:97-260 pattern): layout from the backend, base_init on the host, upload
   void init_poisson_fft() {
-    if (!(mesh.periodic_BC[0] && mesh.periodic_BC[1] && mesh.periodic_BC[2])) return;
+    const bool p000 = mesh.periodic_BC[0] && mesh.periodic_BC[1] && mesh.periodic_BC[2];
+    const bool p010 = mesh.periodic_BC[0] && !mesh.periodic_BC[1] && mesh.periodic_BC[2];
+    if (!p000 && !(p010 && mesh.nproc == 1)) return;  // other cases: the solver has no FFT Poisson (poisson_fft fails)
     int n_spec[3], n_sp_st[3];
     X3D2H_CALL(x3d2c_poisson_spec_layout(ctx, n_spec, n_sp_st));
     pfft.base_init(mesh, xdirps, ydirps, zdirps, n_spec, n_sp_st);
-    X3D2H_CALL(x3d2c_poisson_create(ctx, reinterpret_cast<const double*>(pfft.waves.data()), &pfft.ax[1], &pfft.bx[1],
-                                    &pfft.ay[1], &pfft.by[1], &pfft.az[1], &pfft.bz[1], &backend.poisson));
+    const double* w = reinterpret_cast<const double*>(pfft.waves.data());
+    if (p000) {
+      X3D2H_CALL(x3d2c_poisson_create(ctx, w, &pfft.ax[1], &pfft.bx[1], &pfft.ay[1], &pfft.by[1], &pfft.az[1], &pfft.bz[1],
+                                      &backend.poisson));
+    } else {  // a_*_re and a_*_im hold the same numbers (see stretching_matrix)
+      const double* ao = pfft.stretched ? pfft.a_odd.data() : nullptr;
+      const double* ae = pfft.stretched == 1 ? pfft.a_even.data() : nullptr;
+      X3D2H_CALL(x3d2c_poisson_create_010(ctx, w, &pfft.ax[1], &pfft.bx[1], &pfft.ay[1], &pfft.by[1], &pfft.az[1],
+                                          &pfft.bz[1], pfft.stretched, ao, ao, ae, ae, &backend.poisson));
+    }
   }
 
   // ---- base-ops mode (X3D2H_FLAG_BASE_OPS): the operator graph of the UNCHANGED reference solver, issued call by
@@ -879,6 +988,21 @@ class Sim {
   // both fields in DIR_Z as in the reference, or the same DIR_C field (solved in place, no reorders)
   void poisson_fft(Field& pressure, const Field& div_u) {
     if (!backend.poisson) fail("FFT Poisson solver is not initialised for these BCs");
+    if (pfft.bc_case == 10) {  // poisson_010 (poisson_fft.f90:228-242) between the reorders of solver.f90:653-678
+      if (pressure.dir != DIR_Z || div_u.dir != DIR_Z) fail("poisson_fft: fields must be in DIR_Z layout");
+      Field* p_temp = allocator.get_block(DIR_C);
+      backend.reorder(*p_temp, div_u, RDR_Z2C);
+      Field* temp = allocator.get_block(DIR_C);
+      X3D2H_CALL(x3d2c_enforce_periodicity_y(ctx, backend.poisson, temp->dev, p_temp->dev));
+      X3D2H_CALL(x3d2c_fft_forward(ctx, backend.poisson, temp->dev));
+      X3D2H_CALL(x3d2c_fft_postprocess_010(ctx, backend.poisson));
+      X3D2H_CALL(x3d2c_fft_backward(ctx, backend.poisson, temp->dev));
+      X3D2H_CALL(x3d2c_undo_periodicity_y(ctx, backend.poisson, p_temp->dev, temp->dev));
+      allocator.release_block(temp);
+      backend.reorder(pressure, *p_temp, RDR_C2Z);
+      allocator.release_block(p_temp);
+      return;
+    }
     if (pressure.dir == DIR_C && &pressure == &div_u) {
       X3D2H_CALL(x3d2c_fft_forward(ctx, backend.poisson, pressure.dev));
       X3D2H_CALL(x3d2c_fft_postprocess_000(ctx, backend.poisson));
@@ -898,7 +1022,7 @@ class Sim {
 
   // solver.f90:693-739
   void pressure_correction(Field& uu, Field& vv, Field& ww) {
-    if (base_ops()) return pressure_correction_base(uu, vv, ww);
+    if (base_ops() || pfft.bc_case == 10) return pressure_correction_base(uu, vv, ww);
     Allocator& A = allocator;
     // the Cartesian field of the FFT is written by the last solve of the divergence and read by the first solve of
     // the gradient: no z2c / c2z passes (same values as the reference's sequence)

@@ -65,6 +65,7 @@ def load():
         x3d2h_tdsops_tables=[C.c_int, C.c_double, C.c_char_p, C.c_char_p, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_char_p,
                              C.c_int, _ip] + [_dp] * 11,
         x3d2h_waves_000=[cfgp, _dp],
+        x3d2h_poisson_tables_010=[cfgp, _ip, _dp, _dp, _dp],
         x3d2h_create=[cfgp, C.POINTER(C.c_void_p)],
         x3d2h_destroy=[C.c_void_p],
         x3d2h_local_dims=[C.c_void_p, C.c_int, _ip],
