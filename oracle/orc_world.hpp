@@ -886,8 +886,10 @@ class World {
       is_010 = false;       // emulation still builds such worlds for operator tests; poisson_fft() then fails when called
       return;
     }
-    if (rm[0].geo.stretched[0] || rm[0].geo.stretched[2])
-      fail("FFT based Poisson solver does not support stretching in x- or z-directions!");
+    if (rm[0].geo.stretched[0] || rm[0].geo.stretched[2]) {  // poisson_fft.f90:166-169: 'FFT based Poisson solver does not
+      is_010 = false;                                          // support stretching in x- or z-directions!' (operator tests
+      return;                                                  // still build such worlds; poisson_fft() fails when called)
+    }
     int nx = gm.global_cell_dims[0], ny = gm.global_cell_dims[1], nz = gm.global_cell_dims[2];
     nx_spec = nx / 2 + 1; ny_spec = ny; nz_spec = nz;
     const Tdsops &sx = xdirps[0].stagder_v2p, &sy = ydirps[0].stagder_v2p, &sz_ = zdirps[0].stagder_v2p;
