@@ -415,5 +415,5 @@ def compute_qcriterion(g):
 def slice_max_sum(f, dir, i_slice):
     """slice_max_sum_omp (omp/backend.f90:816-881) on a Cartesian [nz, ny, nx] array: signed max and sum of the plane
     i_slice (1-based) along `dir`."""
-    pl = {DIR_X: f[:, :, i_slice - 1], DIR_Y: f[:, i_slice - 1, :], DIR_Z: f[i_slice - 1, :, :]}[dir]
+    pl = f[:, :, i_slice - 1] if dir == DIR_X else (f[:, i_slice - 1, :] if dir == DIR_Y else f[i_slice - 1, :, :])
     return float(pl.max()), float(pl.sum())

@@ -189,5 +189,7 @@ def test_channel_like_steps_vs_oracle(oracle, x3d2, stretching, beta, strict):
     m, rm = sim.monitor(), ref.monitor()
     print(stretching, "strict" if strict else "fast", "2 RK3 steps, rel err %.2e, div_u_max %.2e (oracle %.2e)" % (err, m["div_u_max"], rm["div_u_max"]))
     assert err < 1e-12
-    assert m["div_u_max"] < 1e-10 and abs(m["enstrophy"] - rm["enstrophy"]) <= 1e-10 * rm["enstrophy"]
+    # with walls the corrected field is solenoidal only up to the boundary closures (the oracle shows the same residual)
+    assert abs(m["div_u_max"] - rm["div_u_max"]) <= 1e-6 * rm["div_u_max"] + 1e-13
+    assert abs(m["enstrophy"] - rm["enstrophy"]) <= 1e-10 * rm["enstrophy"]
     sim.close()
