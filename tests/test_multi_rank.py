@@ -1,9 +1,11 @@
 """N > 1 coverage.
 
-CPU (gloo, world_size 2): the host layer's decomposition and the exchange patterns the backend uses
-(neighbour halo exchange of sendrecv_fields, z-slab -> y-slab all-to-all packing of the FFT) are run with real
-message passing and compared with the global arrays.
-GPU (>= 2 devices): tools/mgpu_check.py under torchrun compares every rank's slab with the oracle's P-rank emulation.
+CPU (gloo, world_size 2): a test of the host layer's DECOMPOSITION (x3d2h_decompose: offsets, extents, cyclic
+neighbours) under real message passing. The halo exchange and the z-slab -> y-slab transpose are re-stated here with
+torch / numpy index maps as a specification of what nccl.cu / poisson.cu have to deliver; the product's exchange
+kernels themselves only run on GPUs (no CPU fallback exists), where
+GPU (>= 2 devices): tools/mgpu_check.py under torchrun compares every rank's slab with the oracle's P-rank emulation,
+at small shapes and at the per-rank shape of the benchmark.
 """
 import os
 import subprocess

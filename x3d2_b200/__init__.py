@@ -28,8 +28,18 @@ def _p(a):
     return a.ctypes.data_as(_dp)
 
 
-def _f(a):
-    return np.ascontiguousarray(a, dtype=np.float64)
+def _f(a, shape=None):
+    """float64, C-contiguous; with `shape` the extents are checked: the host layer copies shape-many doubles."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and a.shape != tuple(shape):
+        raise ValueError(f"x3d2_b200: array of shape {a.shape} where the rank-local extents are {tuple(shape)}")
+    return a
+
+
+def _out_ok(a, shape):
+    if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.shape == tuple(shape)):
+        raise ValueError(f"x3d2_b200: output arrays must be C-contiguous float64 of shape {tuple(shape)}")
+    return a
 
 
 def _chk(rc):
@@ -178,11 +188,11 @@ class Sim:
         _chk(self._h.x3d2h_init_tgv(self.h))
 
     def set_uvw(self, u, v, w):
-        u, v, w = _f(u), _f(v), _f(w)
+        u, v, w = (_f(a, self.shape()) for a in (u, v, w))
         _chk(self._h.x3d2h_set_velocity(self.h, _p(u), _p(v), _p(w)))
 
     def get_uvw(self, out=None):
-        u, v, w = out if out is not None else (self._out(), self._out(), self._out())
+        u, v, w = [_out_ok(a, self.shape()) for a in out] if out is not None else (self._out(), self._out(), self._out())
         _chk(self._h.x3d2h_get_velocity(self.h, _p(u), _p(v), _p(w)))
         return u, v, w
 
@@ -211,46 +221,46 @@ class Sim:
 
     # ------------------------------------------------------------------ operators on host data
     def transeq(self, u, v, w):
-        u, v, w = _f(u), _f(v), _f(w)
+        u, v, w = (_f(a, self.shape()) for a in (u, v, w))
         a, b, c = self._out(), self._out(), self._out()
         _chk(self._h.x3d2h_transeq(self.h, _p(u), _p(v), _p(w), _p(a), _p(b), _p(c)))
         return a, b, c
 
     def transeq_dir(self, dir, u, v, w):
-        u, v, w = _f(u), _f(v), _f(w)
+        u, v, w = (_f(a, self.shape()) for a in (u, v, w))
         a, b, c = self._out(), self._out(), self._out()
         _chk(self._h.x3d2h_transeq_dir(self.h, dir, _p(u), _p(v), _p(w), _p(a), _p(b), _p(c)))
         return a, b, c
 
     def transeq_lowmem(self, u, v, w):
         """solver.f90:391-505: (du, dv, dw, u after its x -> y -> z -> x round trip)."""
-        u, v, w = _f(u), _f(v), _f(w)
+        u, v, w = (_f(a, self.shape()) for a in (u, v, w))
         a, b, c, ub = self._out(), self._out(), self._out(), self._out()
         _chk(self._h.x3d2h_transeq_lowmem(self.h, _p(u), _p(v), _p(w), _p(a), _p(b), _p(c), _p(ub)))
         return a, b, c, ub
 
     def transeq_species(self, u, v, w, spec, nu_s):
-        u, v, w, spec = _f(u), _f(v), _f(w), _f(spec)
+        u, v, w, spec = (_f(a, self.shape()) for a in (u, v, w, spec))
         d = self._out()
         _chk(self._h.x3d2h_transeq_species(self.h, _p(u), _p(v), _p(w), _p(spec), float(nu_s), _p(d)))
         return d
 
     def derived(self, what, grads):
         """compute_vorticity / compute_qcriterion from the nine velocity gradients (dudx, dudy, ..., dwdz)."""
-        g = [_f(a) for a in grads]
+        g = [_f(a, self.shape()) for a in grads]
         arr = (_dp * 9)(*[_p(a) for a in g])
         out = self._out()
         _chk(self._h.x3d2h_derived(self.h, what.encode(), arr, _p(out)))
         return out
 
     def slice_max_sum(self, dir, x, i_slice, loc=VERT):
-        x = _f(x)
+        x = _f(x, self.shape(loc))
         mx, sm = C.c_double(0), C.c_double(0)
         _chk(self._h.x3d2h_slice_max_sum(self.h, dir, loc, _p(x), i_slice, C.byref(mx), C.byref(sm)))
         return mx.value, sm.value
 
     def tds_solve(self, dir, opname, f, in_loc=VERT):
-        f = _f(f)
+        f = _f(f, self.shape(in_loc))
         move = {"stagder_v2p": 1, "interpl_v2p": 1, "stagder_p2v": -1, "interpl_p2v": -1}.get(opname, 0)
         out = self._out(in_loc + move * 10 ** dir)
         ol = C.c_int(0)
@@ -280,25 +290,25 @@ class Sim:
         return (oa, ob) if mode == "dual" else oa
 
     def divergence(self, u, v, w):
-        u, v, w = _f(u), _f(v), _f(w)
+        u, v, w = (_f(a, self.shape()) for a in (u, v, w))
         d = self._out(CELL)
         _chk(self._h.x3d2h_divergence(self.h, _p(u), _p(v), _p(w), _p(d)))
         return d
 
     def gradient(self, p):
-        p = _f(p)
+        p = _f(p, self.shape(CELL))
         a, b, c = self._out(), self._out(), self._out()
         _chk(self._h.x3d2h_gradient(self.h, _p(p), _p(a), _p(b), _p(c)))
         return a, b, c
 
     def curl(self, u, v, w):
-        u, v, w = _f(u), _f(v), _f(w)
+        u, v, w = (_f(a, self.shape()) for a in (u, v, w))
         a, b, c = self._out(), self._out(), self._out()
         _chk(self._h.x3d2h_curl(self.h, _p(u), _p(v), _p(w), _p(a), _p(b), _p(c)))
         return a, b, c
 
     def poisson(self, f):
-        f = _f(f)
+        f = _f(f, self.shape(CELL))
         p = self._out(CELL)
         _chk(self._h.x3d2h_poisson(self.h, _p(f), _p(p)))
         return p
@@ -316,40 +326,40 @@ class Sim:
         return out
 
     def reorder_chain(self, f, names):
-        f = _f(f)
+        f = _f(f, self.shape())
         out = self._out()
         r = (C.c_int * len(names))(*[RDR[n] for n in names])
         _chk(self._h.x3d2h_reorder_chain(self.h, _p(f), r, len(names), _p(out)))
         return out
 
     def sum_intox(self, dir_from, a, b):
-        a, b = _f(a), _f(b)
+        a, b = _f(a, self.shape()), _f(b, self.shape())
         out = self._out()
         _chk(self._h.x3d2h_sum_intox(self.h, dir_from, _p(a), _p(b), _p(out)))
         return out
 
     def vecadd(self, dir, a, x, b, y):
-        x, y = _f(x), _f(y)
+        x, y = _f(x, self.shape()), _f(y, self.shape())
         out = self._out()
         _chk(self._h.x3d2h_vecadd(self.h, dir, a, _p(x), b, _p(y), _p(out)))
         return out
 
     def scalar_product(self, dir, x, y, loc=VERT):
-        x, y = _f(x), _f(y)
+        x, y = _f(x, self.shape(loc)), _f(y, self.shape(loc))
         s = C.c_double(0)
         _chk(self._h.x3d2h_scalar_product(self.h, dir, loc, _p(x), _p(y), C.byref(s)))
         return s.value
 
     def field_max_mean(self, dir, x, loc=VERT):
-        x = _f(x)
+        x = _f(x, self.shape(loc))
         mx, mean = C.c_double(0), C.c_double(0)
         _chk(self._h.x3d2h_field_max_mean(self.h, dir, loc, _p(x), C.byref(mx), C.byref(mean)))
         return mx.value, mean.value
 
     def fieldop(self, op, dir, x, y=None, a=0.0, loc=VERT, extra=None):
         """field_scale / field_shift / vecmult / veccopy / fill / volume_integral / set_face / set_face_from_field."""
-        x = _f(x)
-        y = _f(y) if y is not None else None
+        x = _f(x, self.shape(loc))
+        y = _f(y, self.shape(loc)) if y is not None else None
         out = self._out(loc)
         s = (C.c_double * 2)(*(extra or (0.0, 0.0)))  # set_face*: (c_end | flow_rate_diff, face)
         _chk(self._h.x3d2h_fieldop(self.h, op.encode(), dir, loc, float(a), _p(x), _p(y) if y is not None else None,

@@ -53,6 +53,13 @@ void set_error(const std::string& msg);
     }                                  \
   } while (0)
 
+// Every entry point makes the context's device current first: the host application (torch, another Sim on another
+// GPU of the same process) may have switched devices between two calls.
+#define X3D2C_ENTER(ctx)                                  \
+  do {                                                    \
+    if (ctx) X3D2C_CHECK_CUDA(cudaSetDevice((ctx)->device)); \
+  } while (0)
+
 #define X3D2C_CHECK_LAUNCH(ctx)                      \
   do {                                               \
     (ctx)->launches++;                               \
@@ -60,6 +67,15 @@ void set_error(const std::string& msg);
   } while (0)
 
 struct NcclApi;  // dlopen'ed entry points (nccl.cu)
+
+// rows of SZ * max(n_groups) doubles in ctx->halo: the reference-order path carves 3 fields x 4 buffers x 4 rows + 2 x 18
+// reduced-system rows (tds_m1.cu: carve), the rank-split fast path 4 x (3 x 4) halo rows + 4 x (9 x 3) carry rows
+// (m3_common.cuh: kDistRows, checked there by a static_assert)
+constexpr int kHaloRowsRef = 3 * 4 * 4 + 2 * 18;
+constexpr int kHaloRowsDist = 4 * (3 * 4) + 4 * (9 * 3);
+constexpr int kHaloRows = kHaloRowsDist > kHaloRowsRef ? kHaloRowsDist : kHaloRowsRef;
+
+constexpr int kMaxDevices = 64;  // per-device caches of launch attributes / occupancy are indexed by the device ordinal
 
 }  // namespace x3d2c
 

@@ -56,7 +56,12 @@ int x3d2c_create(const x3d2c_config* cfg, x3d2c_ctx** out) {
               "). The cuda_c backend has no CPU fallback.");
     return X3D2C_ECUDA;
   }
-  auto* ctx = new x3d2c_ctx;
+  // released by the guard on every early return (X3D2C_CHECK_* / REQUIRE below), handed over at the end
+  struct Guard {
+    x3d2c_ctx* c;
+    ~Guard() { if (c) x3d2c_destroy(c); }
+  } guard{new x3d2c_ctx};
+  x3d2c_ctx* ctx = guard.c;
   ctx->cfg = *cfg;
   ctx->cfg.nccl_unique_id = nullptr;
   if (cfg->device >= 0) X3D2C_CHECK_CUDA(cudaSetDevice(cfg->device));
@@ -77,8 +82,7 @@ int x3d2c_create(const x3d2c_config* cfg, x3d2c_ctx** out) {
   // 9 quantities x 4 buffers x 1 row, sized for the largest cross-section (omp/backend.f90:84-112)
   int ng = ctx->n_groups[1] > ctx->n_groups[2] ? ctx->n_groups[1] : ctx->n_groups[2];
   if (ctx->n_groups[3] > ng) ng = ctx->n_groups[3];
-  // multi-rank contexts also hold the exchange buffers of the distributed fast path (m3_common.cuh: DistBufs)
-  const int halo_rows = (ctx->cfg.nproc > 1 || ctx->force_dist) ? 4 * (3 * 4) + 4 * (9 * 3) : 3 * 4 * 4 + 9 * 4 * 1;  // m3::kDistRows
+  const int halo_rows = kHaloRows;  // common.cuh: both carvings fit (checked where they are made)
   ctx->halo_doubles = (size_t)SZ * ng * halo_rows;
   X3D2C_CHECK_CUDA(cudaMalloc(&ctx->halo, sizeof(double) * ctx->halo_doubles));
   X3D2C_CHECK_CUDA(cudaMemsetAsync(ctx->halo, 0, sizeof(double) * ctx->halo_doubles, ctx->stream));
@@ -92,11 +96,13 @@ int x3d2c_create(const x3d2c_config* cfg, x3d2c_ctx** out) {
     ctx->cfg.nccl_unique_id = nullptr;
     if (rc) return rc;
   }
+  guard.c = nullptr;
   *out = ctx;
   return X3D2C_OK;
 }
 
 int x3d2c_destroy(x3d2c_ctx* ctx) {
+  X3D2C_ENTER(ctx);
   if (!ctx) return X3D2C_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
@@ -106,17 +112,19 @@ int x3d2c_destroy(x3d2c_ctx* ctx) {
   if (ctx->halo) cudaFree(ctx->halo);
   if (ctx->red) cudaFree(ctx->red);
   if (ctx->red_host) cudaFreeHost(ctx->red_host);
-  cudaStreamDestroy(ctx->stream);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return X3D2C_OK;
 }
 
 int x3d2c_sync(x3d2c_ctx* ctx) {
+  X3D2C_ENTER(ctx);
   X3D2C_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
   return X3D2C_OK;
 }
 
 int x3d2c_get_padded_dims(const x3d2c_ctx* ctx, int dims_padded[3], int n_groups[3], long long* ngrid) {
+  X3D2C_ENTER(ctx);
   dims_padded[0] = ctx->nx_pad; dims_padded[1] = ctx->ny_pad; dims_padded[2] = ctx->nz_pad;
   n_groups[0] = ctx->n_groups[1]; n_groups[1] = ctx->n_groups[2]; n_groups[2] = ctx->n_groups[3];
   *ngrid = ctx->ngrid;
@@ -127,6 +135,7 @@ long long x3d2c_launch_count(const x3d2c_ctx* ctx) { return ctx->launches; }
 void* x3d2c_stream(const x3d2c_ctx* ctx) { return (void*)ctx->stream; }
 
 int x3d2c_field_alloc(x3d2c_ctx* ctx, double** dev) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && dev, "x3d2c_field_alloc: null argument");
   cudaError_t e = cudaMalloc(dev, sizeof(double) * ctx->ngrid);
   if (e != cudaSuccess) {
@@ -138,18 +147,21 @@ int x3d2c_field_alloc(x3d2c_ctx* ctx, double** dev) {
 }
 
 int x3d2c_field_free(x3d2c_ctx* ctx, double* dev) {
+  X3D2C_ENTER(ctx);
   X3D2C_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
   X3D2C_CHECK_CUDA(cudaFree(dev));
   return X3D2C_OK;
 }
 
 int x3d2c_copy_data_to_f(x3d2c_ctx* ctx, double* dev, const double* host_data) {
+  X3D2C_ENTER(ctx);
   X3D2C_CHECK_CUDA(cudaMemcpyAsync(dev, host_data, sizeof(double) * ctx->ngrid, cudaMemcpyHostToDevice, ctx->stream));
   X3D2C_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
   return X3D2C_OK;
 }
 
 int x3d2c_copy_f_to_data(x3d2c_ctx* ctx, double* host_data, const double* dev) {
+  X3D2C_ENTER(ctx);
   X3D2C_CHECK_CUDA(cudaMemcpyAsync(host_data, dev, sizeof(double) * ctx->ngrid, cudaMemcpyDeviceToHost, ctx->stream));
   X3D2C_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
   return X3D2C_OK;
@@ -160,6 +172,7 @@ int x3d2c_tdsops_create(x3d2c_ctx* ctx, int n_tds, int n_rhs, int move, int peri
                         const double* dist_bw, const double* dist_sa, const double* dist_sc,
                         const double* dist_af, const double* stretch, const double* stretch_correct,
                         x3d2c_tdsops** out) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && out && coeffs && coeffs_s && coeffs_e && dist_fw && dist_bw && dist_sa && dist_sc &&
                     dist_af && stretch && stretch_correct, "x3d2c_tdsops_create: null argument");
   X3D2C_REQUIRE(n_tds >= 9 && (n_rhs == n_tds || n_rhs == n_tds + 1), "x3d2c_tdsops_create: bad n_tds / n_rhs");
@@ -201,6 +214,7 @@ int x3d2c_tdsops_create(x3d2c_ctx* ctx, int n_tds, int n_rhs, int move, int peri
 }
 
 int x3d2c_tdsops_destroy(x3d2c_ctx* ctx, x3d2c_tdsops* ops) {
+  X3D2C_ENTER(ctx);
   if (!ops) return X3D2C_OK;
   X3D2C_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ops->d_block) cudaFree(ops->d_block);

@@ -322,14 +322,17 @@ using namespace x3d2c;
 extern "C" {
 
 int x3d2c_field_fill(x3d2c_ctx* ctx, double* dev, double c) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && dev, "x3d2c_field_fill: null argument");
   return run_stream<OP_FILL>(ctx, dev, nullptr, c, 0.0);
 }
 int x3d2c_veccopy(x3d2c_ctx* ctx, double* dst, const double* src) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && dst && src, "x3d2c_veccopy: null argument");
   return run_stream<OP_COPY>(ctx, dst, src, 0.0, 0.0);
 }
 int x3d2c_vecadd(x3d2c_ctx* ctx, double a, const double* x, double b, double* y) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && x && y, "x3d2c_vecadd: null argument");
   if (ctx->strict) {
     axpby_strict_kernel<<<kBlocks, kThreads, 0, ctx->stream>>>(y, x, a, b, ctx->ngrid);
@@ -340,6 +343,7 @@ int x3d2c_vecadd(x3d2c_ctx* ctx, double a, const double* x, double b, double* y)
 }
 int x3d2c_veclincomb(x3d2c_ctx* ctx, double* out, const double* base, int n, const double* coef,
                      const double* const* x) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && out && base && n >= 1 && n <= 4 && coef && x, "x3d2c_veclincomb: bad argument");
   LinComb q{};
   q.base = base;
@@ -357,14 +361,17 @@ int x3d2c_veclincomb(x3d2c_ctx* ctx, double* out, const double* base, int n, con
   return X3D2C_OK;
 }
 int x3d2c_vecmult(x3d2c_ctx* ctx, double* y, const double* x) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && x && y, "x3d2c_vecmult: null argument");
   return run_stream<OP_MULT>(ctx, y, x, 0.0, 0.0);
 }
 int x3d2c_field_scale(x3d2c_ctx* ctx, double* f, double a) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && f, "x3d2c_field_scale: null argument");
   return run_stream<OP_SCALE>(ctx, f, nullptr, a, 0.0);
 }
 int x3d2c_field_shift(x3d2c_ctx* ctx, double* f, double a) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && f, "x3d2c_field_shift: null argument");
   return run_stream<OP_SHIFT>(ctx, f, nullptr, a, 0.0);
 }
@@ -380,6 +387,7 @@ static int face_geom(const x3d2c_ctx* ctx, int data_loc, FaceGeom* g) {
 }
 
 int x3d2c_field_set_face(x3d2c_ctx* ctx, double* f, int data_loc, double c_start, double c_end, int face) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && f, "x3d2c_field_set_face: null argument");
   X3D2C_REQUIRE(face == X3D2C_X_FACE || face == X3D2C_Y_FACE || face == X3D2C_Z_FACE, "face is undefined.");
   X3D2C_REQUIRE(face != X3D2C_X_FACE, "Setting X_FACE is not yet supported.");  // omp/backend.f90:930-931
@@ -394,6 +402,7 @@ int x3d2c_field_set_face(x3d2c_ctx* ctx, double* f, int data_loc, double c_start
 
 int x3d2c_field_set_face_from_field(x3d2c_ctx* ctx, double* f, const double* f_start, int data_loc, double c_end,
                                     int face, double flow_rate_diff) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && f && f_start, "x3d2c_field_set_face_from_field: null argument");
   X3D2C_REQUIRE(face == X3D2C_X_FACE || face == X3D2C_Y_FACE,
                 "field_set_face_from_field: only X_FACE and Y_FACE supported.");  // omp/backend.f90:1017-1018
@@ -410,6 +419,7 @@ int x3d2c_field_set_face_from_field(x3d2c_ctx* ctx, double* f, const double* f_s
 }
 
 int x3d2c_scalar_product(x3d2c_ctx* ctx, int dir, int data_loc, const double* x, const double* y, double* s) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && x && y && s, "x3d2c_scalar_product: null argument");
   RedGeom q;
   int rc = red_geom(ctx, dir, data_loc, &q);
@@ -422,6 +432,7 @@ int x3d2c_scalar_product(x3d2c_ctx* ctx, int dir, int data_loc, const double* x,
 }
 
 int x3d2c_field_max_mean(x3d2c_ctx* ctx, int dir, int data_loc, const double* f, double* max_val, double* mean_val) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && f && max_val && mean_val, "x3d2c_field_max_mean: null argument");
   RedGeom q;
   int rc = red_geom(ctx, dir, data_loc, &q);
@@ -446,6 +457,7 @@ int x3d2c_field_max_mean(x3d2c_ctx* ctx, int dir, int data_loc, const double* f,
 
 int x3d2c_slice_max_sum(x3d2c_ctx* ctx, int dir, int data_loc, const double* f, int i_slice, double* max_val,
                         double* sum_val) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && f && max_val && sum_val, "x3d2c_slice_max_sum: null argument");
   X3D2C_REQUIRE(dir != X3D2C_DIR_C, "slice_max_sum does not support DIR_C fields!");
   RedGeom q;
@@ -478,17 +490,20 @@ static int derive(x3d2c_ctx* ctx, bool qcrit, double* out, const double* const* 
 int x3d2c_compute_vorticity(x3d2c_ctx* ctx, double* field_out, const double* dudx, const double* dudy,
                             const double* dudz, const double* dvdx, const double* dvdy, const double* dvdz,
                             const double* dwdx, const double* dwdy, const double* dwdz) {
+  X3D2C_ENTER(ctx);
   const double* g[9] = {dudx, dudy, dudz, dvdx, dvdy, dvdz, dwdx, dwdy, dwdz};
   return derive(ctx, false, field_out, g);
 }
 int x3d2c_compute_qcriterion(x3d2c_ctx* ctx, double* field_out, const double* dudx, const double* dudy,
                              const double* dudz, const double* dvdx, const double* dvdy, const double* dvdz,
                              const double* dwdx, const double* dwdy, const double* dwdz) {
+  X3D2C_ENTER(ctx);
   const double* g[9] = {dudx, dudy, dudz, dvdx, dvdy, dvdz, dwdx, dwdy, dwdz};
   return derive(ctx, true, field_out, g);
 }
 
 int x3d2c_field_volume_integral(x3d2c_ctx* ctx, int data_loc, const double* f, double* s) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && f && s, "x3d2c_field_volume_integral: null argument");
   RedGeom q;
   int rc = red_geom(ctx, X3D2C_DIR_X, data_loc, &q);

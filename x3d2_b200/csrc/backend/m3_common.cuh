@@ -254,6 +254,7 @@ struct DistBufs {
   double *carr_to_prev, *carr_to_next, *carr_from_prev, *carr_from_next;
 };
 constexpr int kDistRows = 4 * (3 * 4) + 4 * (9 * EXP_ROWS);  // rows of SZ*G doubles that DistBufs needs
+static_assert(kDistRows <= x3d2c::kHaloRows, "ctx->halo (ctx.cu) is too small for the rank-split exchange buffers");
 DistBufs carve_dist(x3d2c_ctx* ctx);
 bool dist_supported(const x3d2c_ctx* ctx, int dir, int n);
 

@@ -148,7 +148,8 @@ bool make_op(const x3d2c_tdsops* t, double scale, bool dist, Op* o, bool exact) 
 }
 
 int num_sms(const x3d2c_ctx* ctx) {
-  static int sms = 0;
+  static int sms_dev[x3d2c::kMaxDevices] = {};
+  int& sms = sms_dev[ctx->device];
   if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   return sms > 0 ? sms : 148;
 }
@@ -175,7 +176,8 @@ DistBufs carve_dist(x3d2c_ctx* ctx) {
   b.carr_to_prev = p; p += 9 * EXP_ROWS * row;
   b.carr_to_next = p; p += 9 * EXP_ROWS * row;
   b.carr_from_prev = p; p += 9 * EXP_ROWS * row;
-  b.carr_from_next = p;
+  b.carr_from_next = p; p += 9 * EXP_ROWS * row;
+  if ((size_t)(p - ctx->halo) > ctx->halo_doubles) { std::fprintf(stderr, "x3d2c: halo buffer overflow in carve_dist()\n"); std::abort(); }
   return b;
 }
 

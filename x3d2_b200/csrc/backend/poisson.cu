@@ -190,6 +190,7 @@ using namespace x3d2c;
 extern "C" {
 
 int x3d2c_poisson_spec_layout(const x3d2c_ctx* ctx, int n_spec[3], int n_sp_st[3]) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && n_spec && n_sp_st, "x3d2c_poisson_spec_layout: null argument");
   X3D2C_REQUIRE(slab_z(ctx), "the cuda_c FFT Poisson solver needs nproc_dir = (1, 1, P)");
   const int P = ctx->cfg.nproc, ny = ctx->cfg.dims_cell_global[1];
@@ -256,6 +257,7 @@ static int stream_barrier(x3d2c_ctx* ctx, x3d2c_poisson* p) { return allreduce(c
 int x3d2c_poisson_create(x3d2c_ctx* ctx, const double* waves, const double* ax, const double* bx,
                          const double* ay, const double* by, const double* az, const double* bz,
                          x3d2c_poisson** out) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && waves && ax && bx && ay && by && az && bz && out, "x3d2c_poisson_create: null argument");
   X3D2C_REQUIRE(ctx->cfg.periodic[0] && ctx->cfg.periodic[1] && ctx->cfg.periodic[2],
                 "x3d2c_poisson_create: the fully periodic (000) solver; walls in y: x3d2c_poisson_create_010");
@@ -268,7 +270,12 @@ int x3d2c::poisson_create_common(x3d2c_ctx* ctx, int bc_case, const double* wave
                                  const double* ay, const double* by, const double* az, const double* bz,
                                  x3d2c_poisson** out) {
   X3D2C_REQUIRE(slab_z(ctx), "x3d2c_poisson_create: needs nproc_dir = (1, 1, P)");
-  auto* p = new x3d2c_poisson;
+  struct Guard {  // no leak on the early returns below
+    x3d2c_ctx* c;
+    x3d2c_poisson* p;
+    ~Guard() { if (p) x3d2c_poisson_destroy(c, p); }
+  } guard{ctx, new x3d2c_poisson};
+  x3d2c_poisson* p = guard.p;
   p->bc_case = bc_case;
   const int P = ctx->cfg.nproc;
   p->nx = ctx->cfg.dims_cell_global[0]; p->ny = ctx->cfg.dims_cell_global[1]; p->nz = ctx->cfg.dims_cell_global[2];
@@ -317,6 +324,7 @@ int x3d2c::poisson_create_common(x3d2c_ctx* ctx, int bc_case, const double* wave
     rc = setup_peer_buffers(ctx, p);
     if (rc) return rc;
   }
+  guard.p = nullptr;
   *out = p;
   return X3D2C_OK;
 }
@@ -324,6 +332,7 @@ int x3d2c::poisson_create_common(x3d2c_ctx* ctx, int bc_case, const double* wave
 extern "C" {
 
 int x3d2c_poisson_destroy(x3d2c_ctx* ctx, x3d2c_poisson* p) {
+  X3D2C_ENTER(ctx);
   if (!p) return X3D2C_OK;
   cudaStreamSynchronize(ctx->stream);
   if (p->have_plans) { cufftDestroy(p->plan_r2c); cufftDestroy(p->plan_c2r); cufftDestroy(p->plan_y); cufftDestroy(p->plan_z); }
@@ -346,6 +355,7 @@ int x3d2c_poisson_destroy(x3d2c_ctx* ctx, x3d2c_poisson* p) {
 static cufftDoubleComplex* spec_buf(const x3d2c_ctx*, x3d2c_poisson* p) { return p->p2p ? p->A : p->B; }
 
 int x3d2c_fft_forward(x3d2c_ctx* ctx, x3d2c_poisson* p, const double* f_c) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && p && f_c, "x3d2c_fft_forward: null argument");
   const double* in = f_c;
   if (p->compact) {
@@ -387,6 +397,7 @@ int x3d2c_fft_forward(x3d2c_ctx* ctx, x3d2c_poisson* p, const double* f_c) {
 }
 
 int x3d2c_fft_postprocess_000(x3d2c_ctx* ctx, x3d2c_poisson* p) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && p, "x3d2c_fft_postprocess_000: null argument");
   SpecParams sp;
   sp.ny_loc = p->ny_loc; sp.nxh = p->nxh; sp.nz = p->nz;
@@ -409,6 +420,7 @@ int x3d2c_fft_postprocess_000(x3d2c_ctx* ctx, x3d2c_poisson* p) {
 }
 
 int x3d2c_fft_backward(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_c) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && p && f_c, "x3d2c_fft_backward: null argument");
   cufftDoubleComplex* c = spec_buf(ctx, p);
   X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_z, c, c, CUFFT_INVERSE));
@@ -445,6 +457,7 @@ int x3d2c_fft_backward(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_c) {
 }
 
 int x3d2c_poisson_get_spectrum(x3d2c_ctx* ctx, x3d2c_poisson* p, double* host_spec) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && p && host_spec, "x3d2c_poisson_get_spectrum: null argument");
   const size_t n = (size_t)p->nxh * p->ny_loc * p->nz;
   std::vector<double> tmp(2 * n);

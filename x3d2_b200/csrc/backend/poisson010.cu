@@ -241,6 +241,7 @@ int x3d2c_poisson_create_010(x3d2c_ctx* ctx, const double* waves, const double* 
                              const double* by, const double* az, const double* bz, int stretched,
                              const double* a_odd_re, const double* a_odd_im, const double* a_even_re,
                              const double* a_even_im, x3d2c_poisson** out) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && waves && ax && bx && ay && by && az && bz && out, "x3d2c_poisson_create_010: null argument");
   X3D2C_REQUIRE(ctx->cfg.periodic[0] && !ctx->cfg.periodic[1] && ctx->cfg.periodic[2],
                 "x3d2c_poisson_create_010: needs periodic x and z and walls in y");
@@ -253,6 +254,11 @@ int x3d2c_poisson_create_010(x3d2c_ctx* ctx, const double* waves, const double* 
   x3d2c_poisson* p = nullptr;
   int rc = poisson_create_common(ctx, 10, waves, ax, bx, ay, by, az, bz, &p);
   if (rc) return rc;
+  struct Guard {
+    x3d2c_ctx* c;
+    x3d2c_poisson* p;
+    ~Guard() { if (p) x3d2c_poisson_destroy(c, p); }
+  } guard{ctx, p};
   p->stretched = stretched;
   if (stretched) {
     const int F = stretched == 1 ? 2 : 1, n = stretched == 1 ? p->ny / 2 : p->ny;
@@ -277,11 +283,13 @@ int x3d2c_poisson_create_010(x3d2c_ctx* ctx, const double* waves, const double* 
   const size_t smem = sizeof(double) * (size_t)LPC * (2 * p->ny + 2);
   X3D2C_REQUIRE(smem <= 227 * 1024, "x3d2c_poisson_create_010: ny too large for the on-chip y lines");
   X3D2C_CHECK_CUDA(cudaFuncSetAttribute(spectral_010_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  guard.p = nullptr;
   *out = p;
   return X3D2C_OK;
 }
 
 int x3d2c_fft_postprocess_010(x3d2c_ctx* ctx, x3d2c_poisson* p) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && p, "x3d2c_fft_postprocess_010: null argument");
   X3D2C_REQUIRE(p->bc_case == 10, "x3d2c_fft_postprocess_010: the solver was not created with x3d2c_poisson_create_010");
   P010 q;
@@ -299,12 +307,14 @@ int x3d2c_fft_postprocess_010(x3d2c_ctx* ctx, x3d2c_poisson* p) {
 }
 
 int x3d2c_enforce_periodicity_y(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_out, const double* f_in) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && p && f_out && f_in && f_out != f_in, "x3d2c_enforce_periodicity_y: bad argument");
   periodicity_y_kernel<true><<<1184, 256, 0, ctx->stream>>>(f_out, f_in, p->nx, p->ny, p->nz_loc, ctx->nx_pad, ctx->ny_pad);
   X3D2C_CHECK_LAUNCH(ctx);
   return X3D2C_OK;
 }
 int x3d2c_undo_periodicity_y(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_out, const double* f_in) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && p && f_out && f_in && f_out != f_in, "x3d2c_undo_periodicity_y: bad argument");
   periodicity_y_kernel<false><<<1184, 256, 0, ctx->stream>>>(f_out, f_in, p->nx, p->ny, p->nz_loc, ctx->nx_pad, ctx->ny_pad);
   X3D2C_CHECK_LAUNCH(ctx);

@@ -127,6 +127,7 @@ using namespace x3d2c;
 extern "C" {
 
 int x3d2c_reorder(x3d2c_ctx* ctx, int rdr, double* dst, const double* src) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && dst && src, "x3d2c_reorder: null argument");
   X3D2C_REQUIRE(dst != src, "x3d2c_reorder: in-place reorder is not supported");
   const int from = rdr / 10, to = rdr % 10;  // src/common.f90:23-26,44-53
@@ -136,6 +137,7 @@ int x3d2c_reorder(x3d2c_ctx* ctx, int rdr, double* dst, const double* src) {
 }
 
 int x3d2c_reorder_x2yz(x3d2c_ctx* ctx, double* dst_y, double* dst_z, const double* src) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && dst_y && dst_z && src, "x3d2c_reorder_x2yz: null argument");
   X3D2C_REQUIRE(dst_y != src && dst_z != src && dst_y != dst_z, "x3d2c_reorder_x2yz: fields must be distinct");
   X3D2C_REQUIRE(ctx->nz_pad <= 65535, "x3d2c_reorder_x2yz: nz exceeds the grid limit");
@@ -147,11 +149,13 @@ int x3d2c_reorder_x2yz(x3d2c_ctx* ctx, double* dst_y, double* dst_z, const doubl
 }
 
 int x3d2c_sum_yintox(x3d2c_ctx* ctx, double* u, const double* u_y) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && u && u_y, "x3d2c_sum_yintox: null argument");
   return launch_reorder(ctx, X3D2C_DIR_Y, X3D2C_DIR_X, u, u_y, true);
 }
 
 int x3d2c_sum_yzintox(x3d2c_ctx* ctx, double* u, const double* u_y, const double* u_z) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && u && u_y && u_z, "x3d2c_sum_yzintox: null argument");
   X3D2C_REQUIRE(ctx->nz_pad <= 65535, "x3d2c_sum_yzintox: nz exceeds the grid limit");
   const dim3 grid(ctx->nx_pad / SZ, ctx->ny_pad / SZ, ctx->nz_pad), block(32, 8);
@@ -162,6 +166,7 @@ int x3d2c_sum_yzintox(x3d2c_ctx* ctx, double* u, const double* u_y, const double
 }
 
 int x3d2c_sum_zintox(x3d2c_ctx* ctx, double* u, const double* u_z) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && u && u_z, "x3d2c_sum_zintox: null argument");
   return launch_reorder(ctx, X3D2C_DIR_Z, X3D2C_DIR_X, u, u_z, true);
 }

@@ -90,6 +90,7 @@ extern "C" {
 
 int x3d2c_tds_solve_r(x3d2c_ctx* ctx, int dir, double* out, const double* in, const x3d2c_tdsops* op, int rdr_in,
                       int rdr_out) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && out && in && op, "x3d2c_tds_solve_r: null argument");
   X3D2C_REQUIRE(dir >= 1 && dir <= 3, "x3d2c_tds_solve_r: dir must be DIR_X/Y/Z");
   X3D2C_REQUIRE(out != in, "x3d2c_tds_solve_r: out and in must be different fields");
@@ -98,6 +99,7 @@ int x3d2c_tds_solve_r(x3d2c_ctx* ctx, int dir, double* out, const double* in, co
 
 int x3d2c_tds_solve_sum_r(x3d2c_ctx* ctx, int dir, double* out, const double* in_a, const x3d2c_tdsops* op_a,
                           const double* in_b, const x3d2c_tdsops* op_b, int rdr_in, int rdr_out) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && out && in_a && in_b && op_a && op_b, "x3d2c_tds_solve_sum_r: null argument");
   X3D2C_REQUIRE(dir >= 1 && dir <= 3, "x3d2c_tds_solve_sum_r: dir must be DIR_X/Y/Z");
   X3D2C_REQUIRE(out != in_a && out != in_b, "x3d2c_tds_solve_sum_r: out must differ from the inputs");
@@ -106,6 +108,7 @@ int x3d2c_tds_solve_sum_r(x3d2c_ctx* ctx, int dir, double* out, const double* in
 
 int x3d2c_tds_solve_dual_r(x3d2c_ctx* ctx, int dir, double* out_a, double* out_b, const double* in,
                            const x3d2c_tdsops* op_a, const x3d2c_tdsops* op_b, int rdr_in, int rdr_out) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && out_a && out_b && in && op_a && op_b, "x3d2c_tds_solve_dual_r: null argument");
   X3D2C_REQUIRE(dir >= 1 && dir <= 3, "x3d2c_tds_solve_dual_r: dir must be DIR_X/Y/Z");
   X3D2C_REQUIRE(out_a != in && out_b != in && out_a != out_b, "x3d2c_tds_solve_dual_r: fields must be distinct");

@@ -395,6 +395,8 @@ HaloBufs carve(x3d2c_ctx* ctx) {
   }
   h.rsend = p; p += 18 * row;
   h.rrecv = p; p += 18 * row;
+  static_assert(3 * 4 * 4 + 2 * 18 == x3d2c::kHaloRowsRef, "carve() and kHaloRowsRef disagree");
+  if ((size_t)(p - ctx->halo) > ctx->halo_doubles) { std::fprintf(stderr, "x3d2c: halo buffer overflow in carve()\n"); std::abort(); }
   h.row = row;
   return h;
 }
@@ -413,6 +415,7 @@ void trace_path(const char* op, int dir, int P, int family) {
 extern "C" {
 
 int x3d2c_tds_solve(x3d2c_ctx* ctx, int dir, double* du, const double* u, const x3d2c_tdsops* ops) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && du && u && ops, "x3d2c_tds_solve: null argument");
   X3D2C_REQUIRE(dir >= 1 && dir <= 3, "x3d2c_tds_solve: dir must be DIR_X/Y/Z");
   X3D2C_REQUIRE(du != u, "x3d2c_tds_solve: du and u must be different fields");
@@ -465,6 +468,7 @@ int x3d2c_tds_solve(x3d2c_ctx* ctx, int dir, double* du, const double* u, const 
 
 int x3d2c_tds_solve_sum(x3d2c_ctx* ctx, int dir, double* out, const double* in_a, const x3d2c_tdsops* op_a,
                         const double* in_b, const x3d2c_tdsops* op_b) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && out && in_a && in_b && op_a && op_b, "x3d2c_tds_solve_sum: null argument");
   X3D2C_REQUIRE(dir >= 1 && dir <= 3, "x3d2c_tds_solve_sum: dir must be DIR_X/Y/Z");
   X3D2C_REQUIRE(out != in_a && out != in_b, "x3d2c_tds_solve_sum: out must differ from the inputs");
@@ -484,6 +488,7 @@ int x3d2c_tds_solve_sum(x3d2c_ctx* ctx, int dir, double* out, const double* in_a
 
 int x3d2c_tds_solve_dual(x3d2c_ctx* ctx, int dir, double* out_a, double* out_b, const double* in,
                          const x3d2c_tdsops* op_a, const x3d2c_tdsops* op_b) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && out_a && out_b && in && op_a && op_b, "x3d2c_tds_solve_dual: null argument");
   X3D2C_REQUIRE(dir >= 1 && dir <= 3, "x3d2c_tds_solve_dual: dir must be DIR_X/Y/Z");
   X3D2C_REQUIRE(out_a != in && out_b != in && out_a != out_b, "x3d2c_tds_solve_dual: fields must be distinct");
@@ -500,6 +505,7 @@ int x3d2c_tds_solve_dual(x3d2c_ctx* ctx, int dir, double* out_a, double* out_b, 
 }
 
 int x3d2c_tds_solve_axpy(x3d2c_ctx* ctx, int dir, double* y, double a, const double* in, const x3d2c_tdsops* op) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && y && in && op, "x3d2c_tds_solve_axpy: null argument");
   X3D2C_REQUIRE(dir >= 1 && dir <= 3, "x3d2c_tds_solve_axpy: dir must be DIR_X/Y/Z");
   X3D2C_REQUIRE(y != in, "x3d2c_tds_solve_axpy: y and in must be different fields");
@@ -519,6 +525,7 @@ int x3d2c_tds_solve_axpy(x3d2c_ctx* ctx, int dir, double* y, double a, const dou
 int x3d2c_transeq(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, const double* u, const double* v,
                   const double* w, double nu, const x3d2c_tdsops* der1st, const x3d2c_tdsops* der1st_sym,
                   const x3d2c_tdsops* der2nd, const x3d2c_tdsops* der2nd_sym) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && du && dv && dw && u && v && w && der1st && der1st_sym && der2nd && der2nd_sym,
                 "x3d2c_transeq: null argument");
   X3D2C_REQUIRE(dir >= 1 && dir <= 3, "x3d2c_transeq: dir must be DIR_X/Y/Z");
@@ -598,6 +605,7 @@ int x3d2c_transeq(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, c
 int x3d2c_transeq_species(x3d2c_ctx* ctx, int dir, double* dspec, const double* uvw, const double* spec, double nu,
                           const x3d2c_tdsops* der1st, const x3d2c_tdsops* der1st_sym, const x3d2c_tdsops* der2nd,
                           int sync) {
+  X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && dspec && uvw && spec && der1st && der1st_sym && der2nd, "x3d2c_transeq_species: null argument");
   X3D2C_REQUIRE(dir >= 1 && dir <= 3, "x3d2c_transeq_species: dir must be DIR_X/Y/Z");
   X3D2C_REQUIRE(der1st->n_rhs == der1st->n_tds && der2nd->n_rhs == der2nd->n_tds && der1st->n_tds == der2nd->n_tds &&

@@ -121,11 +121,11 @@ constexpr size_t kSmemMax = 75 * 1024;  // three CTAs per SM
 
 template <int L, unsigned M, bool DIST>
 int launch_tds(x3d2c_ctx* ctx, const TdsParams& p, int threads, size_t smem) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[x3d2c::kMaxDevices] = {};  // per device: function attributes belong to the device's context
+  if (!attr_set[ctx->device]) {
     X3D2C_CHECK_CUDA(cudaFuncSetAttribute(tds_m3_kernel<L, M, DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)kSmemMax));
-    attr_set = true;
+    attr_set[ctx->device] = true;
   }
   int grid = num_sms(ctx) * 3;
   if (grid > p.g.tiles) grid = p.g.tiles;

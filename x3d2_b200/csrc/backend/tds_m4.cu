@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) tds_m4_kernel(const __grid_const
 template <int L, int NT, unsigned M, int MODE, bool DIST>
 int launch(x3d2c_ctx* ctx, const TdsParams4& p) {
   constexpr size_t smem = Shape<L, NT, MODE>::smem(DIST);
-  static int per_sm = 0;  // resident CTAs per SM (registers and shared memory), queried once
+  static int per_sm_dev[x3d2c::kMaxDevices] = {};  // resident CTAs per SM (registers and shared memory), once per device
+  int& per_sm = per_sm_dev[ctx->device];
   if (!per_sm) {
     X3D2C_CHECK_CUDA(cudaFuncSetAttribute(tds_m4_kernel<L, NT, M, MODE, DIST>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -138,11 +138,11 @@ size_t smem_bytes(int nseg, int L, int nr, bool split) {
 
 template <int L, unsigned M, int MODE, bool DIST>
 int launch(x3d2c_ctx* ctx, const PairParams& p, int threads, size_t smem) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[x3d2c::kMaxDevices] = {};  // per device: function attributes belong to the device's context
+  if (!attr_set[ctx->device]) {
     X3D2C_CHECK_CUDA(cudaFuncSetAttribute(tds_pair_kernel<L, M, MODE, DIST>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemSm - 1024)));
-    attr_set = true;
+    attr_set[ctx->device] = true;
   }
   int per_sm = (int)((kSmemSm + 1024) / (smem + 1024));
   if (per_sm > 256 / threads) per_sm = 256 / threads;  // register file

@@ -159,11 +159,11 @@ constexpr size_t kSmemSm = 227 * 1024;  // shared memory of one SM available to 
 
 template <int L, unsigned M1, unsigned M2, bool DIST>
 int launch(x3d2c_ctx* ctx, const Params& p, int threads, size_t smem) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[x3d2c::kMaxDevices] = {};  // per device: function attributes belong to the device's context
+  if (!attr_set[ctx->device]) {
     X3D2C_CHECK_CUDA(cudaFuncSetAttribute(transeq_m3_kernel<L, M1, M2, DIST>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemSm - 1024)));
-    attr_set = true;
+    attr_set[ctx->device] = true;
   }
   int per_sm = (int)((kSmemSm + 1024) / (smem + 1024));  // CTAs that fit one SM's shared memory ...
   if (per_sm > kMaxThreads / threads) per_sm = kMaxThreads / threads;  // ... and register file

@@ -218,7 +218,8 @@ template <int L, int NT, bool DIST>
 int launch4(x3d2c_ctx* ctx, const Params4& p) {
   constexpr size_t smem = sizeof(double) * (6 * S * NT + 6 * NT + 2 +
                                             (DIST ? Stage<L, NT>::doubles + 2 * 2 * NS * EXP_ROWS * L : 0));
-  static int per_sm = 0;
+  static int per_sm_dev[x3d2c::kMaxDevices] = {};  // once per device
+  int& per_sm = per_sm_dev[ctx->device];
   if (!per_sm) {
     X3D2C_CHECK_CUDA(cudaFuncSetAttribute(transeq_m4_kernel<L, NT, DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));

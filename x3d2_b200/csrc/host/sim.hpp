@@ -609,6 +609,14 @@ class Sim {
     bc.sz = SZ; bc.rank = mesh.nrank; bc.nproc = mesh.nproc; bc.device = cfg.device; bc.flags = cfg.flags & 0xff;
     bc.nccl_unique_id = cfg.nccl_unique_id;
     X3D2H_CALL(x3d2c_create(&bc, &ctx));
+    try {
+      construct();
+    } catch (...) {  // a constructor that throws does not run the destructor: release the context, fields and handles
+      release();
+      throw;
+    }
+  }
+  void construct() {
     allocator.init(ctx);
     backend.ctx = ctx; backend.mesh = &mesh; backend.allocator = &allocator;
     // solver init (solver.f90:111-212)
@@ -621,7 +629,8 @@ class Sim {
     allocate_tdsops(xdirps); allocate_tdsops(ydirps); allocate_tdsops(zdirps);
     init_poisson_fft();
   }
-  ~Sim() {
+  ~Sim() { release(); }
+  void release() {
     if (!ctx) return;
     x3d2c_sync(ctx);
     if (backend.poisson) x3d2c_poisson_destroy(ctx, backend.poisson);
@@ -631,6 +640,7 @@ class Sim {
         if (o->h) x3d2c_tdsops_destroy(ctx, o->h);
     allocator.destroy();
     x3d2c_destroy(ctx);
+    ctx = nullptr;
   }
 
   // solver.f90:214-289
