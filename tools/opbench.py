@@ -1,6 +1,8 @@
 """Per-operator device timing (CUDA events on the backend's stream) against the algorithmic bytes of SURVEY.md §8d.
 
-usage: python tools/opbench.py [N | nx,ny,nz] [--strict] [--ops=transeq_z,poisson,...]
+usage: python tools/opbench.py [N | nx,ny,nz] [--strict] [--channel] [--ops=transeq_z,poisson,...]
+       --channel: walls in y (Dirichlet), y stretched 'top-bottom' with beta = 0.259065151, L = (4, 2, 2), Re = 4200
+                  (examples/channel/input.x3d; BASELINE.json configs[4] is 512,257,512)
        python -m torch.distributed.run --nnodes=1 --nproc-per-node P --master-addr 127.0.0.1 tools/opbench.py [N]
            (P ranks, z-slabs of N^3 points each: the z operators run the rank-split kernels + NCCL exchanges)
 """
@@ -55,9 +57,13 @@ def main():
         dist.broadcast_object_list(buf, src=0)
         sim = X.Sim((grid[0], grid[1], grid[2] * world), nproc_dir=(1, 1, world), rank=rank, nproc=world, device=local, strict=strict,
                     nccl_unique_id=buf[0])
+    elif "--channel" in sys.argv:
+        sim = X.Sim(tuple(grid), strict=strict, L=(4.0, 2.0, 2.0), bcs=((0, 0), (2, 2), (0, 0)), Re=4200.0, dt=0.005,
+                    stretching=("uniform", "top-bottom", "uniform"), beta=(1.0, 0.259065151, 1.0))
     else:
         sim = X.Sim(tuple(grid), strict=strict)
-    sim.init_tgv()
+    if "--channel" not in sys.argv:
+        sim.init_tgv()
     stream = torch.cuda.ExternalStream(sim.stream())
     npts = grid[0] * grid[1] * grid[2]
     rows = []

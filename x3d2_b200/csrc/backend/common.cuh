@@ -94,7 +94,12 @@ struct x3d2c_tdsops {
   double* d_block = nullptr;  // one allocation holding all seven arrays
   std::vector<double> h_fw, h_bw, h_sa, h_sc, h_af, h_stretch, h_stretch_correct;
   // fast-path tables (m3): generic first-order recurrences z_j = A_j z_{j-1} + B_j r_j, y_j = C_j y_{j+1} + E_j z_j
+  // generic segment-parallel tables (tds_g.cu): per-row recurrences z_j = A_j z_{j-1} + B_j r_j, y_j = C_j y_{j+1} + E_j z_j,
+  // carry weights, substitution vectors; built on first use. gen_state: 0 not built, 1 ready, -1 not eligible
   double* d_m3 = nullptr;
+  double* d_stc = nullptr;  // stretch_correct padded to the processed rows (transeq)
+  int gen_state = 0, gen_nseg = 0;
+  std::vector<double> gen_scalars;
   int has_stretch = 0, has_stretch_correct = 0;
   unsigned tap_mask = 0x1ff;  // non-zero bulk taps
 };
@@ -153,6 +158,11 @@ int launch_reorder(x3d2c_ctx* ctx, int dir_from, int dir_to, double* dst, const 
 int ensure_scratch(x3d2c_ctx* ctx, int count = 2);
 int ensure_scratch_slot(x3d2c_ctx* ctx, int i);
 int get_dims_dataloc(const x3d2c_ctx* ctx, int data_loc, int dims[3], bool global);
+// generic segment-parallel kernels for single-rank directions, any operator (tds_g.cu); EUNSUPPORTED -> tds_m1.cu
+int tds_g(x3d2c_ctx* ctx, int dir, double* du, const double* u, const x3d2c_tdsops* ops);
+int transeq_g(x3d2c_ctx* ctx, int dir, double* const out[3], const double* const in[3], double nu,
+              const x3d2c_tdsops* der1st, const x3d2c_tdsops* der1st_sym, const x3d2c_tdsops* der2nd,
+              const x3d2c_tdsops* der2nd_sym);
 // shared part of x3d2c_poisson_create / x3d2c_poisson_create_010 (poisson.cu)
 int poisson_create_common(x3d2c_ctx* ctx, int bc_case, const double* waves, const double* ax, const double* bx,
                           const double* ay, const double* by, const double* az, const double* bz, x3d2c_poisson** out);

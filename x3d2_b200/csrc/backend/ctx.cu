@@ -219,6 +219,7 @@ int x3d2c_tdsops_destroy(x3d2c_ctx* ctx, x3d2c_tdsops* ops) {
   X3D2C_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ops->d_block) cudaFree(ops->d_block);
   if (ops->d_m3) cudaFree(ops->d_m3);
+  if (ops->d_stc) cudaFree(ops->d_stc);
   delete ops;
   return X3D2C_OK;
 }

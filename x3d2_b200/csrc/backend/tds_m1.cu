@@ -408,7 +408,9 @@ void trace_path(const char* op, int dir, int P, int family) {
   if (on < 0) on = std::getenv("X3D2C_TRACE") ? 1 : 0;
   if (on)
     std::fprintf(stderr, "[x3d2c] %s dir=%d ranks=%d -> %s\n", op, dir, P,
-                 family == 4 ? "m4 (tma tiles)" : (family == 3 ? "m3 (cp.async tiles)" : "m1 (reference order)"));
+                 family == 4 ? "m4 (tma tiles)"
+                             : (family == 3 ? "m3 (cp.async tiles)"
+                                            : (family == 5 ? "g (generic segment-parallel)" : "m1 (reference order)")));
 }
 }  // namespace
 
@@ -426,7 +428,9 @@ int x3d2c_tds_solve(x3d2c_ctx* ctx, int dir, double* du, const double* u, const 
     int rc = tds_m4(ctx, dir, 0, du, nullptr, u, nullptr, ops, ops, 1.0, dir, dir);
     const bool tma = rc != X3D2C_EUNSUPPORTED;
     if (!tma) rc = tds_solve_m3(ctx, dir, du, u, ops);
-    trace_path("tds_solve", dir, P, tma ? 4 : (rc != X3D2C_EUNSUPPORTED ? 3 : 1));
+    bool gen = false;
+    if (rc == X3D2C_EUNSUPPORTED) { rc = tds_g(ctx, dir, du, u, ops); gen = rc != X3D2C_EUNSUPPORTED; }
+    trace_path("tds_solve", dir, P, tma ? 4 : (gen ? 5 : (rc != X3D2C_EUNSUPPORTED ? 3 : 1)));
     if (rc != X3D2C_EUNSUPPORTED) return rc;
   }
   const dim3 block(128), grid((G + 3) / 4);
@@ -537,8 +541,10 @@ int x3d2c_transeq(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, c
     int rc = transeq_m4(ctx, dir, du, dv, dw, u, v, w, nu, der1st, der1st_sym, der2nd, der2nd_sym);  // TMA tiles
     const bool tma = rc != X3D2C_EUNSUPPORTED;
     if (!tma) rc = transeq_m3(ctx, dir, du, dv, dw, u, v, w, nu, der1st, der1st_sym, der2nd, der2nd_sym);
-    trace_path("transeq", dir, P, tma ? 4 : (rc != X3D2C_EUNSUPPORTED ? 3 : 1));
-    if (rc != X3D2C_EUNSUPPORTED) return rc;
+    if (rc != X3D2C_EUNSUPPORTED) {
+      trace_path("transeq", dir, P, tma ? 4 : 3);
+      return rc;
+    }
   }
   // argument permutation of omp/backend.f90:154,168,182: component 0 is the line-aligned velocity
   double* out[3];
@@ -546,6 +552,14 @@ int x3d2c_transeq(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, c
   if (dir == X3D2C_DIR_X) { out[0] = du; out[1] = dv; out[2] = dw; in[0] = u; in[1] = v; in[2] = w; }
   else if (dir == X3D2C_DIR_Y) { out[0] = dv; out[1] = du; out[2] = dw; in[0] = v; in[1] = u; in[2] = w; }
   else { out[0] = dw; out[1] = du; out[2] = dv; in[0] = w; in[1] = u; in[2] = v; }
+  if (!ctx->strict) {  // walls, stretched meshes, ragged lines: generic segment-parallel kernel (tds_g.cu)
+    int rc = transeq_g(ctx, dir, out, in, nu, der1st, der1st_sym, der2nd, der2nd_sym);
+    if (rc != X3D2C_EUNSUPPORTED) {
+      trace_path("transeq", dir, P, 5);
+      return rc;
+    }
+  }
+  trace_path("transeq", dir, P, 1);
   int rc = ensure_scratch(ctx);
   if (rc) return rc;
   const int n_pad = ctx->n_pad(dir), G = ctx->n_groups[dir];

@@ -219,7 +219,10 @@ int dispatch_mask(x3d2c_ctx* ctx, const TdsParams4& p, unsigned mask) {
 }
 
 // Tiles of 256 threads: the copy-bound tds kernels want rows of at least 64 bytes (L >= 8) where the line allows it
-bool tds_shape(int n, int* L, int* NT) {
+bool tds_shape(int n, int mode, int* L, int* NT) {
+  // 1024-point lines: a single solve has room for 64-byte rows (one CTA of 512 threads, two 64 KB tile buffers); the
+  // two-tile modes keep 32-byte rows
+  if (n == 1024 && mode == SINGLE) { *L = 8; *NT = 512; return true; }
   switch (n) {
     case 64: *L = 32; *NT = 128; return true;
     case 128: *L = 32; *NT = 256; return true;
@@ -234,6 +237,10 @@ bool tds_shape(int n, int* L, int* NT) {
 template <int MODE, bool DIST>
 int dispatch_shape(x3d2c_ctx* ctx, const TdsParams4& p, int L, int NT, unsigned mask) {
   if (NT == 128) return dispatch_mask<32, 128, MODE, DIST>(ctx, p, mask);
+  if (NT == 512) {
+    if (MODE == SINGLE) return dispatch_mask<8, 512, SINGLE, DIST>(ctx, p, mask);
+    return X3D2C_EUNSUPPORTED;
+  }
   switch (L) {
     case 4: return dispatch_mask<4, 256, MODE, DIST>(ctx, p, mask);
     case 8: return dispatch_mask<8, 256, MODE, DIST>(ctx, p, mask);
@@ -267,7 +274,7 @@ int tds_m4(x3d2c_ctx* ctx, int dir, int mode, double* out_a, double* out_b, cons
   const bool split = ctx->cfg.nproc_dir[dir - 1] > 1 || ctx->force_dist;
   if (split && (lay_in != dir || !dist_supported(ctx, dir, n))) return X3D2C_EUNSUPPORTED;
   int L = 0, NT = 0;
-  if (!tds_shape(n, &L, &NT)) return X3D2C_EUNSUPPORTED;
+  if (!tds_shape(n, mode, &L, &NT)) return X3D2C_EUNSUPPORTED;
   const bool two_ops = mode == SUM || mode == DUAL;
   if (two_ops && (tb->n_tds != n || tb->n_rhs != ta->n_rhs)) return X3D2C_EUNSUPPORTED;
   TdsParams4 p{};
