@@ -588,8 +588,13 @@ int tds_g(x3d2c_ctx* ctx, int dir, double* du, const double* u, const x3d2c_tdso
 int transeq_g(x3d2c_ctx* ctx, int dir, double* const out[3], const double* const in[3], double nu,
               const x3d2c_tdsops* der1st, const x3d2c_tdsops* der1st_sym, const x3d2c_tdsops* der2nd,
               const x3d2c_tdsops* der2nd_sym) {
+  // Measured on a B200 (profiles/r02_opbench_channel_512x257x512.txt): with 17 segments per 257-point line, 255
+  // registers per thread and 24 table look-ups per row this kernel keeps only 4-5 warps per SM busy and needs 14.8 ms per
+  // call at 512 x 257 x 512, the one-thread-per-line kernels 7.5 ms. It is therefore opt-in (X3D2C_TRANSEQ_GENERIC=1;
+  // tests run it for parity); tds_solve uses its generic kernel by default (0.59 ms against 0.66 ms).
+  static const bool enabled = std::getenv("X3D2C_TRANSEQ_GENERIC") != nullptr;
   static const bool disabled = std::getenv("X3D2C_NO_GENERIC") != nullptr;
-  if (disabled || ctx->strict || ctx->cfg.nproc_dir[dir - 1] > 1 || ctx->force_dist) return X3D2C_EUNSUPPORTED;
+  if (!enabled || disabled || ctx->strict || ctx->cfg.nproc_dir[dir - 1] > 1 || ctx->force_dist) return X3D2C_EUNSUPPORTED;
   TransG p{};
   GenHost h, h2;
   // component 0: (der1st, der1st_sym, der2nd); components 1, 2: (der1st_sym, der1st, der2nd_sym)  omp/backend.f90:246-260

@@ -671,6 +671,7 @@ class Sim {
     const bool p010 = mesh.periodic_BC[0] && !mesh.periodic_BC[1] && mesh.periodic_BC[2];
     // other cases (and stretching in x or z, poisson_fft.f90:166-169): the solver has no FFT Poisson, poisson_fft() fails
     if ((!p000 && !(p010 && mesh.nproc == 1)) || mesh.stretched[0] || mesh.stretched[2]) return;
+    if (p010 && (mesh.global_cell_dims[1] % 2 || mesh.global_cell_dims[1] < 8)) return;  // the paired-mode step needs an even count
     int n_spec[3], n_sp_st[3];
     X3D2H_CALL(x3d2c_poisson_spec_layout(ctx, n_spec, n_sp_st));
     pfft.base_init(mesh, xdirps, ydirps, zdirps, n_spec, n_sp_st);
