@@ -22,14 +22,27 @@ import x3d2_b200 as X
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
-    args = [int(a) for a in sys.argv[1:]]
+    args = [int(a) for a in sys.argv[1:] if not a.startswith("--")]
     dims = tuple(args[:3]) if len(args) >= 3 else (64, 64, 64 * world)
     steps = args[3] if len(args) >= 4 else 2
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     c, _ = X.load()
     ok = True
-    for strict in (False, True):
+    modes = (False,) if "--fast-only" in sys.argv else (False, True)
+    rng = np.random.default_rng(7)
+    gf = [rng.standard_normal((dims[2], dims[1], dims[0])) for _ in range(3)]
+    exp = rmon = None
+    if rank == 0:  # the oracle's P-rank emulation, once for both modes
+        import _oracle as O
+        ref = O.World(dims, nproc_dir=(1, 1, world))
+        ref.init_tgv()
+        ref.step(steps)
+        exp = list(ref.get_uvw()) + [ref.tds_solve(3, "der1st", gf[0])] + list(ref.transeq_dir(3, *gf)) + \
+              [ref.divergence(*gf), ref.poisson(gf[0] - gf[0].mean())]
+        rmon = ref.monitor()
+        del ref
+    for strict in modes:
         buf = [None]  # one ncclUniqueId per communicator
         if rank == 0:
             raw = ctypes.create_string_buffer(128)
@@ -43,8 +56,6 @@ def main():
         u, v, w = sim.get_uvw()
         mon = sim.monitor()
         # single operators on seeded data (each rank generates the global field and takes its slab)
-        rng = np.random.default_rng(7)
-        gf = [rng.standard_normal((dims[2], dims[1], dims[0])) for _ in range(3)]
         nzl = dims[2] // world
         sl = slice(rank * nzl, (rank + 1) * nzl)
         loc = [g[sl] for g in gf]
@@ -56,19 +67,19 @@ def main():
         gathered = [None] * world
         dist.all_gather_object(gathered, parts)
         if rank == 0:
-            import _oracle as O
-            ref = O.World(dims, nproc_dir=(1, 1, world))
-            ref.init_tgv()
-            ref.step(steps)
-            exp = list(ref.get_uvw()) + [ref.tds_solve(3, "der1st", gf[0])] + list(ref.transeq_dir(3, *gf)) + \
-                  [ref.divergence(*gf), ref.poisson(gf[0] - gf[0].mean())]
             names = ["u", "v", "w", "tds_z", "transeq_z_du", "transeq_z_dv", "transeq_z_dw", "div", "poisson"]
-            rmon = ref.monitor()
+            # velocities and the three transeq outputs are compared relative to the scale of the VECTOR (north_star:
+            # "velocity fields within 1e-12 relative"): w of the Taylor-Green vortex starts at zero and stays orders of
+            # magnitude below u, v, so its own maximum is not a meaningful scale; the per-field ratio is printed too
+            scale = {0: max(np.abs(exp[i]).max() for i in (0, 1, 2)), 4: max(np.abs(exp[i]).max() for i in (4, 5, 6))}
             for i, name in enumerate(names):
                 got = np.concatenate([g[i] for g in gathered], axis=0)
-                err = np.abs(got - exp[i]).max() / np.abs(exp[i]).max()
+                own = np.abs(exp[i]).max()
+                sc = scale[0] if i < 3 else (scale[4] if 4 <= i <= 6 else own)
+                err = np.abs(got - exp[i]).max() / sc
                 exact = np.array_equal(got, exp[i])
-                print(f"[mgpu P={world} strict={strict}] {name:14s} rel err {err:.3e} bit-exact={exact}")
+                print(f"[mgpu P={world} strict={strict}] {name:14s} rel err {err:.3e} (vs own max {np.abs(got - exp[i]).max() / own:.3e}) "
+                      f"bit-exact={exact}", flush=True)
                 ok &= err < 1e-12
             for k in ("enstrophy", "ke"):
                 e = abs(mon[k] - rmon[k]) / rmon[k]

@@ -73,7 +73,10 @@ struct NcclApi;  // dlopen'ed entry points (nccl.cu)
 // (m3_common.cuh: kDistRows, checked there by a static_assert)
 constexpr int kHaloRowsRef = 3 * 4 * 4 + 2 * 18;
 constexpr int kHaloRowsDist = 4 * (3 * 4) + 4 * (9 * 3);
-constexpr int kHaloRows = kHaloRowsDist > kHaloRowsRef ? kHaloRowsDist : kHaloRowsRef;
+// + a second set of the RECEIVE buffers of the rank-split path (2 x 12 halo rows, 2 x 27 carry rows): with peer stores the
+// neighbours write the next operator's rows while this rank still reads the current ones (m3_edge.cu)
+constexpr int kHaloRowsRecv2 = 2 * (3 * 4) + 2 * (9 * 3);
+constexpr int kHaloRows = (kHaloRowsDist > kHaloRowsRef ? kHaloRowsDist : kHaloRowsRef) + kHaloRowsRecv2;
 
 constexpr int kMaxDevices = 64;  // per-device caches of launch attributes / occupancy are indexed by the device ordinal
 
@@ -126,6 +129,13 @@ struct x3d2c_ctx {
   // multi-rank
   void* nccl_comm = nullptr;
   x3d2c::NcclApi* nccl = nullptr;
+  // neighbours' exchange buffers mapped with CUDA IPC: halo and carry rows are stored straight into them by the pack /
+  // edge kernels and announced with flags (m3_edge.cu); the flags live behind the halo rows in the same allocation
+  bool halo_p2p = false;
+  double* peer_halo[8] = {nullptr};
+  unsigned long long* halo_flags = nullptr;
+  unsigned long long* peer_halo_flags[8] = {nullptr};
+  unsigned long long edge_epoch[4] = {0, 0, 0, 0};  // [dir]: number of rank-split exchanges so far
 
   int n_pad(int dir) const { return dir == X3D2C_DIR_X ? nx_pad : (dir == X3D2C_DIR_Y ? ny_pad : nz_pad); }
 };
@@ -145,6 +155,19 @@ struct x3d2c_poisson {
   cufftDoubleComplex* peerA[8] = {nullptr};
   cufftDoubleComplex* peerB[8] = {nullptr};
   double* bar_word = nullptr;  // device word of the all-reduce barriers
+  // pipelined exchange (P > 1, poisson.cu): the planes of the slab are transformed and sent chunk by chunk; the copies
+  // (DMA engines, second stream) overlap the transforms of the next chunk; ranks signal each other with flags in peer
+  // memory instead of all-reduce barriers
+  bool pipe = false;
+  int nch = 1;                                   // chunks of nz_loc / nch planes
+  cufftDoubleComplex* Cx = nullptr;              // C(j_loc, i, k): destination of the forward exchange, spectral buffer
+  cufftDoubleComplex* peerC[8] = {nullptr};
+  unsigned long long* flags = nullptr;           // behind Cx in the same allocation: [0..7] forward done by rank r,
+  unsigned long long* peerFlags[8] = {nullptr};  //   [8 + 8 r + c] backward chunk c delivered by rank r
+  unsigned long long epoch = 0;
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t ev_chunk[8] = {nullptr}, ev_z = nullptr;
+  cufftHandle plan_r2c_c = 0, plan_c2r_c = 0, plan_y_c = 0;
   // non-periodic y (poisson010.cu)
   int bc_case = 0;      // 0: 000, 10: 010
   int stretched = 0;    // 0 uniform, 1 odd / even families, 2 one family ('bottom')
@@ -158,6 +181,8 @@ int launch_reorder(x3d2c_ctx* ctx, int dir_from, int dir_to, double* dst, const 
 int ensure_scratch(x3d2c_ctx* ctx, int count = 2);
 int ensure_scratch_slot(x3d2c_ctx* ctx, int i);
 int get_dims_dataloc(const x3d2c_ctx* ctx, int data_loc, int dims[3], bool global);
+int setup_peer_halo(x3d2c_ctx* ctx);    // nccl.cu: maps the peers' exchange buffers (P > 1)
+void release_peer_halo(x3d2c_ctx* ctx);
 // generic segment-parallel kernels for single-rank directions, any operator (tds_g.cu); EUNSUPPORTED -> tds_m1.cu
 int tds_g(x3d2c_ctx* ctx, int dir, double* du, const double* u, const x3d2c_tdsops* ops);
 int transeq_g(x3d2c_ctx* ctx, int dir, double* const out[3], const double* const in[3], double nu,

@@ -84,8 +84,9 @@ int x3d2c_create(const x3d2c_config* cfg, x3d2c_ctx** out) {
   if (ctx->n_groups[3] > ng) ng = ctx->n_groups[3];
   const int halo_rows = kHaloRows;  // common.cuh: both carvings fit (checked where they are made)
   ctx->halo_doubles = (size_t)SZ * ng * halo_rows;
-  X3D2C_CHECK_CUDA(cudaMalloc(&ctx->halo, sizeof(double) * ctx->halo_doubles));
-  X3D2C_CHECK_CUDA(cudaMemsetAsync(ctx->halo, 0, sizeof(double) * ctx->halo_doubles, ctx->stream));
+  X3D2C_CHECK_CUDA(cudaMalloc(&ctx->halo, sizeof(double) * ctx->halo_doubles + 1024));  // + flags of the peer exchange
+  X3D2C_CHECK_CUDA(cudaMemsetAsync(ctx->halo, 0, sizeof(double) * ctx->halo_doubles + 1024, ctx->stream));
+  ctx->halo_flags = reinterpret_cast<unsigned long long*>(ctx->halo + ctx->halo_doubles);
   ctx->red_blocks = 1184;  // 8 CTAs per SM on 148 SMs
   X3D2C_CHECK_CUDA(cudaMalloc(&ctx->red, sizeof(double) * (2 * ctx->red_blocks + 8)));
   X3D2C_CHECK_CUDA(cudaMallocHost(&ctx->red_host, sizeof(double) * 8));
@@ -95,6 +96,7 @@ int x3d2c_create(const x3d2c_config* cfg, x3d2c_ctx** out) {
     int rc = nccl_init(ctx);
     ctx->cfg.nccl_unique_id = nullptr;
     if (rc) return rc;
+    if ((rc = setup_peer_halo(ctx))) return rc;
   }
   guard.c = nullptr;
   *out = ctx;
@@ -106,6 +108,7 @@ int x3d2c_destroy(x3d2c_ctx* ctx) {
   if (!ctx) return X3D2C_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  release_peer_halo(ctx);
   nccl_finalize(ctx);
   for (int i = 0; i < 6; ++i)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);

@@ -255,7 +255,7 @@ struct DistBufs {
 };
 constexpr int kDistRows = 4 * (3 * 4) + 4 * (9 * EXP_ROWS);  // rows of SZ*G doubles that DistBufs needs
 static_assert(kDistRows <= x3d2c::kHaloRows, "ctx->halo (ctx.cu) is too small for the rank-split exchange buffers");
-DistBufs carve_dist(x3d2c_ctx* ctx);
+DistBufs carve_dist(x3d2c_ctx* ctx, int recv_set = 0);  // recv_set 1: the second set of receive buffers
 bool dist_supported(const x3d2c_ctx* ctx, int dir, int n);
 
 // Edge kernel input: nf fields with ns / nf recurrences each (m3_edge.cu: edge_kernel);
@@ -268,6 +268,7 @@ struct EdgeParams {
   double *to_prev, *to_next;      // (SZ, EXP_ROWS, ns, G)
 };
 // packs the halos of nf fields, exchanges them, computes and exchanges the boundary carries
-int exchange_edges(x3d2c_ctx* ctx, int dir, const double* const* fields, int nf, EdgeParams& ep, const DistBufs& b);
+// (with peer stores the receive buffers alternate between two sets: `b` is updated to the set this exchange filled)
+int exchange_edges(x3d2c_ctx* ctx, int dir, const double* const* fields, int nf, EdgeParams& ep, DistBufs& b);
 
 }  // namespace m3

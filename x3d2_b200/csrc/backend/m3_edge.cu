@@ -23,6 +23,19 @@ struct PackParams {
   int n, n_pad, nf;
 };
 
+// flags of the peer exchange: slot = ((dir - 1) * 2 + phase) * 2 + side; side 0: written by the previous rank, 1: by the next
+__global__ void edge_signal_kernel(unsigned long long* to_prev, unsigned long long* to_next, const unsigned long long v) {
+  __threadfence_system();  // the stores of the preceding kernel on this stream are complete
+  *reinterpret_cast<volatile unsigned long long*>(threadIdx.x == 0 ? to_prev : to_next) = v;
+  __threadfence_system();
+}
+__global__ void edge_wait_kernel(const unsigned long long* from_prev, const unsigned long long* from_next,
+                                 const unsigned long long v) {
+  const volatile unsigned long long* f = threadIdx.x == 0 ? from_prev : from_next;
+  while (*f < v) __nanosleep(100);
+  __threadfence_system();
+}
+
 // first / last four rows of nf directional fields -> (SZ, 4, nf, G)
 __global__ void __launch_bounds__(128) halo_pack_kernel(double* __restrict__ send_s, double* __restrict__ send_e,
                                                         const __grid_constant__ PackParams p) {
@@ -163,7 +176,7 @@ bool dist_supported(const x3d2c_ctx* ctx, int dir, int n) {
   return n % S == 0 && n >= 2 * DMAX * S;
 }
 
-DistBufs carve_dist(x3d2c_ctx* ctx) {
+DistBufs carve_dist(x3d2c_ctx* ctx, int recv_set) {
   int ng = ctx->n_groups[1] > ctx->n_groups[2] ? ctx->n_groups[1] : ctx->n_groups[2];
   if (ctx->n_groups[3] > ng) ng = ctx->n_groups[3];
   const size_t row = (size_t)SZ * ng;
@@ -177,12 +190,44 @@ DistBufs carve_dist(x3d2c_ctx* ctx) {
   b.carr_to_next = p; p += 9 * EXP_ROWS * row;
   b.carr_from_prev = p; p += 9 * EXP_ROWS * row;
   b.carr_from_next = p; p += 9 * EXP_ROWS * row;
+  if (recv_set) {  // the alternate receive buffers live behind everything else (common.cuh: kHaloRowsRecv2)
+    p = ctx->halo + (size_t)(x3d2c::kHaloRows - x3d2c::kHaloRowsRecv2) * row;
+    b.halo_recv_s = p; p += 12 * row;
+    b.halo_recv_e = p; p += 12 * row;
+    b.carr_from_prev = p; p += 9 * EXP_ROWS * row;
+    b.carr_from_next = p; p += 9 * EXP_ROWS * row;
+  }
   if ((size_t)(p - ctx->halo) > ctx->halo_doubles) { std::fprintf(stderr, "x3d2c: halo buffer overflow in carve_dist()\n"); std::abort(); }
   return b;
 }
 
-int exchange_edges(x3d2c_ctx* ctx, int dir, const double* const* fields, int nf, EdgeParams& ep, const DistBufs& b) {
+int exchange_edges(x3d2c_ctx* ctx, int dir, const double* const* fields, int nf, EdgeParams& ep, DistBufs& b) {
   const int G = ctx->n_groups[dir];
+  // Peer-store path (P > 1, buffers mapped): the pack kernel writes this rank's first / last four rows straight into
+  // the neighbours' receive buffers, the edge kernel its carries; each phase is announced with one flag per neighbour
+  // and awaited with a two-thread kernel. The receive buffers alternate between two sets (see common.cuh).
+  const bool peer = ctx->halo_p2p && ctx->cfg.nproc_dir[dir - 1] > 1;
+  double *dst_halo_s = b.halo_send_s, *dst_halo_e = b.halo_send_e, *dst_to_prev = b.carr_to_prev, *dst_to_next = b.carr_to_next;
+  unsigned long long epoch = 0;
+  unsigned long long *sig_prev[2] = {nullptr, nullptr}, *sig_next[2] = {nullptr, nullptr}, *my_flag[2][2] = {{nullptr}};
+  if (peer) {
+    epoch = ++ctx->edge_epoch[dir];
+    const int set = (int)(epoch & 1);
+    b = carve_dist(ctx, set);
+    const int prev = ctx->cfg.pprev[dir - 1], next = ctx->cfg.pnext[dir - 1];
+    auto remote = [&](int r, const double* local) { return ctx->peer_halo[r] + (local - ctx->halo); };
+    dst_halo_s = remote(prev, b.halo_recv_e);   // my first rows are the previous rank's "after the line" rows
+    dst_halo_e = remote(next, b.halo_recv_s);
+    dst_to_prev = remote(prev, b.carr_from_next);
+    dst_to_next = remote(next, b.carr_from_prev);
+    for (int ph = 0; ph < 2; ++ph) {
+      const int slot = ((dir - 1) * 2 + ph) * 2;
+      sig_prev[ph] = ctx->peer_halo_flags[prev] + slot + 1;  // I am prev's next rank
+      sig_next[ph] = ctx->peer_halo_flags[next] + slot + 0;
+      my_flag[ph][0] = ctx->halo_flags + slot + 0;
+      my_flag[ph][1] = ctx->halo_flags + slot + 1;
+    }
+  }
   // X3D2C_TRACE_TIMES=1: device time of the four phases on stderr (debugging aid; synchronises)
   static const bool timing = std::getenv("X3D2C_TRACE_TIMES") != nullptr;
   cudaEvent_t ev[5];
@@ -195,19 +240,27 @@ int exchange_edges(x3d2c_ctx* ctx, int dir, const double* const* fields, int nf,
   pp.n = ep.n;
   pp.n_pad = ep.n_pad;
   pp.nf = nf;
-  halo_pack_kernel<<<dim3(G, nf), 128, 0, ctx->stream>>>(b.halo_send_s, b.halo_send_e, pp);
+  halo_pack_kernel<<<dim3(G, nf), 128, 0, ctx->stream>>>(dst_halo_s, dst_halo_e, pp);
   X3D2C_CHECK_LAUNCH(ctx);
   mark(1);
-  int rc = x3d2c::sendrecv_fields(ctx, dir, b.halo_recv_s, b.halo_recv_e, b.halo_send_s, b.halo_send_e,
-                                  (size_t)SZ * 4 * nf * G);
-  if (rc) return rc;
+  int rc = X3D2C_OK;
+  if (peer) {
+    edge_signal_kernel<<<1, 2, 0, ctx->stream>>>(sig_prev[0], sig_next[0], epoch);
+    X3D2C_CHECK_LAUNCH(ctx);
+    edge_wait_kernel<<<1, 2, 0, ctx->stream>>>(my_flag[0][0], my_flag[0][1], epoch);
+    X3D2C_CHECK_LAUNCH(ctx);
+  } else {
+    rc = x3d2c::sendrecv_fields(ctx, dir, b.halo_recv_s, b.halo_recv_e, b.halo_send_s, b.halo_send_e,
+                                (size_t)SZ * 4 * nf * G);
+    if (rc) return rc;
+  }
   mark(2);
   ep.G = G;
   ep.nf = nf;
   ep.halo_s = b.halo_recv_s;
   ep.halo_e = b.halo_recv_e;
-  ep.to_prev = b.carr_to_prev;
-  ep.to_next = b.carr_to_next;
+  ep.to_prev = dst_to_prev;
+  ep.to_next = dst_to_next;
   const dim3 eg(G, nf), eb(32, 2 * DMAX);
   if (ep.transeq)
     edge_kernel<3, true><<<eg, eb, 0, ctx->stream>>>(ep);
@@ -217,8 +270,15 @@ int exchange_edges(x3d2c_ctx* ctx, int dir, const double* const* fields, int nf,
     edge_kernel<1, false><<<eg, eb, 0, ctx->stream>>>(ep);
   X3D2C_CHECK_LAUNCH(ctx);
   mark(3);
-  rc = x3d2c::sendrecv_fields(ctx, dir, b.carr_from_prev, b.carr_from_next, b.carr_to_prev, b.carr_to_next,
-                              (size_t)SZ * EXP_ROWS * ep.ns * G);
+  if (peer) {
+    edge_signal_kernel<<<1, 2, 0, ctx->stream>>>(sig_prev[1], sig_next[1], epoch);
+    X3D2C_CHECK_LAUNCH(ctx);
+    edge_wait_kernel<<<1, 2, 0, ctx->stream>>>(my_flag[1][0], my_flag[1][1], epoch);
+    X3D2C_CHECK_LAUNCH(ctx);
+  } else {
+    rc = x3d2c::sendrecv_fields(ctx, dir, b.carr_from_prev, b.carr_from_next, b.carr_to_prev, b.carr_to_next,
+                                (size_t)SZ * EXP_ROWS * ep.ns * G);
+  }
   mark(4);
   if (timing) {
     cudaEventSynchronize(ev[4]);

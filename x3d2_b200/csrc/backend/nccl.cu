@@ -133,6 +133,59 @@ int alltoall(x3d2c_ctx* ctx, double* recv, const double* send, size_t block_doub
   return X3D2C_OK;
 }
 
+// Maps every rank's exchange buffer (ctx->halo + flags) into this process with CUDA IPC so that the halo / carry rows
+// of rank-split directions can be stored straight into the neighbours' buffers (m3_edge.cu). All ranks agree on the
+// outcome; on any failure (or X3D2C_NO_P2P) the grouped ncclSend / ncclRecv exchange stays in use.
+int setup_peer_halo(x3d2c_ctx* ctx) {
+  const int P = ctx->cfg.nproc, me = ctx->cfg.rank;
+  if (P <= 1 || P > 8 || std::getenv("X3D2C_NO_P2P") || std::getenv("X3D2C_NO_P2P_HALO")) return X3D2C_OK;
+  constexpr int HD = sizeof(cudaIpcMemHandle_t) / sizeof(double);
+  cudaIpcMemHandle_t h;
+  std::memset(&h, 0, sizeof h);
+  bool ok = cudaIpcGetMemHandle(&h, ctx->halo) == cudaSuccess;
+  if (!ok) cudaGetLastError();
+  std::vector<double> rep((size_t)HD * P), all((size_t)HD * P);
+  for (int r = 0; r < P; ++r) std::memcpy(&rep[(size_t)r * HD], &h, sizeof h);
+  double *d_send = nullptr, *d_recv = nullptr, *d_flag = nullptr;
+  X3D2C_CHECK_CUDA(cudaMalloc(&d_send, sizeof(double) * HD * P));
+  X3D2C_CHECK_CUDA(cudaMalloc(&d_recv, sizeof(double) * HD * P));
+  X3D2C_CHECK_CUDA(cudaMalloc(&d_flag, sizeof(double)));
+  X3D2C_CHECK_CUDA(cudaMemcpyAsync(d_send, rep.data(), sizeof(double) * HD * P, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = alltoall(ctx, d_recv, d_send, HD);
+  if (rc) return rc;
+  X3D2C_CHECK_CUDA(cudaMemcpyAsync(all.data(), d_recv, sizeof(double) * HD * P, cudaMemcpyDeviceToHost, ctx->stream));
+  X3D2C_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int r = 0; r < P && ok; ++r) {
+    if (r == me) { ctx->peer_halo[r] = ctx->halo; continue; }
+    cudaIpcMemHandle_t hr;
+    std::memcpy(&hr, &all[(size_t)r * HD], sizeof hr);
+    void* pa = nullptr;
+    ok = cudaIpcOpenMemHandle(&pa, hr, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    ctx->peer_halo[r] = (double*)pa;
+  }
+  const double flag = ok ? 0.0 : 1.0;
+  X3D2C_CHECK_CUDA(cudaMemcpyAsync(d_flag, &flag, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = allreduce(ctx, d_flag, 1, 0))) return rc;
+  double failed = 1.0;
+  X3D2C_CHECK_CUDA(cudaMemcpyAsync(&failed, d_flag, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  X3D2C_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->halo_p2p = failed == 0.0;
+  if (ctx->halo_p2p)
+    for (int r = 0; r < P; ++r)
+      ctx->peer_halo_flags[r] = reinterpret_cast<unsigned long long*>(ctx->peer_halo[r] + ctx->halo_doubles);
+  cudaFree(d_send); cudaFree(d_recv); cudaFree(d_flag);
+  if (std::getenv("X3D2C_TRACE"))
+    std::fprintf(stderr, "[x3d2c] rank %d halo / carry exchange: %s\n", me,
+                 ctx->halo_p2p ? "peer stores from the pack / edge kernels + flags (CUDA IPC)" : "ncclSend/Recv");
+  return X3D2C_OK;
+}
+
+void release_peer_halo(x3d2c_ctx* ctx) {
+  for (int r = 0; r < 8; ++r)
+    if (r != ctx->cfg.rank && ctx->peer_halo[r]) { cudaIpcCloseMemHandle(ctx->peer_halo[r]); ctx->peer_halo[r] = nullptr; }
+}
+
 }  // namespace x3d2c
 
 extern "C" int x3d2c_nccl_unique_id(void* out128) {

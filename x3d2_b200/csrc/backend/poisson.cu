@@ -103,6 +103,26 @@ slab_exchange_kernel(const PeerPtrs dst, const double2* __restrict__ src, const 
   }
 }
 
+// cross-rank signalling of the pipelined exchange: flags in peer memory (monotonic solve counter)
+struct FlagPtrs { unsigned long long* p[8]; };
+__global__ void set_flags_kernel(const FlagPtrs dst, const int P, const int slot, const unsigned long long v) {
+  const int r = threadIdx.x;
+  if (r < P) {
+    __threadfence_system();  // the copies issued before this kernel on the same stream are complete
+    *reinterpret_cast<volatile unsigned long long*>(dst.p[r] + slot) = v;
+    __threadfence_system();
+  }
+}
+__global__ void wait_flags_kernel(const unsigned long long* flags, const int P, const int base, const int stride,
+                                  const unsigned long long v) {
+  const int r = threadIdx.x;
+  if (r < P) {
+    const volatile unsigned long long* f = flags + base + r * stride;
+    while (*f < v) __nanosleep(200);
+    __threadfence_system();
+  }
+}
+
 struct SpecParams {
   int ny_loc, nxh, nz;  // extents of C(j_loc, i, k)
   int nx_g, ny_g, nz_g; // global cell dims
@@ -206,11 +226,13 @@ int x3d2c_poisson_spec_layout(const x3d2c_ctx* ctx, int n_spec[3], int n_sp_st[3
 // fails the NCCL send/recv exchange stays in use.
 static int setup_peer_buffers(x3d2c_ctx* ctx, x3d2c_poisson* p) {
   const int P = ctx->cfg.nproc, me = ctx->cfg.rank;
-  constexpr int HD = 2 * sizeof(cudaIpcMemHandle_t) / sizeof(double);  // doubles per rank: handles of A and B
+  constexpr int HD = 3 * sizeof(cudaIpcMemHandle_t) / sizeof(double);  // doubles per rank: handles of A, B and Cx
   static_assert(sizeof(cudaIpcMemHandle_t) % sizeof(double) == 0, "handle size");
   std::vector<double> mine(HD), all((size_t)HD * P), rep((size_t)HD * P);
-  cudaIpcMemHandle_t h[2];
+  cudaIpcMemHandle_t h[3];
+  std::memset(h, 0, sizeof h);
   bool ok = cudaIpcGetMemHandle(&h[0], p->A) == cudaSuccess && cudaIpcGetMemHandle(&h[1], p->B) == cudaSuccess;
+  if (ok && p->Cx) ok = cudaIpcGetMemHandle(&h[2], p->Cx) == cudaSuccess;
   if (!ok) cudaGetLastError();
   std::memcpy(mine.data(), h, sizeof h);
   for (int r = 0; r < P; ++r) std::memcpy(&rep[(size_t)r * HD], mine.data(), sizeof h);
@@ -225,15 +247,17 @@ static int setup_peer_buffers(x3d2c_ctx* ctx, x3d2c_poisson* p) {
   X3D2C_CHECK_CUDA(cudaMemcpyAsync(all.data(), d_recv, sizeof(double) * HD * P, cudaMemcpyDeviceToHost, ctx->stream));
   X3D2C_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
   for (int r = 0; r < P && ok; ++r) {
-    if (r == me) { p->peerA[r] = p->A; p->peerB[r] = p->B; continue; }
-    cudaIpcMemHandle_t hr[2];
+    if (r == me) { p->peerA[r] = p->A; p->peerB[r] = p->B; p->peerC[r] = p->Cx; continue; }
+    cudaIpcMemHandle_t hr[3];
     std::memcpy(hr, &all[(size_t)r * HD], sizeof hr);
-    void *pa = nullptr, *pb = nullptr;
+    void *pa = nullptr, *pb = nullptr, *pc = nullptr;
     ok = cudaIpcOpenMemHandle(&pa, hr[0], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
          cudaIpcOpenMemHandle(&pb, hr[1], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    if (ok && p->Cx) ok = cudaIpcOpenMemHandle(&pc, hr[2], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
     if (!ok) cudaGetLastError();
     p->peerA[r] = (cufftDoubleComplex*)pa;
     p->peerB[r] = (cufftDoubleComplex*)pb;
+    p->peerC[r] = (cufftDoubleComplex*)pc;
   }
   // agreement: minimum of the success flags
   const double flag = ok ? 0.0 : 1.0;
@@ -321,8 +345,34 @@ int x3d2c::poisson_create_common(x3d2c_ctx* ctx, int bc_case, const double* wave
   X3D2C_CHECK_CUFFT(cufftSetStream(p->plan_z, ctx->stream));
   p->have_plans = true;
   if (P > 1 && P <= 8 && !std::getenv("X3D2C_NO_P2P")) {
+    // pipelined exchange: a dedicated destination buffer (+ 1 KB of flags behind it), chunked plans, a copy stream
+    const int nch = p->nz_loc % 4 == 0 ? 4 : (p->nz_loc % 2 == 0 ? 2 : 1);
+    const bool want_pipe = !std::getenv("X3D2C_NO_PIPE");
+    if (want_pipe) {
+      X3D2C_CHECK_CUDA(cudaMalloc(&p->Cx, sizeof(cufftDoubleComplex) * n_spec + 1024));
+      X3D2C_CHECK_CUDA(cudaMemset(p->Cx, 0, sizeof(cufftDoubleComplex) * n_spec + 1024));
+      p->flags = reinterpret_cast<unsigned long long*>(p->Cx + n_spec);
+    }
     rc = setup_peer_buffers(ctx, p);
     if (rc) return rc;
+    if (p->p2p && want_pipe) {
+      p->nch = nch;
+      const int pl = p->nz_loc / nch;
+      for (int r = 0; r < P; ++r) p->peerFlags[r] = reinterpret_cast<unsigned long long*>(p->peerC[r] + n_spec);
+      X3D2C_CHECK_CUFFT(cufftPlanMany(&p->plan_r2c_c, 1, n_x, n_x, 1, p->nx, n_x, 1, p->nxh, CUFFT_D2Z, p->ny * pl));
+      X3D2C_CHECK_CUFFT(cufftPlanMany(&p->plan_c2r_c, 1, n_x, n_x, 1, p->nxh, n_x, 1, p->nx, CUFFT_Z2D, p->ny * pl));
+      X3D2C_CHECK_CUFFT(cufftPlanMany(&p->plan_y_c, 1, n_y, n_y, 1, p->ny, n_y, 1, p->ny, CUFFT_Z2Z, p->nxh * pl));
+      X3D2C_CHECK_CUFFT(cufftSetStream(p->plan_r2c_c, ctx->stream));
+      X3D2C_CHECK_CUFFT(cufftSetStream(p->plan_c2r_c, ctx->stream));
+      X3D2C_CHECK_CUFFT(cufftSetStream(p->plan_y_c, ctx->stream));
+      X3D2C_CHECK_CUDA(cudaStreamCreateWithFlags(&p->s2, cudaStreamNonBlocking));
+      for (int c = 0; c < nch; ++c) X3D2C_CHECK_CUDA(cudaEventCreateWithFlags(&p->ev_chunk[c], cudaEventDisableTiming));
+      X3D2C_CHECK_CUDA(cudaEventCreateWithFlags(&p->ev_z, cudaEventDisableTiming));
+      p->pipe = true;
+      if (std::getenv("X3D2C_TRACE"))
+        std::fprintf(stderr, "[x3d2c] rank %d poisson exchange pipelined: %d chunks of %d planes, DMA copies + peer flags\n",
+                     ctx->cfg.rank, nch, pl);
+    }
   }
   guard.p = nullptr;
   *out = p;
@@ -341,6 +391,14 @@ int x3d2c_poisson_destroy(x3d2c_ctx* ctx, x3d2c_poisson* p) {
     if (p->peerA[r]) cudaIpcCloseMemHandle(p->peerA[r]);
     if (p->peerB[r]) cudaIpcCloseMemHandle(p->peerB[r]);
   }
+  for (int r = 0; r < 8; ++r)
+    if (r != ctx->cfg.rank && p->peerC[r]) cudaIpcCloseMemHandle(p->peerC[r]);
+  if (p->plan_r2c_c) { cufftDestroy(p->plan_r2c_c); cufftDestroy(p->plan_c2r_c); cufftDestroy(p->plan_y_c); }
+  for (int c = 0; c < 8; ++c)
+    if (p->ev_chunk[c]) cudaEventDestroy(p->ev_chunk[c]);
+  if (p->ev_z) cudaEventDestroy(p->ev_z);
+  if (p->s2) cudaStreamDestroy(p->s2);
+  if (p->Cx) cudaFree(p->Cx);
   if (p->bar_word) cudaFree(p->bar_word);
   if (p->fac_im && p->fac_im != p->fac_re) cudaFree(p->fac_im);
   if (p->fac_re) cudaFree(p->fac_re);
@@ -352,7 +410,96 @@ int x3d2c_poisson_destroy(x3d2c_ctx* ctx, x3d2c_poisson* p) {
 }
 
 // the spectrum C(j_loc, i, k) lives in p->B, or in p->A when the peers write it there directly
-static cufftDoubleComplex* spec_buf(const x3d2c_ctx*, x3d2c_poisson* p) { return p->p2p ? p->A : p->B; }
+static cufftDoubleComplex* spec_buf(const x3d2c_ctx*, x3d2c_poisson* p) { return p->pipe ? p->Cx : (p->p2p ? p->A : p->B); }
+
+// Pipelined forward transform (P > 1): the slab is processed in chunks of planes; x transform, transpose and y
+// transform of chunk c + 1 run on the context's stream while the copy engines move chunk c to the y slabs of all
+// ranks (second stream). No all-reduce barrier: every rank raises a flag on every peer once its copies are complete.
+static int forward_pipelined(x3d2c_ctx* ctx, x3d2c_poisson* p, const double* in) {
+  const int P = ctx->cfg.nproc, me = ctx->cfg.rank, nch = p->nch, pl = p->nz_loc / nch;
+  const size_t plane_r = (size_t)p->nx * p->ny, plane_c = (size_t)p->nxh * p->ny;
+  const size_t blk = (size_t)p->nz_loc * p->nxh;  // rows (i, k_loc) of one rank block in Cx
+  const size_t row = sizeof(cufftDoubleComplex) * p->ny_loc;
+  p->epoch++;
+  FlagPtrs fp;
+  for (int r = 0; r < 8; ++r) fp.p[r] = p->peerFlags[r];
+  for (int c = 0; c < nch; ++c) {
+    cufftDoubleComplex* a = p->A + (size_t)c * pl * plane_c;
+    cufftDoubleComplex* b = p->B + (size_t)c * pl * plane_c;
+    X3D2C_CHECK_CUFFT(cufftExecD2Z(p->plan_r2c_c, const_cast<double*>(in) + (size_t)c * pl * plane_r, a));
+    ctx->launches++;
+    const dim3 grid((p->nxh + 31) / 32, (p->ny + 31) / 32, pl), block(32, 8);
+    cplx_transpose_kernel<<<grid, block, 0, ctx->stream>>>((double2*)b, (const double2*)a, p->nxh, p->ny);
+    X3D2C_CHECK_LAUNCH(ctx);
+    X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_y_c, b, b, CUFFT_FORWARD));
+    ctx->launches++;
+    X3D2C_CHECK_CUDA(cudaEventRecord(p->ev_chunk[c], ctx->stream));
+    X3D2C_CHECK_CUDA(cudaStreamWaitEvent(p->s2, p->ev_chunk[c], 0));
+    const size_t q0 = (size_t)p->nxh * pl * c;  // first row (i + nxh k_loc) of the chunk
+    for (int d = 1; d <= P; ++d) {              // start with the next rank: spreads the traffic over the links
+      const int r = (me + d) % P;
+      // B(j, q) with j in rank r's range  ->  Cx_r[(me * blk + q) * ny_loc + jl]
+      X3D2C_CHECK_CUDA(cudaMemcpy2DAsync(p->peerC[r] + ((size_t)me * blk + q0) * p->ny_loc, row,
+                                         p->B + (size_t)r * p->ny_loc + (size_t)p->ny * q0,
+                                         sizeof(cufftDoubleComplex) * p->ny, row, (size_t)p->nxh * pl,
+                                         cudaMemcpyDefault, p->s2));
+    }
+  }
+  set_flags_kernel<<<1, 32, 0, p->s2>>>(fp, P, me, p->epoch);
+  X3D2C_CHECK_LAUNCH(ctx);
+  wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(p->flags, P, 0, 1, p->epoch);
+  X3D2C_CHECK_LAUNCH(ctx);
+  X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_z, p->Cx, p->Cx, CUFFT_FORWARD));
+  ctx->launches++;
+  return X3D2C_OK;
+}
+
+// Pipelined backward transform: after the z transform the copy engines deliver the planes chunk by chunk to their
+// z slabs; a rank starts the y transform, transpose and x transform of a chunk as soon as all ranks have flagged it.
+static int backward_pipelined(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_c) {
+  const int P = ctx->cfg.nproc, me = ctx->cfg.rank, nch = p->nch, pl = p->nz_loc / nch;
+  const size_t plane_r = (size_t)p->nx * p->ny, plane_c = (size_t)p->nxh * p->ny;
+  const size_t blk = (size_t)p->nz_loc * p->nxh;
+  const size_t row = sizeof(cufftDoubleComplex) * p->ny_loc;
+  FlagPtrs fp;
+  for (int r = 0; r < 8; ++r) fp.p[r] = p->peerFlags[r];
+  X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_z, p->Cx, p->Cx, CUFFT_INVERSE));
+  ctx->launches++;
+  X3D2C_CHECK_CUDA(cudaEventRecord(p->ev_z, ctx->stream));
+  X3D2C_CHECK_CUDA(cudaStreamWaitEvent(p->s2, p->ev_z, 0));
+  for (int c = 0; c < nch; ++c) {
+    const size_t q0 = (size_t)p->nxh * pl * c;
+    for (int d = 1; d <= P; ++d) {
+      const int s = (me + d) % P;
+      // Cx[(s * blk + q) * ny_loc + jl]  ->  B_s[(me * ny_loc + jl) + ny * q]
+      X3D2C_CHECK_CUDA(cudaMemcpy2DAsync(p->peerB[s] + (size_t)me * p->ny_loc + (size_t)p->ny * q0,
+                                         sizeof(cufftDoubleComplex) * p->ny,
+                                         p->Cx + ((size_t)s * blk + q0) * p->ny_loc, row, row, (size_t)p->nxh * pl,
+                                         cudaMemcpyDefault, p->s2));
+    }
+    set_flags_kernel<<<1, 32, 0, p->s2>>>(fp, P, 8 + 8 * me + c, p->epoch);
+    X3D2C_CHECK_LAUNCH(ctx);
+  }
+  double* outp = p->compact ? p->compact : f_c;
+  for (int c = 0; c < nch; ++c) {
+    wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(p->flags, P, 8 + c, 8, p->epoch);
+    X3D2C_CHECK_LAUNCH(ctx);
+    cufftDoubleComplex* a = p->A + (size_t)c * pl * plane_c;
+    cufftDoubleComplex* b = p->B + (size_t)c * pl * plane_c;
+    X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_y_c, b, b, CUFFT_INVERSE));
+    ctx->launches++;
+    const dim3 grid((p->ny + 31) / 32, (p->nxh + 31) / 32, pl), block(32, 8);
+    cplx_transpose_kernel<<<grid, block, 0, ctx->stream>>>((double2*)a, (const double2*)b, p->ny, p->nxh);
+    X3D2C_CHECK_LAUNCH(ctx);
+    X3D2C_CHECK_CUFFT(cufftExecZ2D(p->plan_c2r_c, a, outp + (size_t)c * pl * plane_r));
+    ctx->launches++;
+  }
+  if (p->compact) {
+    pad_copy_kernel<false><<<1184, 256, 0, ctx->stream>>>(p->compact, f_c, p->nx, p->ny, p->nz_loc, ctx->nx_pad, ctx->ny_pad);
+    X3D2C_CHECK_LAUNCH(ctx);
+  }
+  return X3D2C_OK;
+}
 
 int x3d2c_fft_forward(x3d2c_ctx* ctx, x3d2c_poisson* p, const double* f_c) {
   X3D2C_ENTER(ctx);
@@ -364,6 +511,7 @@ int x3d2c_fft_forward(x3d2c_ctx* ctx, x3d2c_poisson* p, const double* f_c) {
     X3D2C_CHECK_LAUNCH(ctx);
     in = p->compact;
   }
+  if (p->pipe) return forward_pipelined(ctx, p, in);
   X3D2C_CHECK_CUFFT(cufftExecD2Z(p->plan_r2c, const_cast<double*>(in), p->A));
   ctx->launches++;
   const dim3 grid((p->nxh + 31) / 32, (p->ny + 31) / 32, p->nz_loc), block(32, 8);
@@ -422,6 +570,7 @@ int x3d2c_fft_postprocess_000(x3d2c_ctx* ctx, x3d2c_poisson* p) {
 int x3d2c_fft_backward(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_c) {
   X3D2C_ENTER(ctx);
   X3D2C_REQUIRE(ctx && p && f_c, "x3d2c_fft_backward: null argument");
+  if (p->pipe) return backward_pipelined(ctx, p, f_c);
   cufftDoubleComplex* c = spec_buf(ctx, p);
   X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_z, c, c, CUFFT_INVERSE));
   ctx->launches++;

@@ -184,7 +184,7 @@ int tds_solve_m3(x3d2c_ctx* ctx, int dir, double* du, const double* u, const x3d
   p.out = du;
   const int threads = L * p.g.nseg;
   if (!split) return dispatch_lanes<false>(ctx, p, L, ops->tap_mask, threads, smem);
-  const DistBufs b = carve_dist(ctx);
+  DistBufs b = carve_dist(ctx);
   EdgeParams ep{};
   ep.n = n;
   ep.n_pad = p.g.n_pad;

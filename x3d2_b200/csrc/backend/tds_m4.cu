@@ -290,7 +290,7 @@ int tds_m4(x3d2c_ctx* ctx, int dir, int mode, double* out_a, double* out_b, cons
   const unsigned mask = two_ops ? (ta->tap_mask | tb->tap_mask) : ta->tap_mask;
   if (!split) return dispatch_mode<false>(ctx, p, mode, L, NT, mask);
   // rank-split direction: halos and boundary carries first (m3_edge.cu), then the main kernel
-  const DistBufs b = carve_dist(ctx);
+  DistBufs b = carve_dist(ctx);
   EdgeParams ep{};
   ep.n = n;
   ep.n_pad = ctx->n_pad(dir);

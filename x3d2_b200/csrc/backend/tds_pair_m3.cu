@@ -200,7 +200,7 @@ int run(x3d2c_ctx* ctx, int dir, PairParams& p, const x3d2c_tdsops* ta, const x3
   p.g.field_doubles = nseg * SP * L + (split ? HALO_ROWS * L : 0);
   const int threads = L * nseg;
   if (!split) return dispatch_lanes<MODE, false>(ctx, p, L, mask, threads, smem);
-  const DistBufs b = carve_dist(ctx);
+  DistBufs b = carve_dist(ctx);
   EdgeParams ep{};
   ep.n = n;
   ep.n_pad = p.g.n_pad;

@@ -252,7 +252,7 @@ int transeq_m3(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, cons
   const int threads = L * nseg;
   const bool compact = der1st->tap_mask == 0x6Cu && der2nd->tap_mask == 0x7Cu;
   if (!split) return dispatch_lanes<false>(ctx, p, L, compact, threads, smem);
-  const DistBufs b = carve_dist(ctx);
+  DistBufs b = carve_dist(ctx);
   EdgeParams ep{};
   ep.n = n;
   ep.n_pad = p.g.n_pad;

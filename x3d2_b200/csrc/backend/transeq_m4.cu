@@ -288,7 +288,7 @@ int transeq_m4(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, cons
     return launch4<4, 256, false>(ctx, p);
   }
   // rank-split direction: halos and boundary carries first (m3_edge.cu), then the main kernel
-  const DistBufs b = carve_dist(ctx);
+  DistBufs b = carve_dist(ctx);
   EdgeParams ep{};
   ep.n = n;
   ep.n_pad = n_pad;
