@@ -76,7 +76,12 @@ constexpr int kHaloRowsDist = 4 * (3 * 4) + 4 * (9 * 3);
 // + a second set of the RECEIVE buffers of the rank-split path (2 x 12 halo rows, 2 x 27 carry rows): with peer stores the
 // neighbours write the next operator's rows while this rank still reads the current ones (m3_edge.cu)
 constexpr int kHaloRowsRecv2 = 2 * (3 * 4) + 2 * (9 * 3);
-constexpr int kHaloRows = (kHaloRowsDist > kHaloRowsRef ? kHaloRowsDist : kHaloRowsRef) + kHaloRowsRecv2;
+// + the receive buffers of the in-kernel carry exchange (m3_common.cuh: InlineCarries): 2 sets x (from prev, from next) x
+// 27 carry rows, kept at the sentinel value between uses
+constexpr int kHaloRowsInline = 2 * 2 * (9 * 3);
+constexpr int kHaloRows = (kHaloRowsDist > kHaloRowsRef ? kHaloRowsDist : kHaloRowsRef) + kHaloRowsRecv2 + kHaloRowsInline;
+// A carry slot that has not been written yet holds this NaN (no computation produces this payload); see m3_common.cuh
+constexpr unsigned long long kCarrySentinel = 0xFFFA5A5AFFFA5A5Aull;
 
 constexpr int kMaxDevices = 64;  // per-device caches of launch attributes / occupancy are indexed by the device ordinal
 
@@ -135,7 +140,7 @@ struct x3d2c_ctx {
   double* peer_halo[8] = {nullptr};
   unsigned long long* halo_flags = nullptr;
   unsigned long long* peer_halo_flags[8] = {nullptr};
-  unsigned long long edge_epoch[4] = {0, 0, 0, 0};  // [dir]: number of rank-split exchanges so far
+  unsigned long long edge_epoch = 0;  // number of rank-split exchanges so far (all directions: the buffers are shared)
 
   int n_pad(int dir) const { return dir == X3D2C_DIR_X ? nx_pad : (dir == X3D2C_DIR_Y ? ny_pad : nz_pad); }
 };
@@ -156,7 +161,7 @@ struct x3d2c_poisson {
   cufftDoubleComplex* peerB[8] = {nullptr};
   double* bar_word = nullptr;  // device word of the all-reduce barriers
   // pipelined exchange (P > 1, poisson.cu): the planes of the slab are transformed and sent chunk by chunk; the copies
-  // (DMA engines, second stream) overlap the transforms of the next chunk; ranks signal each other with flags in peer
+  // (peer stores on a second stream) overlap the transforms of the next chunk; ranks signal each other with flags in peer
   // memory instead of all-reduce barriers
   bool pipe = false;
   int nch = 1;                                   // chunks of nz_loc / nch planes

@@ -40,6 +40,12 @@ void nccl_finalize(x3d2c_ctx* ctx);  // nccl.cu
 
 using namespace x3d2c;
 
+namespace {
+__global__ void fill_u64_kernel(unsigned long long* p, size_t n, unsigned long long v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+}  // namespace
+
 extern "C" {
 
 const char* x3d2c_last_error(void) { return g_last_error.c_str(); }
@@ -87,6 +93,12 @@ int x3d2c_create(const x3d2c_config* cfg, x3d2c_ctx** out) {
   X3D2C_CHECK_CUDA(cudaMalloc(&ctx->halo, sizeof(double) * ctx->halo_doubles + 1024));  // + flags of the peer exchange
   X3D2C_CHECK_CUDA(cudaMemsetAsync(ctx->halo, 0, sizeof(double) * ctx->halo_doubles + 1024, ctx->stream));
   ctx->halo_flags = reinterpret_cast<unsigned long long*>(ctx->halo + ctx->halo_doubles);
+  {  // the in-kernel carry exchange expects its receive slots at the sentinel
+    const size_t n_inl = (size_t)SZ * ng * kHaloRowsInline;
+    fill_u64_kernel<<<1184, 256, 0, ctx->stream>>>(
+        reinterpret_cast<unsigned long long*>(ctx->halo + ctx->halo_doubles - n_inl), n_inl, kCarrySentinel);
+    X3D2C_CHECK_CUDA(cudaGetLastError());
+  }
   ctx->red_blocks = 1184;  // 8 CTAs per SM on 148 SMs
   X3D2C_CHECK_CUDA(cudaMalloc(&ctx->red, sizeof(double) * (2 * ctx->red_blocks + 8)));
   X3D2C_CHECK_CUDA(cudaMallocHost(&ctx->red_host, sizeof(double) * 8));

@@ -178,7 +178,8 @@ struct Copier {
 // segments, extn rows 0..2 hold the sum of all terms that next's first segments contribute to yin of this rank's
 // last three segments (computed by next's edge kernel), lane applied. Otherwise the line is periodic and segment
 // indices wrap.
-template <int L, bool DIST>
+// EXT = false (rank-split lines only): the neighbouring ranks' terms are left out; carries_ext() supplies them later.
+template <int L, bool DIST, bool EXT = true>
 __device__ __forceinline__ void carries(const int ze, const int ys, const int stride, const int extp, const int extn,
                                         const Op& o, const int q, const int nseg, double& zin, double& yin) {
   double zv[2 * DMAX];  // ze(q - DMAX .. q + DMAX - 1)
@@ -186,8 +187,8 @@ __device__ __forceinline__ void carries(const int ze, const int ys, const int st
   for (int t = 0; t < 2 * DMAX; ++t) {
     int s = q - DMAX + t;
     if (DIST) {
-      const bool beyond = s >= nseg;
-      const int a = s < 0 ? extp + (s + DMAX) * L : ze + (beyond ? 0 : s) * stride;
+      const bool beyond = s >= nseg || (!EXT && s < 0);
+      const int a = (EXT && s < 0) ? extp + (s + DMAX) * L : ze + (beyond ? 0 : s) * stride;
       zv[t] = smem[a];
       if (beyond) zv[t] = 0.0;
     } else {
@@ -200,7 +201,7 @@ __device__ __forceinline__ void carries(const int ze, const int ys, const int st
 #pragma unroll
   for (int d = 1; d <= DMAX; ++d) zin = fma(o.zw[d - 1], zv[DMAX - d], zin);
   yin = 0.0;
-  if (DIST) {
+  if (DIST && EXT) {
     const int r = q - (nseg - DMAX);
     if (r >= 0) yin = smem[extn + r * L];
   }
@@ -219,6 +220,143 @@ __device__ __forceinline__ void carries(const int ze, const int ys, const int st
   }
 #pragma unroll
   for (int m = -(DMAX - 1); m <= DMAX - 1; ++m) yin = fma(o.om[m + DMAX - 1], zv[DMAX + m], yin);
+}
+
+// ---- in-kernel carry exchange of a rank-split line --------------------------------------------------------------
+// Instead of a separate edge kernel that repeats the sweeps of the six segments next to the rank boundaries, the main
+// kernel itself hands its boundary carries to the neighbours: right after the local sweeps of a tile the threads of the
+// last three segments store their ze into the next rank's receive slots and the threads of the first three segments
+// what they add to yin of the previous rank's last segments (peer stores over NVLink), then poll their own slots for the
+// neighbours' values of the same tile. Every 8-byte slot validates itself: it holds kCarrySentinel until the neighbour
+// has written it and is put back to the sentinel by its (only) reader, so no flags or fences are needed. Two sets of
+// slots alternate between consecutive exchanges: a neighbour can be at most one operator ahead (it needs this rank's
+// carries of that operator to finish it), so it never writes a slot that is still unread.
+struct InlineCarries {
+  double *to_prev, *to_next;      // the neighbours' from_next / from_prev (peer mapped; this rank's own with one rank)
+  double *from_prev, *from_next;  // (SZ, EXP_ROWS, ns, G); null: carries come from the edge kernel
+};
+
+__device__ __forceinline__ void push_carry(double* dst, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst), "d"(v) : "memory");
+}
+__device__ __forceinline__ double take_carry(double* src) {
+  unsigned long long v;
+  long long t0 = 0;
+  for (unsigned spins = 0;; ++spins) {
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+    if (v != x3d2c::kCarrySentinel) break;
+    if (spins == 64) t0 = clock64();
+    if (spins > 64) {
+      __nanosleep(40);
+      if (clock64() - t0 > 40000000000ll) {  // ~20 s: the neighbour is gone; fail instead of hanging the device
+        printf("x3d2c: carry exchange timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+        __trap();
+      }
+    }
+  }
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(src), "l"(x3d2c::kCarrySentinel) : "memory");
+  return __longlong_as_double((long long)v);
+}
+
+// One recurrence of one tile. ze / ys: shared offsets of the carries of segment 0 (lane applied, L doubles between
+// segments); slot: offset of row 0 of this recurrence for this thread's lane in the (SZ, EXP_ROWS, ns, G) arrays;
+// xp / xn: shared offsets (lane applied) where carries() expects the rows from the previous / next rank.
+// Pushing and polling are separate so that a kernel can put other work between them (the neighbour needs about as
+// long as this rank to reach the same tile, and the stores take a few microseconds over NVLink).
+template <int L>
+__device__ __forceinline__ void push_carries_inline(const InlineCarries& c, const size_t slot, const int ze, const int ys,
+                                                    const Op& o, const int q, const int nseg) {
+  const int r = q - (nseg - DMAX);
+  if (r >= 0) {
+    push_carry(c.to_next + slot + (size_t)r * SZ, smem[ze + q * L]);
+  } else if (q < DMAX) {
+    // what this rank's first segments add to yin of the previous rank's segment nseg' - 3 + q (see carries())
+    double acc = 0.0;
+#pragma unroll
+    for (int d = 1; d <= DMAX; ++d)
+      if (q + d - DMAX >= 0) acc = fma(o.yw[d - 1], smem[ys + (q + d - DMAX) * L], acc);
+#pragma unroll
+    for (int m = 1; m <= DMAX - 1; ++m)
+      if (q + m - DMAX >= 0) acc = fma(o.om[m + DMAX - 1], smem[ze + (q + m - DMAX) * L], acc);
+    push_carry(c.to_prev + slot + (size_t)q * SZ, acc);
+  }
+}
+// N slots at once: all loads are in flight together, so that a poll whose data has arrived costs one trip to L2
+template <int N>
+__device__ __forceinline__ void take_carries(double* const (&src)[N], double (&out)[N]) {
+  unsigned long long v[N];
+  long long t0 = 0;
+  for (unsigned spins = 0;; ++spins) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v[i]) : "l"(src[i]) : "memory");
+    bool all = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) all = all && v[i] != x3d2c::kCarrySentinel;
+    if (all) break;
+    if (spins == 64) t0 = clock64();
+    if (spins > 64) {
+      __nanosleep(40);
+      if (clock64() - t0 > 40000000000ll) {
+        printf("x3d2c: carry exchange timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+        __trap();
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(src[i]), "l"(x3d2c::kCarrySentinel) : "memory");
+    out[i] = __longlong_as_double((long long)v[i]);
+  }
+}
+
+// N recurrences whose slots are `sstride` doubles apart and whose shared rows are `xstride` doubles apart
+template <int L, int N>
+__device__ __forceinline__ void poll_carries_inline(const InlineCarries& c, const size_t slot, const size_t sstride,
+                                                    const int q, const int nseg, const int xp, const int xn,
+                                                    const int xstride) {
+  const int r = q - (nseg - DMAX);
+  if (r >= 0 || q < DMAX) {
+    const bool nx = r >= 0;
+    double* const base = (nx ? c.from_next : c.from_prev) + slot + (size_t)(nx ? r : q) * SZ;
+    double* src[N];
+    double v[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) src[i] = base + i * sstride;
+    take_carries<N>(src, v);
+    const int x = nx ? xn + r * L : xp + q * L;
+#pragma unroll
+    for (int i = 0; i < N; ++i) smem[x + i * xstride] = v[i];
+  }
+}
+template <int L>
+__device__ __forceinline__ void poll_carries_inline(const InlineCarries& c, const size_t slot, const int q, const int nseg,
+                                                    const int xp, const int xn) {
+  poll_carries_inline<L, 1>(c, slot, 0, q, nseg, xp, xn, 0);
+}
+template <int L>
+__device__ __forceinline__ void exchange_carries_inline(const InlineCarries& c, const size_t slot, const int ze,
+                                                        const int ys, const Op& o, const int q, const int nseg,
+                                                        const int xp, const int xn) {
+  push_carries_inline<L>(c, slot, ze, ys, o, q, nseg);
+  poll_carries_inline<L>(c, slot, q, nseg, xp, xn);
+}
+
+// The terms of carries() that come from the neighbouring ranks (zero for all but the first / last DMAX segments)
+template <int L>
+__device__ __forceinline__ void carries_ext(const int extp, const int extn, const Op& o, const int q, const int nseg,
+                                            double& zin, double& yin) {
+  zin = 0.0;
+  yin = 0.0;
+  const int r = q - (nseg - DMAX);
+  if (r >= 0) yin = smem[extn + r * L];
+  if (q < DMAX) {
+#pragma unroll
+    for (int d = 1; d <= DMAX; ++d)
+      if (q - d < 0) zin = fma(o.zw[d - 1], smem[extp + (q - d + DMAX) * L], zin);
+#pragma unroll
+    for (int m = -(DMAX - 1); m <= -1; ++m)
+      if (q + m < 0) yin = fma(o.om[m + DMAX - 1], smem[extp + (q + m + DMAX) * L], yin);
+  }
 }
 
 // window element t (row j0 - 4 + t, t = 0..S+7) given the bases of the previous, own and next segment
@@ -254,7 +392,7 @@ struct DistBufs {
   double *carr_to_prev, *carr_to_next, *carr_from_prev, *carr_from_next;
 };
 constexpr int kDistRows = 4 * (3 * 4) + 4 * (9 * EXP_ROWS);  // rows of SZ*G doubles that DistBufs needs
-static_assert(kDistRows <= x3d2c::kHaloRows, "ctx->halo (ctx.cu) is too small for the rank-split exchange buffers");
+static_assert(kDistRows + x3d2c::kHaloRowsRecv2 + x3d2c::kHaloRowsInline <= x3d2c::kHaloRows, "ctx->halo (ctx.cu) is too small for the rank-split exchange buffers");
 DistBufs carve_dist(x3d2c_ctx* ctx, int recv_set = 0);  // recv_set 1: the second set of receive buffers
 bool dist_supported(const x3d2c_ctx* ctx, int dir, int n);
 
@@ -268,7 +406,10 @@ struct EdgeParams {
   double *to_prev, *to_next;      // (SZ, EXP_ROWS, ns, G)
 };
 // packs the halos of nf fields, exchanges them, computes and exchanges the boundary carries
-// (with peer stores the receive buffers alternate between two sets: `b` is updated to the set this exchange filled)
-int exchange_edges(x3d2c_ctx* ctx, int dir, const double* const* fields, int nf, EdgeParams& ep, DistBufs& b);
+// (with peer stores the receive buffers alternate between two sets: `b` is updated to the set this exchange filled).
+// inl != null and the in-kernel carry exchange is possible (peer-mapped buffers, or a single rank that is its own
+// neighbour): only the halos are exchanged and *inl describes the slots of this exchange; otherwise inl->from_prev = null.
+int exchange_edges(x3d2c_ctx* ctx, int dir, const double* const* fields, int nf, EdgeParams& ep, DistBufs& b,
+                   InlineCarries* inl = nullptr);
 
 }  // namespace m3

@@ -190,8 +190,8 @@ DistBufs carve_dist(x3d2c_ctx* ctx, int recv_set) {
   b.carr_to_next = p; p += 9 * EXP_ROWS * row;
   b.carr_from_prev = p; p += 9 * EXP_ROWS * row;
   b.carr_from_next = p; p += 9 * EXP_ROWS * row;
-  if (recv_set) {  // the alternate receive buffers live behind everything else (common.cuh: kHaloRowsRecv2)
-    p = ctx->halo + (size_t)(x3d2c::kHaloRows - x3d2c::kHaloRowsRecv2) * row;
+  if (recv_set) {  // the alternate receive buffers live behind the first set (common.cuh: kHaloRowsRecv2)
+    p = ctx->halo + (size_t)(x3d2c::kHaloRows - x3d2c::kHaloRowsInline - x3d2c::kHaloRowsRecv2) * row;
     b.halo_recv_s = p; p += 12 * row;
     b.halo_recv_e = p; p += 12 * row;
     b.carr_from_prev = p; p += 9 * EXP_ROWS * row;
@@ -201,8 +201,10 @@ DistBufs carve_dist(x3d2c_ctx* ctx, int recv_set) {
   return b;
 }
 
-int exchange_edges(x3d2c_ctx* ctx, int dir, const double* const* fields, int nf, EdgeParams& ep, DistBufs& b) {
+int exchange_edges(x3d2c_ctx* ctx, int dir, const double* const* fields, int nf, EdgeParams& ep, DistBufs& b,
+                   InlineCarries* inl) {
   const int G = ctx->n_groups[dir];
+  static const bool no_inline = std::getenv("X3D2C_NO_INLINE_CARRIES") != nullptr;
   // Peer-store path (P > 1, buffers mapped): the pack kernel writes this rank's first / last four rows straight into
   // the neighbours' receive buffers, the edge kernel its carries; each phase is announced with one flag per neighbour
   // and awaited with a two-thread kernel. The receive buffers alternate between two sets (see common.cuh).
@@ -210,9 +212,22 @@ int exchange_edges(x3d2c_ctx* ctx, int dir, const double* const* fields, int nf,
   double *dst_halo_s = b.halo_send_s, *dst_halo_e = b.halo_send_e, *dst_to_prev = b.carr_to_prev, *dst_to_next = b.carr_to_next;
   unsigned long long epoch = 0;
   unsigned long long *sig_prev[2] = {nullptr, nullptr}, *sig_next[2] = {nullptr, nullptr}, *my_flag[2][2] = {{nullptr}};
+  epoch = ++ctx->edge_epoch;
+  const int set = (int)(epoch & 1);
+  const bool use_inline = inl && !no_inline && (peer || ctx->cfg.nproc_dir[dir - 1] == 1);
+  if (inl) *inl = InlineCarries{};
+  if (use_inline) {
+    int ng = ctx->n_groups[1] > ctx->n_groups[2] ? ctx->n_groups[1] : ctx->n_groups[2];
+    if (ctx->n_groups[3] > ng) ng = ctx->n_groups[3];
+    const size_t row = (size_t)SZ * ng;
+    double* base = ctx->halo + (size_t)(x3d2c::kHaloRows - x3d2c::kHaloRowsInline) * row + (size_t)set * 2 * 9 * EXP_ROWS * row;
+    inl->from_prev = base;
+    inl->from_next = base + 9 * EXP_ROWS * row;
+    const int prev = ctx->cfg.pprev[dir - 1], next = ctx->cfg.pnext[dir - 1];
+    inl->to_prev = peer ? ctx->peer_halo[prev] + (inl->from_next - ctx->halo) : inl->from_next;
+    inl->to_next = peer ? ctx->peer_halo[next] + (inl->from_prev - ctx->halo) : inl->from_prev;
+  }
   if (peer) {
-    epoch = ++ctx->edge_epoch[dir];
-    const int set = (int)(epoch & 1);
     b = carve_dist(ctx, set);
     const int prev = ctx->cfg.pprev[dir - 1], next = ctx->cfg.pnext[dir - 1];
     auto remote = [&](int r, const double* local) { return ctx->peer_halo[r] + (local - ctx->halo); };
@@ -255,6 +270,17 @@ int exchange_edges(x3d2c_ctx* ctx, int dir, const double* const* fields, int nf,
     if (rc) return rc;
   }
   mark(2);
+  if (use_inline) {
+    if (timing) {
+      cudaEventSynchronize(ev[2]);
+      float t[2];
+      for (int i = 0; i < 2; ++i) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
+      std::fprintf(stderr, "[x3d2c] rank %d edges dir=%d ns=%d: pack %.3f ms, halo exchange %.3f, carries in the main kernel\n",
+                   ctx->cfg.rank, dir, ep.ns, t[0], t[1]);
+      for (auto& e : ev) cudaEventDestroy(e);
+    }
+    return X3D2C_OK;
+  }
   ep.G = G;
   ep.nf = nf;
   ep.halo_s = b.halo_recv_s;

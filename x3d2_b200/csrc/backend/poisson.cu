@@ -103,6 +103,31 @@ slab_exchange_kernel(const PeerPtrs dst, const double2* __restrict__ src, const 
   }
 }
 
+// One chunk of planes of the pipelined exchange (rows q0 .. q0 + rows - 1 of (i, k_loc)), every element stored straight
+// into the destination rank's buffer (peer stores over NVLink; the own block is an ordinary store):
+//   FWD: local B(j, q)           ->  rank r = j / ny_loc:  Cx_r[(rank * blk + q) * ny_loc + jl]
+//   BWD: local Cx(jl, q, s)      ->  rank s:               B_s[(rank * ny_loc + jl) + ny * q]
+template <bool FWD>
+__global__ void __launch_bounds__(256)
+chunk_exchange_kernel(const PeerPtrs dst, const double2* __restrict__ src, const int ny, const int ny_loc, const int P,
+                      const size_t blk, const size_t q0, const size_t rows, const int rank) {
+  const size_t n = (size_t)ny * rows;  // == ny_loc * rows * P
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    if (FWD) {
+      const int j = (int)(t % ny);
+      const size_t q = q0 + t / ny;
+      const int r = j / ny_loc, jl = j - r * ny_loc;
+      dst.p[r][((size_t)rank * blk + q) * ny_loc + jl] = src[(size_t)ny * q + j];
+    } else {
+      const int jl = (int)(t % ny_loc);
+      const size_t u = t / ny_loc;
+      const int s = (int)(u / rows);
+      const size_t q = q0 + (u - (size_t)s * rows);
+      dst.p[s][(size_t)rank * ny_loc + jl + (size_t)ny * q] = src[((size_t)s * blk + q) * ny_loc + jl];
+    }
+  }
+}
+
 // cross-rank signalling of the pipelined exchange: flags in peer memory (monotonic solve counter)
 struct FlagPtrs { unsigned long long* p[8]; };
 __global__ void set_flags_kernel(const FlagPtrs dst, const int P, const int slot, const unsigned long long v) {
@@ -365,12 +390,16 @@ int x3d2c::poisson_create_common(x3d2c_ctx* ctx, int bc_case, const double* wave
       X3D2C_CHECK_CUFFT(cufftSetStream(p->plan_r2c_c, ctx->stream));
       X3D2C_CHECK_CUFFT(cufftSetStream(p->plan_c2r_c, ctx->stream));
       X3D2C_CHECK_CUFFT(cufftSetStream(p->plan_y_c, ctx->stream));
-      X3D2C_CHECK_CUDA(cudaStreamCreateWithFlags(&p->s2, cudaStreamNonBlocking));
+      // the exchange stream outranks the transforms: its blocks are placed first whenever an SM frees slots, so the
+      // NVLink stores start as soon as a chunk is ready instead of behind the queued blocks of the next transform
+      int prio_lo = 0, prio_hi = 0;
+      X3D2C_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      X3D2C_CHECK_CUDA(cudaStreamCreateWithPriority(&p->s2, cudaStreamNonBlocking, getenv("X3D2C_PIPE_NO_PRIO") ? prio_lo : prio_hi));
       for (int c = 0; c < nch; ++c) X3D2C_CHECK_CUDA(cudaEventCreateWithFlags(&p->ev_chunk[c], cudaEventDisableTiming));
       X3D2C_CHECK_CUDA(cudaEventCreateWithFlags(&p->ev_z, cudaEventDisableTiming));
       p->pipe = true;
       if (std::getenv("X3D2C_TRACE"))
-        std::fprintf(stderr, "[x3d2c] rank %d poisson exchange pipelined: %d chunks of %d planes, DMA copies + peer flags\n",
+        std::fprintf(stderr, "[x3d2c] rank %d poisson exchange pipelined: %d chunks of %d planes, peer stores on a second stream + flags\n",
                      ctx->cfg.rank, nch, pl);
     }
   }
@@ -413,16 +442,68 @@ int x3d2c_poisson_destroy(x3d2c_ctx* ctx, x3d2c_poisson* p) {
 static cufftDoubleComplex* spec_buf(const x3d2c_ctx*, x3d2c_poisson* p) { return p->pipe ? p->Cx : (p->p2p ? p->A : p->B); }
 
 // Pipelined forward transform (P > 1): the slab is processed in chunks of planes; x transform, transpose and y
-// transform of chunk c + 1 run on the context's stream while the copy engines move chunk c to the y slabs of all
-// ranks (second stream). No all-reduce barrier: every rank raises a flag on every peer once its copies are complete.
+// transform of chunk c + 1 run on the context's stream while an exchange kernel moves chunk c to the y slabs of all
+// ranks with peer stores (second stream). No all-reduce barrier: every rank raises a flag on every peer once its copies are complete.
+// blocks of the chunk exchange: 4 per SM keep half of every SM's thread slots free for the transforms of the next chunk
+static int exchange_blocks() {
+  static const int n = [] {
+    const char* e = getenv("X3D2C_PIPE_BLOCKS");
+    return e && atoi(e) > 0 ? atoi(e) : 148 * 4;
+  }();
+  return n;
+}
+
+// Diagnostic timeline (X3D2C_POISSON_TIMELINE=1): events recorded on both streams during the sixth solve, printed as
+// milliseconds since the start of its forward transform.
+struct Timeline {
+  static constexpr int kMax = 96;
+  cudaEvent_t ev[kMax];
+  const char* label[kMax];
+  int chunk[kMax];
+  int n = 0, calls = 0;
+  bool enabled = false, armed = false, created = false;
+  void begin(cudaStream_t s) {
+    static const bool on = getenv("X3D2C_POISSON_TIMELINE") != nullptr;
+    enabled = on;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (on) cudaStreamIsCapturing(s, &st);
+    armed = enabled && st == cudaStreamCaptureStatusNone && ++calls == 6;
+    if (armed && !created) {
+      for (auto& e : ev) cudaEventCreate(&e);
+      created = true;
+    }
+    n = 0;
+  }
+  void mark(const char* what, int c, cudaStream_t s) {
+    if (!armed || n >= kMax) return;
+    label[n] = what;
+    chunk[n] = c;
+    cudaEventRecord(ev[n++], s);
+  }
+  void report(int rank, cudaStream_t s1, cudaStream_t s2) {
+    if (!armed) return;
+    cudaStreamSynchronize(s1);
+    cudaStreamSynchronize(s2);
+    for (int i = 1; i < n; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[0], ev[i]);
+      fprintf(stderr, "[x3d2c] rank %d poisson timeline %7.3f ms  %s %d\n", rank, ms, label[i], chunk[i]);
+    }
+    armed = false;
+  }
+};
+static Timeline g_tl;
+
 static int forward_pipelined(x3d2c_ctx* ctx, x3d2c_poisson* p, const double* in) {
   const int P = ctx->cfg.nproc, me = ctx->cfg.rank, nch = p->nch, pl = p->nz_loc / nch;
   const size_t plane_r = (size_t)p->nx * p->ny, plane_c = (size_t)p->nxh * p->ny;
   const size_t blk = (size_t)p->nz_loc * p->nxh;  // rows (i, k_loc) of one rank block in Cx
-  const size_t row = sizeof(cufftDoubleComplex) * p->ny_loc;
   p->epoch++;
   FlagPtrs fp;
-  for (int r = 0; r < 8; ++r) fp.p[r] = p->peerFlags[r];
+  PeerPtrs dstC;
+  for (int r = 0; r < 8; ++r) { fp.p[r] = p->peerFlags[r]; dstC.p[r] = (double2*)p->peerC[r]; }
+  g_tl.begin(ctx->stream);
+  g_tl.mark("start", 0, ctx->stream);
   for (int c = 0; c < nch; ++c) {
     cufftDoubleComplex* a = p->A + (size_t)c * pl * plane_c;
     cufftDoubleComplex* b = p->B + (size_t)c * pl * plane_c;
@@ -436,54 +517,52 @@ static int forward_pipelined(x3d2c_ctx* ctx, x3d2c_poisson* p, const double* in)
     X3D2C_CHECK_CUDA(cudaEventRecord(p->ev_chunk[c], ctx->stream));
     X3D2C_CHECK_CUDA(cudaStreamWaitEvent(p->s2, p->ev_chunk[c], 0));
     const size_t q0 = (size_t)p->nxh * pl * c;  // first row (i + nxh k_loc) of the chunk
-    for (int d = 1; d <= P; ++d) {              // start with the next rank: spreads the traffic over the links
-      const int r = (me + d) % P;
-      // B(j, q) with j in rank r's range  ->  Cx_r[(me * blk + q) * ny_loc + jl]
-      X3D2C_CHECK_CUDA(cudaMemcpy2DAsync(p->peerC[r] + ((size_t)me * blk + q0) * p->ny_loc, row,
-                                         p->B + (size_t)r * p->ny_loc + (size_t)p->ny * q0,
-                                         sizeof(cufftDoubleComplex) * p->ny, row, (size_t)p->nxh * pl,
-                                         cudaMemcpyDefault, p->s2));
-    }
+    chunk_exchange_kernel<true><<<exchange_blocks(), 256, 0, p->s2>>>(dstC, (const double2*)p->B, p->ny, p->ny_loc, P, blk, q0,
+                                                                   (size_t)p->nxh * pl, me);
+    X3D2C_CHECK_LAUNCH(ctx);
+    g_tl.mark("fwd xy transforms done (main)", c, ctx->stream);
+    g_tl.mark("fwd exchange done (s2)", c, p->s2);
   }
   set_flags_kernel<<<1, 32, 0, p->s2>>>(fp, P, me, p->epoch);
   X3D2C_CHECK_LAUNCH(ctx);
   wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(p->flags, P, 0, 1, p->epoch);
   X3D2C_CHECK_LAUNCH(ctx);
+  g_tl.mark("fwd all ranks delivered (main)", 0, ctx->stream);
   X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_z, p->Cx, p->Cx, CUFFT_FORWARD));
   ctx->launches++;
+  g_tl.mark("fwd z transform done (main)", 0, ctx->stream);
   return X3D2C_OK;
 }
 
-// Pipelined backward transform: after the z transform the copy engines deliver the planes chunk by chunk to their
+// Pipelined backward transform: after the z transform exchange kernels deliver the planes chunk by chunk to their
 // z slabs; a rank starts the y transform, transpose and x transform of a chunk as soon as all ranks have flagged it.
 static int backward_pipelined(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_c) {
   const int P = ctx->cfg.nproc, me = ctx->cfg.rank, nch = p->nch, pl = p->nz_loc / nch;
   const size_t plane_r = (size_t)p->nx * p->ny, plane_c = (size_t)p->nxh * p->ny;
   const size_t blk = (size_t)p->nz_loc * p->nxh;
-  const size_t row = sizeof(cufftDoubleComplex) * p->ny_loc;
   FlagPtrs fp;
-  for (int r = 0; r < 8; ++r) fp.p[r] = p->peerFlags[r];
+  PeerPtrs dstB;
+  for (int r = 0; r < 8; ++r) { fp.p[r] = p->peerFlags[r]; dstB.p[r] = (double2*)p->peerB[r]; }
+  g_tl.mark("bwd start (main)", 0, ctx->stream);
   X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_z, p->Cx, p->Cx, CUFFT_INVERSE));
   ctx->launches++;
+  g_tl.mark("bwd z transform done (main)", 0, ctx->stream);
   X3D2C_CHECK_CUDA(cudaEventRecord(p->ev_z, ctx->stream));
   X3D2C_CHECK_CUDA(cudaStreamWaitEvent(p->s2, p->ev_z, 0));
   for (int c = 0; c < nch; ++c) {
     const size_t q0 = (size_t)p->nxh * pl * c;
-    for (int d = 1; d <= P; ++d) {
-      const int s = (me + d) % P;
-      // Cx[(s * blk + q) * ny_loc + jl]  ->  B_s[(me * ny_loc + jl) + ny * q]
-      X3D2C_CHECK_CUDA(cudaMemcpy2DAsync(p->peerB[s] + (size_t)me * p->ny_loc + (size_t)p->ny * q0,
-                                         sizeof(cufftDoubleComplex) * p->ny,
-                                         p->Cx + ((size_t)s * blk + q0) * p->ny_loc, row, row, (size_t)p->nxh * pl,
-                                         cudaMemcpyDefault, p->s2));
-    }
+    chunk_exchange_kernel<false><<<exchange_blocks(), 256, 0, p->s2>>>(dstB, (const double2*)p->Cx, p->ny, p->ny_loc, P, blk, q0,
+                                                                    (size_t)p->nxh * pl, me);
+    X3D2C_CHECK_LAUNCH(ctx);
     set_flags_kernel<<<1, 32, 0, p->s2>>>(fp, P, 8 + 8 * me + c, p->epoch);
     X3D2C_CHECK_LAUNCH(ctx);
+    g_tl.mark("bwd exchange done (s2)", c, p->s2);
   }
   double* outp = p->compact ? p->compact : f_c;
   for (int c = 0; c < nch; ++c) {
     wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(p->flags, P, 8 + c, 8, p->epoch);
     X3D2C_CHECK_LAUNCH(ctx);
+    g_tl.mark("bwd chunk delivered by all ranks (main)", c, ctx->stream);
     cufftDoubleComplex* a = p->A + (size_t)c * pl * plane_c;
     cufftDoubleComplex* b = p->B + (size_t)c * pl * plane_c;
     X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_y_c, b, b, CUFFT_INVERSE));
@@ -493,11 +572,13 @@ static int backward_pipelined(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_c) {
     X3D2C_CHECK_LAUNCH(ctx);
     X3D2C_CHECK_CUFFT(cufftExecZ2D(p->plan_c2r_c, a, outp + (size_t)c * pl * plane_r));
     ctx->launches++;
+    g_tl.mark("bwd yx transforms done (main)", c, ctx->stream);
   }
   if (p->compact) {
     pad_copy_kernel<false><<<1184, 256, 0, ctx->stream>>>(p->compact, f_c, p->nx, p->ny, p->nz_loc, ctx->nx_pad, ctx->ny_pad);
     X3D2C_CHECK_LAUNCH(ctx);
   }
+  g_tl.report(ctx->cfg.rank, ctx->stream, p->s2);
   return X3D2C_OK;
 }
 
@@ -512,13 +593,18 @@ int x3d2c_fft_forward(x3d2c_ctx* ctx, x3d2c_poisson* p, const double* f_c) {
     in = p->compact;
   }
   if (p->pipe) return forward_pipelined(ctx, p, in);
+  g_tl.begin(ctx->stream);
+  g_tl.mark("start", 0, ctx->stream);
   X3D2C_CHECK_CUFFT(cufftExecD2Z(p->plan_r2c, const_cast<double*>(in), p->A));
   ctx->launches++;
+  g_tl.mark("fwd x transform done", 0, ctx->stream);
   const dim3 grid((p->nxh + 31) / 32, (p->ny + 31) / 32, p->nz_loc), block(32, 8);
   cplx_transpose_kernel<<<grid, block, 0, ctx->stream>>>((double2*)p->B, (const double2*)p->A, p->nxh, p->ny);
   X3D2C_CHECK_LAUNCH(ctx);
+  g_tl.mark("fwd transpose done", 0, ctx->stream);
   X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_y, p->B, p->B, CUFFT_FORWARD));
   ctx->launches++;
+  g_tl.mark("fwd y transform done", 0, ctx->stream);
   cufftDoubleComplex* c = p->B;
   if (p->p2p) {
     // every rank has finished reading its A (transpose above) -> A may be written by the peers; afterwards: all
@@ -530,7 +616,9 @@ int x3d2c_fft_forward(x3d2c_ctx* ctx, x3d2c_poisson* p, const double* f_c) {
     slab_exchange_kernel<true><<<1184, 256, 0, ctx->stream>>>(dst, (const double2*)p->B, p->ny, p->ny_loc, p->nxh,
                                                               p->nz_loc, ctx->cfg.rank);
     X3D2C_CHECK_LAUNCH(ctx);
+    g_tl.mark("fwd barrier + exchange kernel done", 0, ctx->stream);
     if ((rc = stream_barrier(ctx, p))) return rc;
+    g_tl.mark("fwd second barrier done", 0, ctx->stream);
     c = p->A;
   } else if (ctx->cfg.nproc > 1) {
     slab_pack_kernel<true><<<1184, 256, 0, ctx->stream>>>((double2*)p->A, (double2*)p->B, p->ny, p->ny_loc, p->nxh, p->nz_loc);
@@ -541,6 +629,7 @@ int x3d2c_fft_forward(x3d2c_ctx* ctx, x3d2c_poisson* p, const double* f_c) {
   }
   X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_z, c, c, CUFFT_FORWARD));
   ctx->launches++;
+  g_tl.mark("fwd z transform done", 0, ctx->stream);
   return X3D2C_OK;
 }
 
@@ -572,8 +661,10 @@ int x3d2c_fft_backward(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_c) {
   X3D2C_REQUIRE(ctx && p && f_c, "x3d2c_fft_backward: null argument");
   if (p->pipe) return backward_pipelined(ctx, p, f_c);
   cufftDoubleComplex* c = spec_buf(ctx, p);
+  g_tl.mark("bwd start", 0, ctx->stream);
   X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_z, c, c, CUFFT_INVERSE));
   ctx->launches++;
+  g_tl.mark("bwd z transform done", 0, ctx->stream);
   if (p->p2p) {
     // B is free on every rank since the barrier that followed the forward exchange
     PeerPtrs dst;
@@ -583,6 +674,7 @@ int x3d2c_fft_backward(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_c) {
     X3D2C_CHECK_LAUNCH(ctx);
     int rc = stream_barrier(ctx, p);
     if (rc) return rc;
+    g_tl.mark("bwd exchange kernel + barrier done", 0, ctx->stream);
   } else if (ctx->cfg.nproc > 1) {
     // y-slabs -> z-slabs: block s of C (k range of rank s) goes back to rank s
     int rc = alltoall(ctx, (double*)p->A, (const double*)p->B, 2 * (size_t)p->ny_loc * p->nxh * p->nz_loc);
@@ -592,16 +684,20 @@ int x3d2c_fft_backward(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_c) {
   }
   X3D2C_CHECK_CUFFT(cufftExecZ2Z(p->plan_y, p->B, p->B, CUFFT_INVERSE));
   ctx->launches++;
+  g_tl.mark("bwd y transform done", 0, ctx->stream);
   const dim3 grid((p->ny + 31) / 32, (p->nxh + 31) / 32, p->nz_loc), block(32, 8);
   cplx_transpose_kernel<<<grid, block, 0, ctx->stream>>>((double2*)p->A, (const double2*)p->B, p->ny, p->nxh);
   X3D2C_CHECK_LAUNCH(ctx);
+  g_tl.mark("bwd transpose done", 0, ctx->stream);
   double* outp = p->compact ? p->compact : f_c;
   X3D2C_CHECK_CUFFT(cufftExecZ2D(p->plan_c2r, p->A, outp));
   ctx->launches++;
+  g_tl.mark("bwd x transform done", 0, ctx->stream);
   if (p->compact) {
     pad_copy_kernel<false><<<1184, 256, 0, ctx->stream>>>(p->compact, f_c, p->nx, p->ny, p->nz_loc, ctx->nx_pad, ctx->ny_pad);
     X3D2C_CHECK_LAUNCH(ctx);
   }
+  g_tl.report(ctx->cfg.rank, ctx->stream, ctx->stream);
   return X3D2C_OK;
 }
 

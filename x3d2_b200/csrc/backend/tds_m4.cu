@@ -5,8 +5,10 @@
 //   DUAL  : out_a = A(in), out_b = B(in)   24 B/pt
 //   AXPY  : y     = y + a A(in)            24 B/pt
 // Periodic, uniform directions with n = 64..1024 a power of two; other shapes use the cp.async kernels. Rank-split
-// directions (DIST) stage halo rows and neighbour carries with cp.async as transeq_m4.cu does; their inputs must be in
-// the direction's own layout (the halo pack and edge kernels read them), the outputs may go through a tensor map.
+// directions (DIST) stage the halo rows with cp.async as transeq_m4.cu does and exchange the boundary carries with the
+// neighbouring ranks from inside the kernel (m3_common.cuh: InlineCarries; without peer-mapped buffers the carries come
+// from the edge kernel and are staged like the halos); their inputs must be in the direction's own layout (the halo pack
+// kernel reads them), the outputs may go through a tensor map.
 // Measured at 512^3: tds_solve 0.395 -> 0.376 ms (87% of HBM peak) with 64-byte rows (L = 8, 256 threads); with
 // 32-byte rows (L = 4, 128 threads) the TMA version is slower (0.52 ms), so narrow tiles stay on the cp.async path.
 #include "m4_common.cuh"
@@ -24,6 +26,7 @@ struct TdsParams4 {
   Op oa, ob;
   // rank-split direction only: received halos (SZ, 4, NF, G) and carries (SZ, 3, NR, G)
   const double *halo_s, *halo_e, *from_prev, *from_next;
+  InlineCarries inl;  // from_prev != null: the carries are exchanged inside this kernel
 };
 
 // F: offset of the own rows' tile; om / op: base of the four rows before / after the own segment
@@ -187,9 +190,181 @@ __global__ void __launch_bounds__(NT, 512 / NT) tds_m4_kernel(const __grid_const
   if (tid == 0) tma_wait_all();
 }
 
+
+// ---- rank-split direction with the carry exchange inside the kernel (m3_common.cuh: InlineCarries) -----------------
+// The wait for the neighbours' carries is taken out of the critical path by finishing every tile one iteration late:
+//   iteration i:  local sweeps of tile i (results stay in registers) -> push its boundary carries
+//                 poll the carries of tile i - 1 (pushed by the neighbours one tile ago), add the carry terms to the
+//                 registers of tile i - 1, write the result into tile i's buffer (its input is dead after the sweeps),
+//                 store it, reload that buffer with tile i + 2.
+// SUM keeps the sum of its two local solutions, AXPY adds y at sweep time (both are linear), DUAL keeps two tiles.
+template <int L, int NT, int MODE>
+struct ShapeI {
+  using Sh = Shape<L, NT, MODE>;
+  static constexpr int NR = Sh::NR, NF = Sh::NF, nseg = Sh::nseg;
+  static constexpr int cset = 2 * NR * NT;                       // (ze, ys) of NR recurrences; two sets
+  static constexpr int cz = 2 * Sh::NSLOT * S * NT;
+  static constexpr int hs0 = cz + 2 * cset + 2;                  // halo staging (after the two mbarriers)
+  static constexpr int xb0 = hs0 + Sh::stage;                    // neighbour carries, two sets
+  static constexpr int xset = 2 * NR * EXP_ROWS * L;
+  static constexpr size_t smem() { return sizeof(double) * (xb0 + 2 * xset); }
+  static __device__ __forceinline__ int stage_off(int j) { return hs0 + (j / nseg) * 4 * NT + (j % nseg) * L; }
+};
+
+template <int L, int NT, unsigned M, int MODE>
+__global__ void __launch_bounds__(NT, MODE == DUAL ? 1 : 512 / NT) tds_m4i_kernel(const __grid_constant__ TdsParams4 p) {
+  using Sh = ShapeI<L, NT, MODE>;
+  constexpr int nseg = Sh::nseg, fd = S * NT, tpg = SZ / L, cpr = L / 2;
+  constexpr int NSLOT = Shape<L, NT, MODE>::NSLOT, NR = Sh::NR, NLOAD = Shape<L, NT, MODE>::NLOAD, NF = Sh::NF, cz = Sh::cz;
+  constexpr int NK = MODE == DUAL ? 2 : 1;  // register tiles kept per tile
+  constexpr unsigned tile_bytes = fd * sizeof(double);
+  const int tid = threadIdx.x, l = tid & (L - 1), q = tid / L;
+  const int b0 = tid, bm = tid - L + (q == 0 ? NT : 0), bp = tid + L - (q == nseg - 1 ? NT : 0);
+  const unsigned bar0 = saddr(smem4 + cz + 2 * Sh::cset), bar1 = bar0 + 8;
+  auto issue_loads = [&](int buf, int tile) {  // thread 0
+    const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
+    const unsigned bar = buf ? bar1 : bar0;
+    mbar_expect_tx(bar, NLOAD * tile_bytes);
+    const int c4 = grp / p.nb, c3 = grp - c4 * p.nb;
+    tma_load_5d(saddr(smem4 + buf * NSLOT * fd), &p.in_a, bar, l0, 0, 0, c3, c4);
+    if (NLOAD == 2) tma_load_5d(saddr(smem4 + (buf * NSLOT + 1) * fd), &p.in_b, bar, l0, 0, 0, c3, c4);
+  };
+  auto stage_halos = [&](int buf, int tile) {  // all threads
+    const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
+    for (int idx = tid; idx < 8 * NF * cpr; idx += NT) {
+      const int row = idx / cpr, c = 2 * (idx - row * cpr);
+      const int f = row >> 3, side = (row >> 2) & 1, r = row & 3;
+      const double* src = (side ? p.halo_e : p.halo_s) + ((size_t)(grp * NF + f) * 4 + r) * SZ + l0 + c;
+      cp_async16(smem4 + Sh::stage_off((buf * NF + f) * 2 + side) + r * NT + c, src);
+    }
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(buf ? bar1 : bar0) : "memory");
+  };
+  if (tid == 0) {
+    mbar_init(bar0, 1 + NT);
+    mbar_init(bar1, 1 + NT);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  {
+    const int t1 = blockIdx.x + gridDim.x;
+    if (tid == 0) {
+      issue_loads(0, blockIdx.x);
+      if (t1 < p.tiles) issue_loads(1, t1);
+    }
+    stage_halos(0, blockIdx.x);
+    if (t1 < p.tiles) stage_halos(1, t1);
+  }
+  double zp[NK][S];  // tile i - 1
+  int prev = -1;
+  for (int tile = blockIdx.x, it = 0;; tile += gridDim.x, ++it) {
+    const bool have = tile < p.tiles;
+    if (!have && prev < 0) break;
+    const int buf = it & 1, cs = cz + buf * Sh::cset, cp = cz + (buf ^ 1) * Sh::cset;
+    const int F0 = buf * NSLOT * fd, F1 = F0 + fd;
+    double zn[NK][S];
+    if (have) {
+      mbar_wait(buf ? bar1 : bar0, (it >> 1) & 1);
+      auto before = [&](int F, int f) { return q == 0 ? Sh::stage_off((buf * NF + f) * 2) + l : F + bm + (S - 4) * NT; };
+      auto after = [&](int F, int f) { return q == nseg - 1 ? Sh::stage_off((buf * NF + f) * 2 + 1) + l : F + bp; };
+      double ze;
+      local_sweeps4<NT, M>(F0, p.oa, before(F0, 0), b0, after(F0, 0), zn[0], ze);
+      smem4[cs + b0] = ze;
+      smem4[cs + NT + b0] = zn[0][0];
+      if (NR == 2) {
+        const int Fb = MODE == SUM ? F1 : F0, fb = MODE == SUM ? 1 : 0;
+        double zb[S];
+        local_sweeps4<NT, M>(Fb, p.ob, before(Fb, fb), b0, after(Fb, fb), zb, ze);
+        smem4[cs + 2 * NT + b0] = ze;
+        smem4[cs + 3 * NT + b0] = zb[0];
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+          if (MODE == SUM) zn[0][k] += zb[k];
+          else zn[NK - 1][k] = zb[k];
+        }
+      }
+      if (MODE == AXPY) {
+#pragma unroll
+        for (int k = 0; k < S; ++k) zn[0][k] += smem4[F1 + b0 + k * NT];
+      }
+    }
+    __syncthreads();  // the carries of tile i are complete; its input tile is dead
+    if (have) {
+      const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
+      const size_t slot = (size_t)grp * NR * EXP_ROWS * SZ + l0 + l;
+      push_carries_inline<L>(p.inl, slot, cs + l, cs + NT + l, p.oa, q, nseg);
+      if (NR == 2) push_carries_inline<L>(p.inl, slot + (size_t)EXP_ROWS * SZ, cs + 2 * NT + l, cs + 3 * NT + l, p.ob, q, nseg);
+    }
+    if (prev >= 0) {
+      const int grp = prev / tpg, l0 = (prev - grp * tpg) * L;
+      const size_t slot = (size_t)grp * NR * EXP_ROWS * SZ + l0 + l;
+      const int xp = Sh::xb0 + (buf ^ 1) * Sh::xset + l, xn = xp + NR * EXP_ROWS * L;
+      poll_carries_inline<L, NR>(p.inl, slot, (size_t)EXP_ROWS * SZ, q, nseg, xp, xn, EXP_ROWS * L);
+      __syncthreads();
+      double zin, yin;
+      carries<L, true>(cp + l, cp + NT + l, L, xp, xn, p.oa, q, nseg, zin, yin);
+#pragma unroll
+      for (int k = 0; k < S; ++k) zp[0][k] = fma(p.oa.Cp[k], yin, fma(p.oa.W[k], zin, zp[0][k]));
+      if (NR == 2) {
+        carries<L, true>(cp + 2 * NT + l, cp + 3 * NT + l, L, xp + EXP_ROWS * L, xn + EXP_ROWS * L, p.ob, q, nseg, zin, yin);
+#pragma unroll
+        for (int k = 0; k < S; ++k) zp[NK - 1][k] = fma(p.ob.Cp[k], yin, fma(p.ob.W[k], zin, zp[NK - 1][k]));
+      }
+      // AXPY stores from the y slot like the plain kernel, everything else from slot 0
+      const int O0 = MODE == AXPY ? F1 : F0;
+#pragma unroll
+      for (int k = 0; k < S; ++k) smem4[O0 + b0 + k * NT] = zp[0][k];
+      if (MODE == DUAL) {
+#pragma unroll
+        for (int k = 0; k < S; ++k) smem4[F1 + b0 + k * NT] = zp[1][k];
+      }
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        const int c4 = grp / p.nb, c3 = grp - c4 * p.nb;
+        tma_store_5d(&p.out_a, saddr(smem4 + O0), l0, 0, 0, c3, c4);
+        if (MODE == DUAL) tma_store_5d(&p.out_b, saddr(smem4 + F1), l0, 0, 0, c3, c4);
+        tma_commit();
+      }
+    }
+    if (!have) break;
+    const int nn = tile + 2 * gridDim.x;
+    if (nn < p.tiles) {
+      stage_halos(buf, nn);  // this buffer's staging area was read by the sweeps above
+      if (tid == 0) {
+        tma_wait_read();  // the store of tile i - 1 has read this buffer
+        issue_loads(buf, nn);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NK; ++j)
+#pragma unroll
+      for (int k = 0; k < S; ++k) zp[j][k] = zn[j][k];
+    prev = tile;
+  }
+  if (tid == 0) tma_wait_all();
+}
+
+template <int L, int NT, unsigned M, int MODE>
+int launch_inline(x3d2c_ctx* ctx, const TdsParams4& p) {
+  constexpr size_t smem = ShapeI<L, NT, MODE>::smem();
+  static int per_sm_dev[x3d2c::kMaxDevices] = {};
+  int& per_sm = per_sm_dev[ctx->device];
+  if (!per_sm) {
+    X3D2C_CHECK_CUDA(cudaFuncSetAttribute(tds_m4i_kernel<L, NT, M, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    X3D2C_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tds_m4i_kernel<L, NT, M, MODE>, NT, smem));
+    if (per_sm < 1) per_sm = 1;
+  }
+  int grid = num_sms(ctx) * per_sm;
+  if (grid > p.tiles) grid = p.tiles;
+  tds_m4i_kernel<L, NT, M, MODE><<<grid, NT, smem, ctx->stream>>>(p);
+  X3D2C_CHECK_LAUNCH(ctx);
+  return X3D2C_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 template <int L, int NT, unsigned M, int MODE, bool DIST>
 int launch(x3d2c_ctx* ctx, const TdsParams4& p) {
+  if (DIST && p.inl.from_prev) return launch_inline<L, NT, M, MODE>(ctx, p);
   constexpr size_t smem = Shape<L, NT, MODE>::smem(DIST);
   static int per_sm_dev[x3d2c::kMaxDevices] = {};  // resident CTAs per SM (registers and shared memory), once per device
   int& per_sm = per_sm_dev[ctx->device];
@@ -301,7 +476,7 @@ int tds_m4(x3d2c_ctx* ctx, int dir, int mode, double* out_a, double* out_b, cons
   ep.f[0] = in_a;
   ep.f[1] = in_b;
   const double* fields[2] = {in_a, in_b};
-  int rc = exchange_edges(ctx, dir, fields, mode == SUM ? 2 : 1, ep, b);
+  int rc = exchange_edges(ctx, dir, fields, mode == SUM ? 2 : 1, ep, b, &p.inl);
   if (rc) return rc;
   p.halo_s = b.halo_recv_s;
   p.halo_e = b.halo_recv_e;
