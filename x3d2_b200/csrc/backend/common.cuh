@@ -168,10 +168,10 @@ struct x3d2c_poisson {
   cufftDoubleComplex* Cx = nullptr;              // C(j_loc, i, k): destination of the forward exchange, spectral buffer
   cufftDoubleComplex* peerC[8] = {nullptr};
   unsigned long long* flags = nullptr;           // behind Cx in the same allocation: [0..7] forward done by rank r,
-  unsigned long long* peerFlags[8] = {nullptr};  //   [8 + 8 r + c] backward chunk c delivered by rank r
+  unsigned long long* peerFlags[8] = {nullptr};  //   [8 + 16 r + c] backward chunk c delivered by rank r
   unsigned long long epoch = 0;
   cudaStream_t s2 = nullptr;
-  cudaEvent_t ev_chunk[8] = {nullptr}, ev_z = nullptr;
+  cudaEvent_t ev_chunk[16] = {nullptr}, ev_z = nullptr;
   cufftHandle plan_r2c_c = 0, plan_c2r_c = 0, plan_y_c = 0;
   // non-periodic y (poisson010.cu)
   int bc_case = 0;      // 0: 000, 10: 010

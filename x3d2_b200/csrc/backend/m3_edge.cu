@@ -36,14 +36,23 @@ __global__ void edge_wait_kernel(const unsigned long long* from_prev, const unsi
   __threadfence_system();
 }
 
-// first / last four rows of nf directional fields -> (SZ, 4, nf, G)
-__global__ void __launch_bounds__(128) halo_pack_kernel(double* __restrict__ send_s, double* __restrict__ send_e,
-                                                        const __grid_constant__ PackParams p) {
-  const int lane = threadIdx.x & 31, row = threadIdx.x >> 5, g = blockIdx.x, f = blockIdx.y;
-  const double* ug = p.f[f] + (size_t)SZ * p.n_pad * g + lane;
-  const size_t o = (((size_t)g * p.nf + f) * 4 + row) * SZ + lane;
-  send_s[o] = ug[(size_t)row * SZ];
-  send_e[o] = ug[(size_t)(p.n - 4 + row) * SZ];
+// first / last four rows of nf directional fields -> (SZ, 4, nf, G). A block of 256 threads moves the eight rows of
+// one field of kPackGroups line groups (the destination may be a neighbour's buffer: 64 x 256-byte rows per block keep
+// enough stores in flight for NVLink; one group per block was launch-bound, 0.30 ms at 1024 x 1024 lines).
+constexpr int kPackGroups = 8;
+__global__ void __launch_bounds__(256) halo_pack_kernel(double* __restrict__ send_s, double* __restrict__ send_e,
+                                                        const int G, const __grid_constant__ PackParams p) {
+  const int lane = threadIdx.x & 31, row = (threadIdx.x >> 5) & 3, end = threadIdx.x >> 7, f = blockIdx.y;
+  const double* src = p.f[f] + (size_t)(end ? p.n - 4 + row : row) * SZ + lane;
+  double* dst = end ? send_e : send_s;
+  double v[kPackGroups];
+  const int g0 = blockIdx.x * kPackGroups;
+#pragma unroll
+  for (int i = 0; i < kPackGroups; ++i)
+    if (g0 + i < G) v[i] = __ldcs(src + (size_t)SZ * p.n_pad * (g0 + i));
+#pragma unroll
+  for (int i = 0; i < kPackGroups; ++i)
+    if (g0 + i < G) dst[(((size_t)(g0 + i) * p.nf + f) * 4 + row) * SZ + lane] = v[i];
 }
 
 // One thread per (lane, edge segment): segments 0..2 and nseg-3..nseg-1 of every line; blockIdx.y = field.
@@ -255,7 +264,7 @@ int exchange_edges(x3d2c_ctx* ctx, int dir, const double* const* fields, int nf,
   pp.n = ep.n;
   pp.n_pad = ep.n_pad;
   pp.nf = nf;
-  halo_pack_kernel<<<dim3(G, nf), 128, 0, ctx->stream>>>(dst_halo_s, dst_halo_e, pp);
+  halo_pack_kernel<<<dim3((G + kPackGroups - 1) / kPackGroups, nf), 256, 0, ctx->stream>>>(dst_halo_s, dst_halo_e, G, pp);
   X3D2C_CHECK_LAUNCH(ctx);
   mark(1);
   int rc = X3D2C_OK;

@@ -196,8 +196,11 @@ process_spectral_000_kernel(double2* __restrict__ c, const double2* __restrict__
   if (fy) { div_r = -div_r; div_c = -div_c; }
   ROT(axv, bxv, +, +)
   // solve
-  const double2 w = waves[idx];
-  if ((w.x < 1.e-16) || (w.y < 1.e-16)) {
+  const double2 w = waves[idx];  // fast mode: -1 / waves, or 0 (poisson_create_common)
+  if (!STRICT) {
+    div_r *= w.x;
+    div_c *= w.y;
+  } else if ((w.x < 1.e-16) || (w.y < 1.e-16)) {
     div_r = 0.0; div_c = 0.0;
   } else {
     div_r = -div_r / w.x;
@@ -345,6 +348,13 @@ int x3d2c::poisson_create_common(x3d2c_ctx* ctx, int bc_case, const double* wave
         const size_t d = j + (size_t)p->ny_loc * (i + (size_t)p->nxh * k);
         wc[2 * d] = waves[2 * s];
         wc[2 * d + 1] = waves[2 * s + 1];
+        if (bc_case == 0 && !ctx->strict) {
+          // fast mode: the kernel multiplies by -1 / waves (0 for the modes the reference sets to zero) instead of
+          // dividing twice per mode - the two FP64 divisions were a third of process_spectral_000's issue slots
+          const bool zero = waves[2 * s] < 1.e-16 || waves[2 * s + 1] < 1.e-16;
+          wc[2 * d] = zero ? 0.0 : -1.0 / waves[2 * s];
+          wc[2 * d + 1] = zero ? 0.0 : -1.0 / waves[2 * s + 1];
+        }
       }
   int rc;
   if ((rc = upload(&p->waves, wc.data(), wc.size(), ctx->stream))) return rc;
@@ -371,11 +381,13 @@ int x3d2c::poisson_create_common(x3d2c_ctx* ctx, int bc_case, const double* wave
   p->have_plans = true;
   if (P > 1 && P <= 8 && !std::getenv("X3D2C_NO_P2P")) {
     // pipelined exchange: a dedicated destination buffer (+ 1 KB of flags behind it), chunked plans, a copy stream
-    const int nch = p->nz_loc % 4 == 0 ? 4 : (p->nz_loc % 2 == 0 ? 2 : 1);
+    int nch = 4;  // X3D2C_PIPE_CHUNKS: 1..16
+    if (const char* e = std::getenv("X3D2C_PIPE_CHUNKS")) nch = std::atoi(e) > 0 && std::atoi(e) <= 16 ? std::atoi(e) : nch;
+    while (nch > 1 && p->nz_loc % nch) nch >>= 1;
     const bool want_pipe = !std::getenv("X3D2C_NO_PIPE");
     if (want_pipe) {
-      X3D2C_CHECK_CUDA(cudaMalloc(&p->Cx, sizeof(cufftDoubleComplex) * n_spec + 1024));
-      X3D2C_CHECK_CUDA(cudaMemset(p->Cx, 0, sizeof(cufftDoubleComplex) * n_spec + 1024));
+      X3D2C_CHECK_CUDA(cudaMalloc(&p->Cx, sizeof(cufftDoubleComplex) * n_spec + 2048));
+      X3D2C_CHECK_CUDA(cudaMemset(p->Cx, 0, sizeof(cufftDoubleComplex) * n_spec + 2048));
       p->flags = reinterpret_cast<unsigned long long*>(p->Cx + n_spec);
     }
     rc = setup_peer_buffers(ctx, p);
@@ -423,7 +435,7 @@ int x3d2c_poisson_destroy(x3d2c_ctx* ctx, x3d2c_poisson* p) {
   for (int r = 0; r < 8; ++r)
     if (r != ctx->cfg.rank && p->peerC[r]) cudaIpcCloseMemHandle(p->peerC[r]);
   if (p->plan_r2c_c) { cufftDestroy(p->plan_r2c_c); cufftDestroy(p->plan_c2r_c); cufftDestroy(p->plan_y_c); }
-  for (int c = 0; c < 8; ++c)
+  for (int c = 0; c < 16; ++c)
     if (p->ev_chunk[c]) cudaEventDestroy(p->ev_chunk[c]);
   if (p->ev_z) cudaEventDestroy(p->ev_z);
   if (p->s2) cudaStreamDestroy(p->s2);
@@ -554,13 +566,13 @@ static int backward_pipelined(x3d2c_ctx* ctx, x3d2c_poisson* p, double* f_c) {
     chunk_exchange_kernel<false><<<exchange_blocks(), 256, 0, p->s2>>>(dstB, (const double2*)p->Cx, p->ny, p->ny_loc, P, blk, q0,
                                                                     (size_t)p->nxh * pl, me);
     X3D2C_CHECK_LAUNCH(ctx);
-    set_flags_kernel<<<1, 32, 0, p->s2>>>(fp, P, 8 + 8 * me + c, p->epoch);
+    set_flags_kernel<<<1, 32, 0, p->s2>>>(fp, P, 8 + 16 * me + c, p->epoch);
     X3D2C_CHECK_LAUNCH(ctx);
     g_tl.mark("bwd exchange done (s2)", c, p->s2);
   }
   double* outp = p->compact ? p->compact : f_c;
   for (int c = 0; c < nch; ++c) {
-    wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(p->flags, P, 8 + c, 8, p->epoch);
+    wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(p->flags, P, 8 + c, 16, p->epoch);
     X3D2C_CHECK_LAUNCH(ctx);
     g_tl.mark("bwd chunk delivered by all ranks (main)", c, ctx->stream);
     cufftDoubleComplex* a = p->A + (size_t)c * pl * plane_c;
