@@ -158,6 +158,10 @@ int x3d2c_tds_solve_sum_r(x3d2c_ctx* ctx, int dir, double* out, const double* in
                           const double* in_b, const x3d2c_tdsops* op_b, int rdr_in, int rdr_out);
 int x3d2c_tds_solve_dual_r(x3d2c_ctx* ctx, int dir, double* out_a, double* out_b, const double* in,
                            const x3d2c_tdsops* op_a, const x3d2c_tdsops* op_b, int rdr_in, int rdr_out);
+/* axpy through an input reorder: reorder(tmp, in, rdr_in); tds_solve(tmp2, tmp, op); vecadd(a, tmp2, 1, y)
+ * (gradient_c2v's y2x reorders followed by the pressure correction, src/vector_calculus.f90:302-330 + src/solver.f90:296-298) */
+int x3d2c_tds_solve_axpy_r(x3d2c_ctx* ctx, int dir, double* y, double a, const double* in, const x3d2c_tdsops* op,
+                           int rdr_in);
 
 /* ---- reorder (src/backend/backend.f90:128-144), rdr is one of X3D2C_RDR_* */
 int x3d2c_reorder(x3d2c_ctx* ctx, int rdr, double* dst, const double* src);

@@ -103,7 +103,8 @@ def test_fused_tds_combinations(oracle, x3d2, dims, bcs, env, strict, monkeypatc
 
 
 RDR_CASES = [(2, 0, 23), (2, 0, 24), (2, 32, 0), (2, 42, 23), (3, 43, 0), (3, 23, 0), (3, 0, 34), (3, 43, 32),
-             (1, 0, 12), (1, 21, 13)]  # (dir, rdr_in, rdr_out); the X cases always run as reorder + operator sequences
+             (1, 0, 12), (1, 21, 13), (1, 21, 0)]  # (dir, rdr_in, rdr_out); X lines: x2y on the output / y2x on the input
+                                                   # go through swizzled tiles (tds_m4.cu XT), (1, 21, 13) as a sequence
 
 
 @pytest.mark.parametrize("dims,bcs,env", [((128, 64, 256), None, {}), ((128, 128, 256), None, {"X3D2C_FORCE_DIST": "1"}),
@@ -128,6 +129,12 @@ def test_tds_through_reorders(oracle, x3d2, dims, bcs, env, strict, monkeypatch)
         ga, gb = sim.tds_fused_r("dual", d, "interpl_p2v", "stagder_p2v", c, rdr_in=rin, rdr_out=rout, in_loc=1110)
         assert rel(ga, ref.tds_solve(d, "interpl_p2v", c, 1110)) <= tol, ("dual a", d, rin, rout)
         assert rel(gb, ref.tds_solve(d, "stagder_p2v", c, 1110)) <= tol, ("dual b", d, rin, rout)
+    # axpy through an input reorder (the gradient's y2x + pressure correction): y - A(c)
+    for d, rin in [(1, 21), (1, 0), (3, 23)]:
+        y = rnd(sim.shape(1110 - 10 ** d), 24)
+        for op in ("stagder_p2v", "interpl_p2v"):
+            e = y - ref.tds_solve(d, op, c, 1110)
+            assert rel(sim.tds_fused_r("axpy", d, op, None, c, y, rdr_in=rin, in_loc=1110), e) <= tol, ("axpy_r", d, rin, op)
     with pytest.raises(RuntimeError, match="rdr_out must be a reorder code that starts from dir"):
         sim.tds_fused_r("single", 2, "interpl_v2p", None, u, rdr_out=34)
     sim.close()

@@ -52,6 +52,15 @@ int run(x3d2c_ctx* ctx, const char* what, int dir, int mode, double* out_a, doub
   // c2z input has its rows one z-plane = 2 MB apart; pressure correction 12.15 ms against 12.02 ms), and rank-split
   // directions need their inputs in the direction's own layout anyway. The outputs go through the tensor map.
   const double *a = in_a, *b = in_b;
+  // ... except x lines: X <-> Y is a 32 x 32 tile transpose, which the swizzled tiles of tds_m4.cu (XT) do on the way in
+  // or out at no cost (divergence: x2y on the output; gradient: y2x on the input)
+  if (!ctx->strict && dir == X3D2C_DIR_X && mode == 0 && (rdr_in != 0) != (rdr_out != 0)) {
+    rc = tds_m4(ctx, dir, mode, out_a, out_b, a, b, op_a, op_b, 1.0, lay_in, lay_out);
+    if (rc != X3D2C_EUNSUPPORTED) {
+      report(rdr_in ? "input through the swizzled tensor map" : "output through the swizzled tensor map");
+      return rc;
+    }
+  }
   if (rdr_in) {
     if ((rc = ensure_scratch_slot(ctx, 2))) return rc;
     if ((rc = x3d2c_reorder(ctx, rdr_in, ctx->scratch[2], in_a))) return rc;
@@ -113,6 +122,30 @@ int x3d2c_tds_solve_dual_r(x3d2c_ctx* ctx, int dir, double* out_a, double* out_b
   X3D2C_REQUIRE(dir >= 1 && dir <= 3, "x3d2c_tds_solve_dual_r: dir must be DIR_X/Y/Z");
   X3D2C_REQUIRE(out_a != in && out_b != in && out_a != out_b, "x3d2c_tds_solve_dual_r: fields must be distinct");
   return run(ctx, "tds_solve_dual_r", dir, 2, out_a, out_b, in, nullptr, op_a, op_b, rdr_in, rdr_out);
+}
+
+int x3d2c_tds_solve_axpy_r(x3d2c_ctx* ctx, int dir, double* y, double a, const double* in, const x3d2c_tdsops* op,
+                           int rdr_in) {
+  X3D2C_ENTER(ctx);
+  X3D2C_REQUIRE(ctx && y && in && op, "x3d2c_tds_solve_axpy_r: null argument");
+  X3D2C_REQUIRE(dir >= 1 && dir <= 3, "x3d2c_tds_solve_axpy_r: dir must be DIR_X/Y/Z");
+  X3D2C_REQUIRE(y != in, "x3d2c_tds_solve_axpy_r: y and in must be different fields");
+  if (!rdr_in) return x3d2c_tds_solve_axpy(ctx, dir, y, a, in, op);
+  int lay_in, lay_out;
+  int rc = layouts(dir, rdr_in, 0, &lay_in, &lay_out);
+  if (rc) return rc;
+  static const bool trace = std::getenv("X3D2C_TRACE") != nullptr;
+  if (!ctx->strict && dir == X3D2C_DIR_X) {
+    rc = tds_m4(ctx, dir, 3, y, nullptr, in, y, op, op, a, lay_in, dir);
+    if (rc != X3D2C_EUNSUPPORTED) {
+      if (trace) std::fprintf(stderr, "[x3d2c] tds_solve_axpy_r dir=%d rdr_in=%d -> input through the swizzled tensor map\n", dir, rdr_in);
+      return rc;
+    }
+  }
+  if (trace) std::fprintf(stderr, "[x3d2c] tds_solve_axpy_r dir=%d rdr_in=%d -> reorder + operator sequence\n", dir, rdr_in);
+  if ((rc = ensure_scratch_slot(ctx, 2))) return rc;
+  if ((rc = x3d2c_reorder(ctx, rdr_in, ctx->scratch[2], in))) return rc;
+  return x3d2c_tds_solve_axpy(ctx, dir, y, a, ctx->scratch[2], op);
 }
 
 }  // extern "C"

@@ -57,6 +57,68 @@ __device__ __forceinline__ void local_sweeps4(const int F, const Op& o, const in
   }
 }
 
+
+// ---- x lines of fields kept in an x-fastest layout (XT: reading or writing through an X <-> Y reorder) ------------
+// In DIR_Y (and DIR_Z, DIR_C) 16 consecutive x of one (y, z) are 128 contiguous bytes, so a 16-point segment of an x
+// line is one row of a 128-byte-swizzled TMA box. The tensor map orders the box as (x in segment, lane y, segment), which
+// lands in shared memory as [segment q][lane l][k]: row r = q L + l = threadIdx.x holds the thread's own 16 points, and
+// the hardware swizzle (16-byte chunk c of row r sits at chunk c ^ (r & 7)) makes the eight threads of a quarter warp hit
+// eight different chunks, so 128-bit accesses are conflict-free. This is the 32 x 32 transpose of reorder.cu done by the
+// TMA engine on the way in or out: no separate pass, no padded staging tile.
+__device__ __forceinline__ double2 lds128(unsigned addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(unsigned addr, double a, double b) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+}
+// window (rows j0 - 4 .. j0 + 19) of thread r from a swizzled tile at shared byte address tile
+template <int L, int NT>
+__device__ __forceinline__ void window_sw(const unsigned tile, const int r, const int q, double (&w)[S + 8]) {
+  constexpr int nseg = NT / L;
+  const int rp = q == 0 ? r + NT - L : r - L, rn = q == nseg - 1 ? r - (NT - L) : r + L;
+  {
+    const unsigned row = tile + rp * 128, x = rp & 7;
+    const double2 a = lds128(row + ((6 ^ x) << 4)), b = lds128(row + ((7 ^ x) << 4));
+    w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y;
+  }
+  {
+    const unsigned row = tile + r * 128, x = r & 7;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const double2 v = lds128(row + ((c ^ x) << 4));
+      w[4 + 2 * c] = v.x;
+      w[5 + 2 * c] = v.y;
+    }
+  }
+  {
+    const unsigned row = tile + rn * 128, x = rn & 7;
+    const double2 a = lds128(row + ((0 ^ x) << 4)), b = lds128(row + ((1 ^ x) << 4));
+    w[S + 4] = a.x; w[S + 5] = a.y; w[S + 6] = b.x; w[S + 7] = b.y;
+  }
+}
+// local_sweeps4 on a window held in registers
+template <unsigned M>
+__device__ __forceinline__ void local_sweeps_w(const Op& o, const double (&w)[S + 8], double (&z)[S], double& ze) {
+  double pz = 0.0;
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    double wf[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wf[t] = w[k + t];
+    pz = fma(o.a, pz, o.fs * sten_exact<M>(o.cfw, wf));
+    z[k] = pz;
+  }
+  ze = pz;
+  double y = 0.0;
+#pragma unroll
+  for (int k = S - 1; k >= 0; --k) {
+    y = fma(o.cb, y, z[k]);
+    z[k] = y;
+  }
+}
+
 template <int L, int NT, int MODE>
 struct Shape {
   static constexpr int NSLOT = MODE == SINGLE ? 1 : 2;
@@ -74,7 +136,9 @@ struct Shape {
 };
 
 // shared memory: [2 buffers][NSLOT tiles of 16 x NT] | NR x (ze, ys)[NT] | 2 mbarriers | DIST: halo staging, carries
-template <int L, int NT, unsigned M, int MODE, bool DIST>
+// XT (x lines only, not rank-split): 1 = out_a is stored through a swizzled map into an x-fastest layout, 2 = in_a is loaded
+// through one (see above); tile coordinates of such a map: (0, y of the first lane, 0, 0, z).
+template <int L, int NT, unsigned M, int MODE, bool DIST, int XT = 0>
 __global__ void __launch_bounds__(NT, 512 / NT) tds_m4_kernel(const __grid_constant__ TdsParams4 p) {
   using Sh = Shape<L, NT, MODE>;
   constexpr int nseg = Sh::nseg, fd = S * NT, tpg = SZ / L, cpr = L / 2;
@@ -88,7 +152,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) tds_m4_kernel(const __grid_const
     const unsigned bar = buf ? bar1 : bar0;
     mbar_expect_tx(bar, NLOAD * tile_bytes);
     const int c4 = grp / p.nb, c3 = grp - c4 * p.nb;
-    tma_load_5d(saddr(smem4 + buf * NSLOT * fd), &p.in_a, bar, l0, 0, 0, c3, c4);
+    if (XT == 2) tma_load_5d(saddr(smem4 + buf * NSLOT * fd), &p.in_a, bar, 0, SZ * c3 + l0, 0, 0, c4);
+    else tma_load_5d(saddr(smem4 + buf * NSLOT * fd), &p.in_a, bar, l0, 0, 0, c3, c4);
     if (NLOAD == 2) tma_load_5d(saddr(smem4 + (buf * NSLOT + 1) * fd), &p.in_b, bar, l0, 0, 0, c3, c4);
   };
   auto stage_neighbours = [&](int buf, int tile) {  // all threads
@@ -137,7 +202,13 @@ __global__ void __launch_bounds__(NT, 512 / NT) tds_m4_kernel(const __grid_const
       return (DIST && q == nseg - 1) ? Sh::stage_off((buf * NF + f) * 2 + 1) + l : F + bp;
     };
     double za[S], zb[S], ze;
-    local_sweeps4<NT, M>(F0, p.oa, before(F0, 0), b0, after(F0, 0), za, ze);
+    if (XT == 2) {
+      double w[S + 8];
+      window_sw<L, NT>(saddr(smem4 + F0), tid, q, w);
+      local_sweeps_w<M>(p.oa, w, za, ze);
+    } else {
+      local_sweeps4<NT, M>(F0, p.oa, before(F0, 0), b0, after(F0, 0), za, ze);
+    }
     smem4[cz + b0] = ze;
     smem4[cz + NT + b0] = za[0];
     if (NR == 2) {
@@ -158,7 +229,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) tds_m4_kernel(const __grid_const
 #pragma unroll
       for (int k = 0; k < S; ++k) zb[k] = fma(p.ob.Cp[k], yin, fma(p.ob.W[k], zin, zb[k]));
     }
-    if (MODE == SINGLE) {
+    if (MODE == SINGLE && XT == 1) {
+      const unsigned row = saddr(smem4 + F0) + tid * 128, x = tid & 7;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) sts128(row + ((c ^ x) << 4), za[2 * c], za[2 * c + 1]);
+    } else if (MODE == SINGLE) {
 #pragma unroll
       for (int k = 0; k < S; ++k) smem4[F0 + b0 + k * NT] = za[k];
     } else if (MODE == SUM) {
@@ -178,7 +253,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) tds_m4_kernel(const __grid_const
     if (tid == 0) {
       const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
       const int c4 = grp / p.nb, c3 = grp - c4 * p.nb;
-      tma_store_5d(&p.out_a, saddr(smem4 + (MODE == AXPY ? F1 : F0)), l0, 0, 0, c3, c4);
+      if (XT == 1) tma_store_5d(&p.out_a, saddr(smem4 + F0), 0, SZ * c3 + l0, 0, 0, c4);
+      else tma_store_5d(&p.out_a, saddr(smem4 + (MODE == AXPY ? F1 : F0)), l0, 0, 0, c3, c4);
       if (MODE == DUAL) tma_store_5d(&p.out_b, saddr(smem4 + F1), l0, 0, 0, c3, c4);
       tma_commit();
       if (nn < p.tiles) {
@@ -382,6 +458,46 @@ int launch(x3d2c_ctx* ctx, const TdsParams4& p) {
   return X3D2C_OK;
 }
 
+template <int L, int NT, unsigned M, int MODE, int XT>
+int launch_xt(x3d2c_ctx* ctx, const TdsParams4& p) {
+  constexpr size_t smem = Shape<L, NT, MODE>::smem(false);
+  static int per_sm_dev[x3d2c::kMaxDevices] = {};
+  int& per_sm = per_sm_dev[ctx->device];
+  if (!per_sm) {
+    X3D2C_CHECK_CUDA(cudaFuncSetAttribute(tds_m4_kernel<L, NT, M, MODE, false, XT>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    X3D2C_CHECK_CUDA(
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tds_m4_kernel<L, NT, M, MODE, false, XT>, NT, smem));
+    if (per_sm < 1) per_sm = 1;
+  }
+  int grid = num_sms(ctx) * per_sm;
+  if (grid > p.tiles) grid = p.tiles;
+  tds_m4_kernel<L, NT, M, MODE, false, XT><<<grid, NT, smem, ctx->stream>>>(p);
+  X3D2C_CHECK_LAUNCH(ctx);
+  return X3D2C_OK;
+}
+
+// the staggered operators of the divergence (v2p, 0x78) and of the gradient (p2v, 0x3C) only
+template <int L, int NT, int MODE, int XT>
+int dispatch_xt_mask(x3d2c_ctx* ctx, const TdsParams4& p, unsigned mask) {
+  switch (mask) {
+    case 0x78u: return launch_xt<L, NT, 0x78u, MODE, XT>(ctx, p);
+    case 0x3Cu: return launch_xt<L, NT, 0x3Cu, MODE, XT>(ctx, p);
+    default: return X3D2C_EUNSUPPORTED;
+  }
+}
+template <int MODE, int XT>
+int dispatch_xt(x3d2c_ctx* ctx, const TdsParams4& p, int L, int NT, unsigned mask) {
+  if (NT == 128) return dispatch_xt_mask<32, 128, MODE, XT>(ctx, p, mask);
+  if (NT == 512) return MODE == SINGLE ? dispatch_xt_mask<8, 512, SINGLE, XT>(ctx, p, mask) : X3D2C_EUNSUPPORTED;
+  switch (L) {
+    case 4: return dispatch_xt_mask<4, 256, MODE, XT>(ctx, p, mask);
+    case 8: return dispatch_xt_mask<8, 256, MODE, XT>(ctx, p, mask);
+    case 16: return dispatch_xt_mask<16, 256, MODE, XT>(ctx, p, mask);
+    default: return dispatch_xt_mask<32, 256, MODE, XT>(ctx, p, mask);
+  }
+}
+
 template <int L, int NT, int MODE, bool DIST>
 int dispatch_mask(x3d2c_ctx* ctx, const TdsParams4& p, unsigned mask) {
   switch (mask) {
@@ -457,6 +573,23 @@ int tds_m4(x3d2c_ctx* ctx, int dir, int mode, double* out_a, double* out_b, cons
   if (two_ops && !make_op(tb, 1.0, split, &p.ob)) return X3D2C_EUNSUPPORTED;
   const int G = ctx->n_groups[dir], nseg = n / S;
   auto map = [&](CUtensorMap* m, const double* f, int layout) { return make_map5(m, f, layout, dir, L, nseg, ctx, &p.nb); };
+  // x lines reading or writing a field kept in the y layout (an X <-> Y reorder folded into the solve)
+  const int xt = dir != X3D2C_DIR_X ? 0 : (lay_out != dir ? 1 : (lay_in != dir ? 2 : 0));
+  if (xt) {
+    static const bool no_xt = std::getenv("X3D2C_NO_XT") != nullptr;
+    if (no_xt || split || (lay_in != dir && lay_out != dir)) return X3D2C_EUNSUPPORTED;
+    if (!(xt == 1 && mode == SINGLE) && !(xt == 2 && (mode == SINGLE || mode == AXPY))) return X3D2C_EUNSUPPORTED;
+    const int lay_native = dir;
+    if (xt == 1) {
+      if (!map(&p.in_a, in_a, lay_native) || !make_map_xt(&p.out_a, out_a, lay_out, L, nseg, ctx)) return X3D2C_EUNSUPPORTED;
+    } else {
+      if (!make_map_xt(&p.in_a, in_a, lay_in, L, nseg, ctx) || !map(&p.out_a, out_a, lay_native)) return X3D2C_EUNSUPPORTED;
+      if (mode == AXPY && !map(&p.in_b, in_b, lay_native)) return X3D2C_EUNSUPPORTED;
+    }
+    p.tiles = G * (SZ / L);
+    if (xt == 1) return dispatch_xt<SINGLE, 1>(ctx, p, L, NT, ta->tap_mask);
+    return mode == SINGLE ? dispatch_xt<SINGLE, 2>(ctx, p, L, NT, ta->tap_mask) : dispatch_xt<AXPY, 2>(ctx, p, L, NT, ta->tap_mask);
+  }
   if (!map(&p.in_a, in_a, lay_in) || !map(&p.out_a, out_a, lay_out)) return X3D2C_EUNSUPPORTED;
   if (mode == SUM && !map(&p.in_b, in_b, lay_in)) return X3D2C_EUNSUPPORTED;
   if (mode == AXPY && !map(&p.in_b, in_b, lay_out)) return X3D2C_EUNSUPPORTED;  // y

@@ -322,8 +322,12 @@ int x3d2h_tds_fused_r(x3d2h_sim* sim, const char* mode, int dir, const char* op_
   } else if (m == "dual") {
     S.backend.tds_solve_dual_r(dir, *oa, *ob, *fa, S.pick(dir, op_a), S.pick(dir, op_b), rdr_in, rdr_out);
     S.get_field(out_b, *ob, out_loc);
+  } else if (m == "axpy") {  // out_a = in_b - A(reorder(in_a)); in_b has the output's extents
+    if (rdr_out) fail("x3d2h_tds_fused_r: axpy takes no output reorder");
+    S.set_field(*oa, in_b, out_loc);
+    S.backend.tds_solve_axpy_r(dir, *oa, -1.0, *fa, S.pick(dir, op_a), rdr_in);
   } else {
-    fail("x3d2h_tds_fused_r: mode must be single, sum or dual");
+    fail("x3d2h_tds_fused_r: mode must be single, sum, dual or axpy");
   }
   S.get_field(out_a, *oa, out_loc);
   H_CATCH

@@ -339,6 +339,10 @@ class Backend {  // cuda_c_backend_t: every method is one deferred procedure of 
     if (u.dir != y.dir) fail("DIR mismatch between fields in tds_solve.");
     X3D2H_CALL(x3d2c_tds_solve_axpy(ctx, u.dir, y.dev, a, u.dev, op.h));
   }
+  void tds_solve_axpy_r(int dir, Field& y, double a, const Field& u, const DevTdsops& op, int rdr_in) {
+    check_r(dir, u, y, rdr_in, 0);
+    X3D2H_CALL(x3d2c_tds_solve_axpy_r(ctx, dir, y.dev, a, u.dev, op.h, rdr_in));
+  }
   void reorder(Field& u_, const Field& u, int direction) {
     X3D2H_CALL(x3d2c_reorder(ctx, direction, u_.dev, u.dev));
     u_.data_loc = u.data_loc;
@@ -910,13 +914,12 @@ class Sim {
     if ((div_u.dir != DIR_Z && div_u.dir != DIR_C) || uu.dir != DIR_X || vv.dir != DIR_X || ww.dir != DIR_X)
       fail("Error in divergence_v2c input/output field dirs: output must be in DIR_Z, inputs must be in DIR_X layout.");
     Allocator& A = allocator;
-    Field *du_x = A.get_block(DIR_X), *dv_x = A.get_block(DIR_X), *dw_x = A.get_block(DIR_X);
-    backend.tds_solve(*du_x, uu, xdirps.stagder_v2p);
-    backend.tds_solve(*dv_x, vv, xdirps.interpl_v2p);
-    backend.tds_solve(*dw_x, ww, xdirps.interpl_v2p);
+    // (u_y, v_y, w_y) = x2y(stagder(u), interpl(v), interpl(w))   (:160-183: tds_solve x3, reorder x3; the reorder is
+    // part of the solve's store)
     Field *u_y = A.get_block(DIR_Y), *v_y = A.get_block(DIR_Y), *w_y = A.get_block(DIR_Y);
-    backend.reorder(*u_y, *du_x, RDR_X2Y); backend.reorder(*v_y, *dv_x, RDR_X2Y); backend.reorder(*w_y, *dw_x, RDR_X2Y);
-    A.release_block(du_x); A.release_block(dv_x); A.release_block(dw_x);
+    backend.tds_solve_r(DIR_X, *u_y, uu, xdirps.stagder_v2p, 0, RDR_X2Y);
+    backend.tds_solve_r(DIR_X, *v_y, vv, xdirps.interpl_v2p, 0, RDR_X2Y);
+    backend.tds_solve_r(DIR_X, *w_y, ww, xdirps.interpl_v2p, 0, RDR_X2Y);
     // u_z = y2z(interpl(u_y) + stagder(v_y)); w_z = y2z(interpl(w_y))   (:185-203: tds_solve x3, vecadd, reorder x2)
     Field *u_z = A.get_block(DIR_Z), *w_z = A.get_block(DIR_Z);
     backend.tds_solve_sum_r(DIR_Y, *u_z, *u_y, ydirps.interpl_v2p, *v_y, ydirps.stagder_v2p, 0, RDR_Y2Z);
@@ -946,22 +949,17 @@ class Sim {
     Field* dpdz_sx_y = A.get_block(DIR_Y);
     backend.tds_solve(*dpdz_sx_y, *dpdz_sxy_y, ydirps.interpl_p2v);
     A.release_block(dpdz_sxy_y);
-    Field* p_sx_x = A.get_block(DIR_X);
-    backend.reorder(*p_sx_x, *p_sx_y, RDR_Y2X); A.release_block(p_sx_y);
-    Field* dpdy_sx_x = A.get_block(DIR_X);
-    backend.reorder(*dpdy_sx_x, *dpdy_sx_y, RDR_Y2X); A.release_block(dpdy_sx_y);
-    Field* dpdz_sx_x = A.get_block(DIR_X);
-    backend.reorder(*dpdz_sx_x, *dpdz_sx_y, RDR_Y2X); A.release_block(dpdz_sx_y);
+    // y2x reorders (:302-318) are part of the x solves' loads
     if (sub) {
-      backend.tds_solve_axpy(*sub[0], -1.0, *p_sx_x, xdirps.stagder_p2v);
-      backend.tds_solve_axpy(*sub[1], -1.0, *dpdy_sx_x, xdirps.interpl_p2v);
-      backend.tds_solve_axpy(*sub[2], -1.0, *dpdz_sx_x, xdirps.interpl_p2v);
+      backend.tds_solve_axpy_r(DIR_X, *sub[0], -1.0, *p_sx_y, xdirps.stagder_p2v, RDR_Y2X);
+      backend.tds_solve_axpy_r(DIR_X, *sub[1], -1.0, *dpdy_sx_y, xdirps.interpl_p2v, RDR_Y2X);
+      backend.tds_solve_axpy_r(DIR_X, *sub[2], -1.0, *dpdz_sx_y, xdirps.interpl_p2v, RDR_Y2X);
     } else {
-      backend.tds_solve(dpdx, *p_sx_x, xdirps.stagder_p2v);
-      backend.tds_solve(dpdy, *dpdy_sx_x, xdirps.interpl_p2v);
-      backend.tds_solve(dpdz, *dpdz_sx_x, xdirps.interpl_p2v);
+      backend.tds_solve_r(DIR_X, dpdx, *p_sx_y, xdirps.stagder_p2v, RDR_Y2X, 0);
+      backend.tds_solve_r(DIR_X, dpdy, *dpdy_sx_y, xdirps.interpl_p2v, RDR_Y2X, 0);
+      backend.tds_solve_r(DIR_X, dpdz, *dpdz_sx_y, xdirps.interpl_p2v, RDR_Y2X, 0);
     }
-    A.release_block(p_sx_x); A.release_block(dpdy_sx_x); A.release_block(dpdz_sx_x);
+    A.release_block(p_sx_y); A.release_block(dpdy_sx_y); A.release_block(dpdz_sx_y);
   }
 
   // vector_calculus.f90:40-140
