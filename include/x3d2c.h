@@ -172,6 +172,12 @@ int x3d2c_sum_yintox(x3d2c_ctx* ctx, double* u, const double* u_y);
 int x3d2c_sum_zintox(x3d2c_ctx* ctx, double* u, const double* u_z);
 /* extension: sum_yintox(u, u_y) followed by sum_zintox(u, u_z) in one pass over u (same order of additions) */
 int x3d2c_sum_yzintox(x3d2c_ctx* ctx, double* u, const double* u_y, const double* u_z);
+/* extension: x3d2c_sum_yzintox(u, u_y, u_z) followed by x3d2c_veclincomb(out, base, [x..., u], [coef..., c_u]) in one
+ * pass (the end of transeq + the Runge-Kutta update, src/solver.f90:340-372 + src/time_integrator.f90:166-231); n <= 3.
+ * store_u == 0: u need not hold the sum on return (the last stage does not keep the derivative). Strict mode runs the
+ * two calls. */
+int x3d2c_sum_yzintox_lincomb(x3d2c_ctx* ctx, double* u, const double* u_y, const double* u_z, int store_u, double* out,
+                              const double* base, int n, const double* coef, const double* const* x, double c_u);
 
 /* ---- veccopy / vecadd / vecmult (src/backend/backend.f90:161-201): whole padded block */
 int x3d2c_veccopy(x3d2c_ctx* ctx, double* dst, const double* src);

@@ -107,6 +107,44 @@ sum2_tile_kernel(double* __restrict__ dst, const double* __restrict__ a, const d
   }
 }
 
+// sum2_tile_kernel followed by a veclincomb whose last term is the finished sum, in the same pass:
+//   s = (u + reorder(a)) + reorder(b);  [u = s];  out = base + sum_k c[k] x[k] + c_s s      (all of them DIR_X)
+struct SumLin {
+  const double* base;
+  const double* x[3];
+  double c[3], c_s;
+  int n, store;
+};
+__global__ void __launch_bounds__(256)
+sum2_lincomb_kernel(double* __restrict__ dst, const double* __restrict__ a, const double* __restrict__ b, double* out,
+                    const Lay la, const Lay lb, const Lay ld, const __grid_constant__ SumLin q) {
+  __shared__ double ta[32][33], tb[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const long long ba = blockIdx.x * la.sxb + blockIdx.y * la.syb + blockIdx.z * la.sz;
+  const long long bb = blockIdx.x * lb.sxb + blockIdx.y * lb.syb + blockIdx.z * lb.sz;
+  const long long bd = blockIdx.x * ld.sxb + blockIdx.y * ld.syb + blockIdx.z * ld.sz;
+  double va[4], vb[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    va[r] = a[ba + tx * la.sxl + (ty + 8 * r) * la.syl];
+    vb[r] = b[bb + tx * lb.sxl + (ty + 8 * r) * lb.syl];
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { ta[ty + 8 * r][tx] = va[r]; tb[ty + 8 * r][tx] = vb[r]; }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const long long i = bd + tx * ld.syl + (ty + 8 * r) * ld.sxl;
+    const double s = (dst[i] + ta[tx][ty + 8 * r]) + tb[tx][ty + 8 * r];
+    if (q.store) dst[i] = s;
+    double o = q.base[i];  // out may alias base
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      if (k < q.n) o = q.c[k] * q.x[k][i] + 1.0 * o;
+    out[i] = q.c_s * s + 1.0 * o;
+  }
+}
+
 }  // namespace
 
 namespace x3d2c {
@@ -161,6 +199,38 @@ int x3d2c_sum_yzintox(x3d2c_ctx* ctx, double* u, const double* u_y, const double
   const dim3 grid(ctx->nx_pad / SZ, ctx->ny_pad / SZ, ctx->nz_pad), block(32, 8);
   sum2_tile_kernel<<<grid, block, 0, ctx->stream>>>(u, u_y, u_z, layout_of(ctx, X3D2C_DIR_Y), layout_of(ctx, X3D2C_DIR_Z),
                                                     layout_of(ctx, X3D2C_DIR_X));
+  X3D2C_CHECK_LAUNCH(ctx);
+  return X3D2C_OK;
+}
+
+int x3d2c_sum_yzintox_lincomb(x3d2c_ctx* ctx, double* u, const double* u_y, const double* u_z, int store_u, double* out,
+                              const double* base, int n, const double* coef, const double* const* x, double c_u) {
+  X3D2C_ENTER(ctx);
+  X3D2C_REQUIRE(ctx && u && u_y && u_z && out && base && n >= 0 && n <= 3 && (n == 0 || (coef && x)),
+                "x3d2c_sum_yzintox_lincomb: bad argument");
+  X3D2C_REQUIRE(out != u, "x3d2c_sum_yzintox_lincomb: out aliases u");
+  for (int k = 0; k < n; ++k)
+    X3D2C_REQUIRE(x[k] && x[k] != out && x[k] != u, "x3d2c_sum_yzintox_lincomb: a term is null or aliases out / u");
+  if (ctx->strict) {  // the defining sequence, bit for bit
+    int rc = x3d2c_sum_yzintox(ctx, u, u_y, u_z);
+    if (rc) return rc;
+    double c[4];
+    const double* t[4];
+    for (int k = 0; k < n; ++k) { c[k] = coef[k]; t[k] = x[k]; }
+    c[n] = c_u;
+    t[n] = u;
+    return x3d2c_veclincomb(ctx, out, base, n + 1, c, t);
+  }
+  X3D2C_REQUIRE(ctx->nz_pad <= 65535, "x3d2c_sum_yzintox_lincomb: nz exceeds the grid limit");
+  SumLin q{};
+  q.base = base;
+  q.n = n;
+  q.c_s = c_u;
+  q.store = store_u ? 1 : 0;
+  for (int k = 0; k < n; ++k) { q.x[k] = x[k]; q.c[k] = coef[k]; }
+  const dim3 grid(ctx->nx_pad / SZ, ctx->ny_pad / SZ, ctx->nz_pad), block(32, 8);
+  sum2_lincomb_kernel<<<grid, block, 0, ctx->stream>>>(u, u_y, u_z, out, layout_of(ctx, X3D2C_DIR_Y),
+                                                       layout_of(ctx, X3D2C_DIR_Z), layout_of(ctx, X3D2C_DIR_X), q);
   X3D2C_CHECK_LAUNCH(ctx);
   return X3D2C_OK;
 }

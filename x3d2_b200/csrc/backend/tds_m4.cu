@@ -23,6 +23,7 @@ struct TdsParams4 {
   CUtensorMap in_a, in_b;    // SUM: two inputs; AXPY: in_b = y
   CUtensorMap out_a, out_b;  // DUAL: two outputs; AXPY: out_a = y
   int tiles, nb;  // tile coordinates: (lane0, 0, 0, group % nb, group / nb)
+  int n4;         // > 0: tiles are numbered with c4 fastest (extent n4), see tile_coords()
   Op oa, ob;
   // rank-split direction only: received halos (SZ, 4, NF, G) and carries (SZ, 3, NR, G)
   const double *halo_s, *halo_e, *from_prev, *from_next;
@@ -119,6 +120,26 @@ __device__ __forceinline__ void local_sweeps_w(const Op& o, const double (&w)[S 
   }
 }
 
+// tile -> (first lane, c3, c4). Default order: lane part, then c3, then c4 (tiles that run at the same time are
+// neighbours in the direction's own layout). With n4 > 0, c4 runs fastest: for a solve that stores into a foreign
+// layout (z lines -> y layout, y lines -> z layout) c4 is the row index of that layout, so the 64-byte pieces written
+// at the same time by neighbouring CTAs fall next to each other instead of one plane (2 MB) apart.
+template <int L>
+__device__ __forceinline__ void tile_coords(const int tile, const int nb, const int n4, int& l0, int& c3, int& c4) {
+  constexpr int tpg = SZ / L;
+  if (n4 > 0) {
+    c4 = tile % n4;
+    const int r = tile / n4;
+    c3 = r / tpg;
+    l0 = (r - c3 * tpg) * L;
+  } else {
+    const int grp = tile / tpg;
+    l0 = (tile - grp * tpg) * L;
+    c4 = grp / nb;
+    c3 = grp - c4 * nb;
+  }
+}
+
 template <int L, int NT, int MODE>
 struct Shape {
   static constexpr int NSLOT = MODE == SINGLE ? 1 : 2;
@@ -148,10 +169,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) tds_m4_kernel(const __grid_const
   const int b0 = tid, bm = tid - L + (q == 0 ? NT : 0), bp = tid + L - (q == nseg - 1 ? NT : 0);
   const unsigned bar0 = saddr(smem4 + cz + 2 * NR * NT), bar1 = bar0 + 8;
   auto issue_loads = [&](int buf, int tile) {  // thread 0
-    const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
+    int l0, c3, c4;
+    tile_coords<L>(tile, p.nb, DIST ? 0 : p.n4, l0, c3, c4);
     const unsigned bar = buf ? bar1 : bar0;
     mbar_expect_tx(bar, NLOAD * tile_bytes);
-    const int c4 = grp / p.nb, c3 = grp - c4 * p.nb;
     if (XT == 2) tma_load_5d(saddr(smem4 + buf * NSLOT * fd), &p.in_a, bar, 0, SZ * c3 + l0, 0, 0, c4);
     else tma_load_5d(saddr(smem4 + buf * NSLOT * fd), &p.in_a, bar, l0, 0, 0, c3, c4);
     if (NLOAD == 2) tma_load_5d(saddr(smem4 + (buf * NSLOT + 1) * fd), &p.in_b, bar, l0, 0, 0, c3, c4);
@@ -251,8 +272,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) tds_m4_kernel(const __grid_const
     const int nn = tile + 2 * gridDim.x;
     if (DIST && nn < p.tiles) stage_neighbours(buf, nn);  // the staging areas of this buffer are free
     if (tid == 0) {
-      const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
-      const int c4 = grp / p.nb, c3 = grp - c4 * p.nb;
+      int l0, c3, c4;
+      tile_coords<L>(tile, p.nb, DIST ? 0 : p.n4, l0, c3, c4);
       if (XT == 1) tma_store_5d(&p.out_a, saddr(smem4 + F0), 0, SZ * c3 + l0, 0, 0, c4);
       else tma_store_5d(&p.out_a, saddr(smem4 + (MODE == AXPY ? F1 : F0)), l0, 0, 0, c3, c4);
       if (MODE == DUAL) tma_store_5d(&p.out_b, saddr(smem4 + F1), l0, 0, 0, c3, c4);
@@ -591,6 +612,13 @@ int tds_m4(x3d2c_ctx* ctx, int dir, int mode, double* out_a, double* out_b, cons
     return mode == SINGLE ? dispatch_xt<SINGLE, 2>(ctx, p, L, NT, ta->tap_mask) : dispatch_xt<AXPY, 2>(ctx, p, L, NT, ta->tap_mask);
   }
   if (!map(&p.in_a, in_a, lay_in) || !map(&p.out_a, out_a, lay_out)) return X3D2C_EUNSUPPORTED;
+  {
+    // tile order with the foreign layout's row index fastest: measured SLOWER for the y <-> z stores of the pressure path
+    // (pressure correction 10.9 against 10.1 ms at 512^3), so it stays an experiment
+    static const bool swap = std::getenv("X3D2C_TILE_ORDER") != nullptr;
+    const bool yz = (dir == X3D2C_DIR_Z && lay_out == X3D2C_DIR_Y) || (dir == X3D2C_DIR_Y && lay_out == X3D2C_DIR_Z);
+    if (yz && !split && swap) p.n4 = G / p.nb;  // c4: y for z lines, z for y lines
+  }
   if (mode == SUM && !map(&p.in_b, in_b, lay_in)) return X3D2C_EUNSUPPORTED;
   if (mode == AXPY && !map(&p.in_b, in_b, lay_out)) return X3D2C_EUNSUPPORTED;  // y
   if (mode == DUAL && !map(&p.out_b, out_b, lay_out)) return X3D2C_EUNSUPPORTED;

@@ -355,6 +355,16 @@ class Backend {  // cuda_c_backend_t: every method is one deferred procedure of 
   void sum_yintox(Field& u, const Field& u_) { X3D2H_CALL(x3d2c_sum_yintox(ctx, u.dev, u_.dev)); }
   void sum_zintox(Field& u, const Field& u_) { X3D2H_CALL(x3d2c_sum_zintox(ctx, u.dev, u_.dev)); }
   void sum_yzintox(Field& u, const Field& u_y, const Field& u_z) { X3D2H_CALL(x3d2c_sum_yzintox(ctx, u.dev, u_y.dev, u_z.dev)); }
+  // sum_yzintox(u, u_y, u_z) + veclincomb(out, base, terms + (c_u, u)) in one pass
+  void sum_yzintox_lincomb(Field& u, const Field& u_y, const Field& u_z, bool store_u, Field& out, const Field& base,
+                           const std::vector<std::pair<double, const Field*>>& terms, double c_u) {
+    if (terms.size() > 3) fail("sum_yzintox_lincomb takes at most 3 terms");
+    double c[3];
+    const double* x[3];
+    for (size_t k = 0; k < terms.size(); ++k) { c[k] = terms[k].first; x[k] = terms[k].second->dev; }
+    X3D2H_CALL(x3d2c_sum_yzintox_lincomb(ctx, u.dev, u_y.dev, u_z.dev, store_u ? 1 : 0, out.dev, base.dev, (int)terms.size(),
+                                         c, x, c_u));
+  }
   void veccopy(Field& dst, const Field& src) {
     if (src.dir != dst.dir) fail("Called vector copy with incompatible fields");
     if (dst.dir == DIR_C) fail("veccopy does not support DIR_C fields");
@@ -889,22 +899,28 @@ class Sim {
   // solver.f90:291-389
   void transeq_default(Field& du, Field& dv, Field& dw, const Field& uu, const Field& vv, const Field& ww) {
     if (base_ops()) return transeq_default_base(du, dv, dw, uu, vv, ww);
+    Field *dy[3], *dz[3];
+    transeq_parts(du, dv, dw, dy, dz, uu, vv, ww);
+    // one pass adds the y and the z contributions (sum_yintox then sum_zintox, in the reference's order)
+    backend.sum_yzintox(du, *dy[0], *dz[0]); backend.sum_yzintox(dv, *dy[1], *dz[1]); backend.sum_yzintox(dw, *dy[2], *dz[2]);
+    for (int i = 0; i < 3; ++i) { allocator.release_block(dy[i]); allocator.release_block(dz[i]); }
+  }
+  // transeq_default without its final sums: (du, dv, dw) hold the x contribution, dy / dz (blocks of the allocator, to be
+  // released by the caller) the y and z contributions in their own layouts
+  void transeq_parts(Field& du, Field& dv, Field& dw, Field* dy[3], Field* dz[3], const Field& uu, const Field& vv,
+                     const Field& ww) {
     Allocator& A = allocator;
     backend.transeq_x(du, dv, dw, uu, vv, ww, nu, xdirps);
     // u, v, w into both pencil layouts with one read each (reference: 3 x reorder X2Y here, 3 x reorder X2Z below)
     Field *u_y = A.get_block(DIR_Y), *v_y = A.get_block(DIR_Y), *w_y = A.get_block(DIR_Y);
     Field *u_z = A.get_block(DIR_Z), *v_z = A.get_block(DIR_Z), *w_z = A.get_block(DIR_Z);
     backend.reorder_x2yz(*u_y, *u_z, uu); backend.reorder_x2yz(*v_y, *v_z, vv); backend.reorder_x2yz(*w_y, *w_z, ww);
-    Field *du_y = A.get_block(DIR_Y), *dv_y = A.get_block(DIR_Y), *dw_y = A.get_block(DIR_Y);
-    backend.transeq_y(*du_y, *dv_y, *dw_y, *u_y, *v_y, *w_y, nu, ydirps);
+    for (int i = 0; i < 3; ++i) dy[i] = A.get_block(DIR_Y);
+    backend.transeq_y(*dy[0], *dy[1], *dy[2], *u_y, *v_y, *w_y, nu, ydirps);
     A.release_block(u_y); A.release_block(v_y); A.release_block(w_y);
-    Field *du_z = A.get_block(DIR_Z), *dv_z = A.get_block(DIR_Z), *dw_z = A.get_block(DIR_Z);
-    backend.transeq_z(*du_z, *dv_z, *dw_z, *u_z, *v_z, *w_z, nu, zdirps);
+    for (int i = 0; i < 3; ++i) dz[i] = A.get_block(DIR_Z);
+    backend.transeq_z(*dz[0], *dz[1], *dz[2], *u_z, *v_z, *w_z, nu, zdirps);
     A.release_block(u_z); A.release_block(v_z); A.release_block(w_z);
-    // one pass adds the y and the z contributions (sum_yintox then sum_zintox, in the reference's order)
-    backend.sum_yzintox(du, *du_y, *du_z); backend.sum_yzintox(dv, *dv_y, *dv_z); backend.sum_yzintox(dw, *dw_y, *dw_z);
-    A.release_block(du_y); A.release_block(dv_y); A.release_block(dw_y);
-    A.release_block(du_z); A.release_block(dv_z); A.release_block(dw_z);
   }
 
   // vector_calculus.f90:142-246
@@ -1086,13 +1102,29 @@ class Sim {
     if (terms.empty()) { if (&out != &base) backend.veccopy(out, base); return; }
     backend.veclincomb(out, base, terms);
   }
-  void runge_kutta(Field* curr[3], Field* deriv[3], double dt_) {
+  // dy / dz != nullptr: deriv[i] still lacks its y and z contributions (transeq_parts); the sums are taken in the same
+  // pass as the update (x3d2c_sum_yzintox_lincomb). The derivative is always the last term of the update.
+  void update_with_deriv(Field& out, const Field& base, Terms terms, Field& d, Field* dy, Field* dz, bool keep_d) {
+    if (!dy) return lincomb_or_copy(out, base, terms);
+    const double c_d = terms.back().first;
+    terms.pop_back();
+    Terms kept;
+    for (auto& t : terms) if (t.first != 0.0) kept.push_back(t);
+    if (c_d == 0.0 || kept.size() > 3 || &out == &d) {  // not expressible in the fused form
+      backend.sum_yzintox(d, *dy, *dz);
+      kept.push_back({c_d, &d});
+      return lincomb_or_copy(out, base, kept);
+    }
+    backend.sum_yzintox_lincomb(d, *dy, *dz, keep_d, out, base, kept, c_d);
+  }
+  void runge_kutta(Field* curr[3], Field* deriv[3], double dt_, Field* const* dy = nullptr, Field* const* dz = nullptr) {
     if (ti_istage == ti_nstage) {
       for (int i = 0; i < 3; ++i) {
         Terms terms;
         for (int j = 1; j <= ti_nstage - 1; ++j) terms.push_back({ti_rk_b[j][ti_nstage] * dt_, olds[i][j + 1]});
         terms.push_back({ti_rk_b[ti_nstage][ti_nstage] * dt_, deriv[i]});
-        lincomb_or_copy(*curr[i], ti_nstage > 1 ? *olds[i][1] : *curr[i], terms);
+        update_with_deriv(*curr[i], ti_nstage > 1 ? *olds[i][1] : *curr[i], terms, *deriv[i], dy ? dy[i] : nullptr,
+                          dz ? dz[i] : nullptr, false);
       }
       ti_istage = 1;
     } else {
@@ -1104,7 +1136,8 @@ class Sim {
         std::swap(olds[i][ti_istage + 1], deriv[i]);  // olds(istage + 1) <- deriv
         Terms terms;
         for (int j = 1; j <= ti_istage; ++j) terms.push_back({ti_rk_a[j][ti_istage][ti_nstage] * dt_, olds[i][j + 1]});
-        lincomb_or_copy(*curr[i], *olds[i][1], terms);
+        update_with_deriv(*curr[i], *olds[i][1], terms, *olds[i][ti_istage + 1], dy ? dy[i] : nullptr, dz ? dz[i] : nullptr,
+                          true);
       }
       ti_istage = ti_istage + 1;
     }
@@ -1133,10 +1166,18 @@ class Sim {
     Field* curr[3] = {u, v, w};
     for (int sub = 1; sub <= ti_nstage; ++sub) {
       Field* deriv[3] = {allocator.get_block(DIR_X), allocator.get_block(DIR_X), allocator.get_block(DIR_X)};
-      transeq_default(*deriv[0], *deriv[1], *deriv[2], *u, *v, *w);
-      if (base_ops()) { if (ti_is_ab) adams_bashforth_base(curr, deriv, dt); else runge_kutta_base(curr, deriv, dt); }
-      else if (ti_is_ab) adams_bashforth(curr, deriv, dt);
-      else runge_kutta(curr, deriv, dt);
+      if (!base_ops() && !ti_is_ab && !(cfg.flags & X3D2C_FLAG_STRICT)) {  // Runge-Kutta, fast mode: the y / z sums of
+        // transeq are taken inside the update pass
+        Field *dy[3], *dz[3];
+        transeq_parts(*deriv[0], *deriv[1], *deriv[2], dy, dz, *u, *v, *w);
+        runge_kutta(curr, deriv, dt, dy, dz);
+        for (int i = 0; i < 3; ++i) { allocator.release_block(dy[i]); allocator.release_block(dz[i]); }
+      } else {
+        transeq_default(*deriv[0], *deriv[1], *deriv[2], *u, *v, *w);
+        if (base_ops()) { if (ti_is_ab) adams_bashforth_base(curr, deriv, dt); else runge_kutta_base(curr, deriv, dt); }
+        else if (ti_is_ab) adams_bashforth(curr, deriv, dt);
+        else runge_kutta(curr, deriv, dt);
+      }
       u = curr[0]; v = curr[1]; w = curr[2];  // the integrators may continue in another block
       for (int i = 0; i < 3; ++i) allocator.release_block(deriv[i]);
       pressure_correction(*u, *v, *w);
