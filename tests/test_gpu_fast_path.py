@@ -108,7 +108,8 @@ RDR_CASES = [(2, 0, 23), (2, 0, 24), (2, 32, 0), (2, 42, 23), (3, 43, 0), (3, 23
 
 
 @pytest.mark.parametrize("dims,bcs,env", [((128, 64, 256), None, {}), ((128, 128, 256), None, {"X3D2C_FORCE_DIST": "1"}),
-                                          ((96, 64, 80), None, {}), ((65, 64, 64), ((2, 2), (0, 0), (1, 1)), {})])
+                                          ((96, 64, 80), None, {}), ((65, 64, 64), ((2, 2), (0, 0), (1, 1)), {}),
+                                          ((1024, 64, 64), None, {}), ((512, 64, 64), None, {}), ((256, 64, 64), None, {})])
 @pytest.mark.parametrize("strict", [False, True], ids=["fast", "strict"])
 def test_tds_through_reorders(oracle, x3d2, dims, bcs, env, strict, monkeypatch):
     """x3d2c_tds_solve_r / _sum_r / _dual_r == reorder -> operator(s) -> reorder. Host arrays are Cartesian, so the
