@@ -111,6 +111,16 @@ int x3d2c_field_fill(x3d2c_ctx* ctx, double* dev, double c);
 /* copy_data_to_f / copy_f_to_data (src/backend/backend.f90:327-349): whole padded block, ngrid doubles */
 int x3d2c_copy_data_to_f(x3d2c_ctx* ctx, double* dev, const double* host_data);
 int x3d2c_copy_f_to_data(x3d2c_ctx* ctx, double* host_data, const double* dev);
+/* extension - I/O lanes: the same copies, asynchronous, on dedicated copy streams that are ordered against the
+ * context's stream with events, so that a caller can stream independent batches through the device (the upload of
+ * batch b + 1 and the download of batch b - 1 overlap the kernels of batch b). lane: 0 = the context's stream,
+ * 1 = upload stream, 2 = download stream; ev: 0..15. The host arrays must be page-locked and stay valid until the lane
+ * has been synchronised. x3d2c_lane_wait on an event that was never recorded is a no-op. */
+int x3d2c_copy_data_to_f_async(x3d2c_ctx* ctx, double* dev, const double* host_pinned, int lane);
+int x3d2c_copy_f_to_data_async(x3d2c_ctx* ctx, double* host_pinned, const double* dev, int lane);
+int x3d2c_lane_record(x3d2c_ctx* ctx, int lane, int ev);
+int x3d2c_lane_wait(x3d2c_ctx* ctx, int lane, int ev);
+int x3d2c_lane_sync(x3d2c_ctx* ctx, int lane);
 
 /* ---- alloc_tdsops (src/backend/backend.f90:351-372; upload pattern of src/backend/cuda/tdsops.f90:31-90).
  * The host computes the tables with tdsops_init (src/tdsops.f90:63-203) and passes them in:

@@ -80,6 +80,13 @@ int x3d2h_set_velocity(x3d2h_sim* sim, const double* u, const double* v, const d
 int x3d2h_get_velocity(x3d2h_sim* sim, double* u, double* v, double* w);
 /* base_case_t%run loop body (src/case/base_case.f90:246-289), nsteps full time steps, asynchronous */
 int x3d2h_step(x3d2h_sim* sim, int nsteps);
+/* n independent batches, one time step each: batch b = upload (u_in, v_in, w_in) -> step -> download into (u_out, v_out,
+ * w_out); uploads and downloads run on the backend's copy lanes and overlap the kernels of the neighbouring batches.
+ * Page-locked host arrays of the local vertex extents; grids that need padding are refused. Returns after everything
+ * has completed. (The same host arrays serve every batch: this is the streaming form of set_velocity / step /
+ * get_velocity for benchmarks and ensembles.) */
+int x3d2h_step_batches(x3d2h_sim* sim, int n_batches, const double* u_in, const double* v_in, const double* w_in,
+                       double* u_out, double* v_out, double* w_out);
 int x3d2h_sync(x3d2h_sim* sim);
 /* monitoring_t%write_step (src/postprocess/monitoring.f90:46-90): enstrophy, kinetic energy, div_u max, mean */
 int x3d2h_monitor(x3d2h_sim* sim, double out[4]);

@@ -67,3 +67,28 @@ def test_derived_fields_and_slice(oracle, x3d2):
     ox, oy, oz = ref.curl(u, v, w)
     assert rel(sim.derived("vorticity", grads), np.sqrt(ox * ox + oy * oy + oz * oz)) < TOL
     sim.close()
+
+
+def test_step_batches_equals_set_step_get(x3d2):
+    """Sim.step_batches (uploads / downloads on copy lanes, overlapped with the kernels of the neighbouring batches) gives
+    every batch exactly what set_uvw -> step -> get_uvw gives; padded grids and Adams-Bashforth are refused."""
+    n = 64
+    sim = x3d2.Sim((n, n, n))
+    sim.init_tgv()
+    sim.step(2)
+    ins = [a.copy() for a in sim.get_uvw()]
+    sim.set_uvw(*ins)
+    sim.step(1)
+    exp = sim.get_uvw()
+    outs = [np.full(sim.shape(), np.nan) for _ in range(3)]
+    for nb in (1, 2, 5):
+        for o in outs:
+            o.fill(np.nan)
+        sim.step_batches(nb, ins, outs)
+        assert all(np.array_equal(o, e) for o, e in zip(outs, exp)), nb
+    sim.close()
+    sim = x3d2.Sim((48, 40, 36))  # nx - 1 not a multiple of 32: padded blocks
+    a = [np.zeros(sim.shape()) for _ in range(3)]
+    with pytest.raises(RuntimeError, match="needs padding"):
+        sim.step_batches(1, a, a)
+    sim.close()

@@ -199,6 +199,13 @@ class Sim:
     def step(self, n=1):
         _chk(self._h.x3d2h_step(self.h, n))
 
+    def step_batches(self, n, ins, outs):
+        """n independent batches, one step each: upload `ins` (u, v, w) -> step -> download into `outs`; the copies overlap
+        the kernels of the neighbouring batches. Arrays: C-contiguous float64 of self.shape(), page-locked for real overlap."""
+        ins = [_out_ok(a, self.shape()) for a in ins]
+        outs = [_out_ok(a, self.shape()) for a in outs]
+        _chk(self._h.x3d2h_step_batches(self.h, n, *[_p(a) for a in ins], *[_p(a) for a in outs]))
+
     def sync(self):
         _chk(self._h.x3d2h_sync(self.h))
 

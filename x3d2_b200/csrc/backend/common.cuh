@@ -116,6 +116,8 @@ struct x3d2c_ctx {
   x3d2c_config cfg;
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t lane[3] = {nullptr, nullptr, nullptr};  // I/O lanes (x3d2c.h): [0] = stream, [1] upload, [2] download; created on use
+  cudaEvent_t lane_ev[16] = {nullptr};
   int strict = 0;
   int force_dist = 0;  // X3D2C_FORCE_DIST: run the rank-split fast path on a single rank (self exchange); tests, profiling
   int nx_pad = 0, ny_pad = 0, nz_pad = 0;

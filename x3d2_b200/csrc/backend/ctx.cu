@@ -120,6 +120,10 @@ int x3d2c_destroy(x3d2c_ctx* ctx) {
   if (!ctx) return X3D2C_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (int l = 1; l <= 2; ++l)
+    if (ctx->lane[l]) { cudaStreamSynchronize(ctx->lane[l]); cudaStreamDestroy(ctx->lane[l]); }
+  for (auto& e : ctx->lane_ev)
+    if (e) cudaEventDestroy(e);
   release_peer_halo(ctx);
   nccl_finalize(ctx);
   for (int i = 0; i < 6; ++i)
@@ -179,6 +183,62 @@ int x3d2c_copy_f_to_data(x3d2c_ctx* ctx, double* host_data, const double* dev) {
   X3D2C_ENTER(ctx);
   X3D2C_CHECK_CUDA(cudaMemcpyAsync(host_data, dev, sizeof(double) * ctx->ngrid, cudaMemcpyDeviceToHost, ctx->stream));
   X3D2C_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return X3D2C_OK;
+}
+
+// ---- I/O lanes (x3d2c.h)
+static int lane_stream(x3d2c_ctx* ctx, int lane, cudaStream_t* s) {
+  X3D2C_REQUIRE(lane >= 0 && lane <= 2, "x3d2c lane: lane must be 0 (compute), 1 (upload) or 2 (download)");
+  if (lane == 0) { *s = ctx->stream; return X3D2C_OK; }
+  if (!ctx->lane[lane]) X3D2C_CHECK_CUDA(cudaStreamCreateWithFlags(&ctx->lane[lane], cudaStreamNonBlocking));
+  *s = ctx->lane[lane];
+  return X3D2C_OK;
+}
+int x3d2c_copy_data_to_f_async(x3d2c_ctx* ctx, double* dev, const double* host_pinned, int lane) {
+  X3D2C_ENTER(ctx);
+  X3D2C_REQUIRE(ctx && dev && host_pinned, "x3d2c_copy_data_to_f_async: null argument");
+  cudaStream_t s;
+  int rc = lane_stream(ctx, lane, &s);
+  if (rc) return rc;
+  X3D2C_CHECK_CUDA(cudaMemcpyAsync(dev, host_pinned, sizeof(double) * ctx->ngrid, cudaMemcpyHostToDevice, s));
+  return X3D2C_OK;
+}
+int x3d2c_copy_f_to_data_async(x3d2c_ctx* ctx, double* host_pinned, const double* dev, int lane) {
+  X3D2C_ENTER(ctx);
+  X3D2C_REQUIRE(ctx && dev && host_pinned, "x3d2c_copy_f_to_data_async: null argument");
+  cudaStream_t s;
+  int rc = lane_stream(ctx, lane, &s);
+  if (rc) return rc;
+  X3D2C_CHECK_CUDA(cudaMemcpyAsync(host_pinned, dev, sizeof(double) * ctx->ngrid, cudaMemcpyDeviceToHost, s));
+  return X3D2C_OK;
+}
+int x3d2c_lane_record(x3d2c_ctx* ctx, int lane, int ev) {
+  X3D2C_ENTER(ctx);
+  X3D2C_REQUIRE(ctx && ev >= 0 && ev < 16, "x3d2c_lane_record: ev must be 0..15");
+  cudaStream_t s;
+  int rc = lane_stream(ctx, lane, &s);
+  if (rc) return rc;
+  if (!ctx->lane_ev[ev]) X3D2C_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->lane_ev[ev], cudaEventDisableTiming));
+  X3D2C_CHECK_CUDA(cudaEventRecord(ctx->lane_ev[ev], s));
+  return X3D2C_OK;
+}
+int x3d2c_lane_wait(x3d2c_ctx* ctx, int lane, int ev) {
+  X3D2C_ENTER(ctx);
+  X3D2C_REQUIRE(ctx && ev >= 0 && ev < 16, "x3d2c_lane_wait: ev must be 0..15");
+  cudaStream_t s;
+  int rc = lane_stream(ctx, lane, &s);
+  if (rc) return rc;
+  if (!ctx->lane_ev[ev]) return X3D2C_OK;  // never recorded: nothing to wait for
+  X3D2C_CHECK_CUDA(cudaStreamWaitEvent(s, ctx->lane_ev[ev], 0));
+  return X3D2C_OK;
+}
+int x3d2c_lane_sync(x3d2c_ctx* ctx, int lane) {
+  X3D2C_ENTER(ctx);
+  X3D2C_REQUIRE(ctx, "x3d2c_lane_sync: null argument");
+  cudaStream_t s;
+  int rc = lane_stream(ctx, lane, &s);
+  if (rc) return rc;
+  X3D2C_CHECK_CUDA(cudaStreamSynchronize(s));
   return X3D2C_OK;
 }
 

@@ -186,6 +186,15 @@ int x3d2h_step(x3d2h_sim* sim, int nsteps) {
   for (int i = 0; i < nsteps; ++i) sim->s->step();
   H_CATCH
 }
+int x3d2h_step_batches(x3d2h_sim* sim, int n_batches, const double* u_in, const double* v_in, const double* w_in,
+                       double* u_out, double* v_out, double* w_out) {
+  H_TRY
+  const double* in[3] = {u_in, v_in, w_in};
+  double* out[3] = {u_out, v_out, w_out};
+  if (!u_in || !v_in || !w_in || !u_out || !v_out || !w_out) fail("x3d2h_step_batches: null argument");
+  sim->s->step_batches(n_batches, in, out);
+  H_CATCH
+}
 int x3d2h_sync(x3d2h_sim* sim) { H_TRY X3D2H_CALL(x3d2c_sync(sim->s->ctx)); H_CATCH }
 int x3d2h_monitor(x3d2h_sim* sim, double out[4]) {
   H_TRY

@@ -1184,6 +1184,50 @@ class Sim {
     }
   }
 
+  // Independent batches streamed through one time step each (ensemble members, parameter sweeps): batch b's velocity is
+  // uploaded from host_in, advanced by one step, and downloaded to host_out. The upload of batch b + 1 and the download
+  // of batch b - 1 run on the backend's copy lanes while the kernels of batch b run on its stream; staging blocks in the
+  // Cartesian layout are double-buffered. Host arrays: un-padded DIR_C blocks (the grid must need no padding), page-locked.
+  void step_batches(int n_batches, const double* const host_in[3], double* const host_out[3]) {
+    if (!is_unpadded(VERT)) fail("step_batches: the grid needs padding; use set_velocity / step / get_velocity");
+    if (ti_is_ab) fail("step_batches: Adams-Bashforth carries history from step to step; batches are independent");
+    Allocator& A = allocator;
+    Field* in[2][3];
+    Field* out[2][3];
+    for (int b = 0; b < 2; ++b)
+      for (int i = 0; i < 3; ++i) { in[b][i] = A.get_block(DIR_C); out[b][i] = A.get_block(DIR_C); }
+    // events: 0,1 upload of set b done; 2,3 staging-in of set b consumed; 4,5 results staged in set b; 6,7 download of set b done
+    auto upload = [&](int b) {
+      const int sset = b & 1;
+      X3D2H_CALL(x3d2c_lane_wait(ctx, 1, 2 + sset));  // the batch that used this set before has been reordered out of it
+      for (int i = 0; i < 3; ++i) X3D2H_CALL(x3d2c_copy_data_to_f_async(ctx, in[sset][i]->dev, host_in[i], 1));
+      X3D2H_CALL(x3d2c_lane_record(ctx, 1, 0 + sset));
+    };
+    if (n_batches > 0) upload(0);
+    Field* state[3];
+    for (int b = 0; b < n_batches; ++b) {
+      const int sset = b & 1;
+      if (b + 1 < n_batches) upload(b + 1);
+      X3D2H_CALL(x3d2c_lane_wait(ctx, 0, 0 + sset));
+      state[0] = u; state[1] = v; state[2] = w;
+      for (int i = 0; i < 3; ++i) { backend.reorder(*state[i], *in[sset][i], RDR_C2X); state[i]->data_loc = VERT; }
+      X3D2H_CALL(x3d2c_lane_record(ctx, 0, 2 + sset));
+      step();
+      X3D2H_CALL(x3d2c_lane_wait(ctx, 0, 6 + sset));  // the previous download from this set has finished
+      state[0] = u; state[1] = v; state[2] = w;
+      for (int i = 0; i < 3; ++i) backend.reorder(*out[sset][i], *state[i], RDR_X2C);
+      X3D2H_CALL(x3d2c_lane_record(ctx, 0, 4 + sset));
+      X3D2H_CALL(x3d2c_lane_wait(ctx, 2, 4 + sset));
+      for (int i = 0; i < 3; ++i) X3D2H_CALL(x3d2c_copy_f_to_data_async(ctx, host_out[i], out[sset][i]->dev, 2));
+      X3D2H_CALL(x3d2c_lane_record(ctx, 2, 6 + sset));
+    }
+    X3D2H_CALL(x3d2c_lane_sync(ctx, 2));
+    X3D2H_CALL(x3d2c_lane_sync(ctx, 1));
+    X3D2H_CALL(x3d2c_sync(ctx));
+    for (int b = 0; b < 2; ++b)
+      for (int i = 0; i < 3; ++i) { A.release_block(in[b][i]); A.release_block(out[b][i]); }
+  }
+
   // ---- host <-> field helpers: local Cartesian un-padded arrays of the data_loc extents
   void pad(std::vector<double>& padded, const double* compact, int data_loc) const {
     int dims[3];
