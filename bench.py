@@ -30,11 +30,11 @@ sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_PT = {"transeq": 48, "tds_solve": 16}  # per transeq_{x,y,z} / tds_solve call
 STEP_BYTES_PER_PT = 3888                                # whole RK3 step, the reference's operator graph
-# What this backend's operator graph moves per RK3 step (DESIGN.md "bytes per step"): per stage transeq 216 (3 x 48
-# kernels, 3 one-read x2y+x2z reorders of 24), divergence 112 (x solves store in the y layout: 3 x 16; y 24 + 16; z 24),
-# Poisson 152, gradient + correction 152 (c2z pass 16, z 24, y 24 + 16, x solves load from the y layout: 3 x 24); the
-# y / z sums of transeq fused with the RK3 update: 3 components x (48 + 56 + 56) per step
-STEP_BYTES_MOVED_PER_PT = 3 * (216 + 112 + 152 + 152) + 3 * (48 + 56 + 56)
+# What this backend's operator graph moves per RK3 step (DESIGN.md "bytes per step"): per stage transeq 192 (3 x 48
+# kernels - the y sweep reads the x layout itself - and 3 x2z reorders of 16), divergence 112 (x solves store in the y
+# layout: 3 x 16; y 24 + 16; z 24), Poisson 152, gradient + correction 152 (c2z pass 16, z 24, y 24 + 16, x solves load from
+# the y layout: 3 x 24); the y / z sums of transeq fused with the RK3 update: 3 components x (48 + 56 + 56) per step
+STEP_BYTES_MOVED_PER_PT = 3 * (192 + 112 + 152 + 152) + 3 * (48 + 56 + 56)
 
 
 def grid_for(n_gpus, base):

@@ -139,6 +139,16 @@ int x3d2c_tdsops_destroy(x3d2c_ctx* ctx, x3d2c_tdsops* ops);
 int x3d2c_transeq(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, const double* u, const double* v,
                   const double* w, double nu, const x3d2c_tdsops* der1st, const x3d2c_tdsops* der1st_sym,
                   const x3d2c_tdsops* der2nd, const x3d2c_tdsops* der2nd_sym);
+/* extension: reorder(u, v, w with rdr_in) followed by transeq in `dir` (transeq_default reorders the velocity before the
+ * y and z sweeps, src/solver.f90:325-327,355-357); rdr_in = 0 is x3d2c_transeq. The fast path lets the y sweep read the
+ * x-layout velocity directly. u, v, w are in the layout rdr_in starts from, du, dv, dw in DIR_`dir`. */
+int x3d2c_transeq_r(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, const double* u, const double* v,
+                    const double* w, double nu, const x3d2c_tdsops* der1st, const x3d2c_tdsops* der1st_sym,
+                    const x3d2c_tdsops* der2nd, const x3d2c_tdsops* der2nd_sym, int rdr_in);
+/* 1 when x3d2c_transeq_r with these arguments runs without a reorder pass (the caller may then skip producing the
+ * reordered copies another way), 0 otherwise */
+int x3d2c_transeq_r_fused(x3d2c_ctx* ctx, int dir, const x3d2c_tdsops* der1st, const x3d2c_tdsops* der1st_sym,
+                          const x3d2c_tdsops* der2nd, const x3d2c_tdsops* der2nd_sym, int rdr_in);
 
 /* ---- tds_solve (src/backend/backend.f90:108-126, cuda/backend.f90:449-521). data_loc bookkeeping
  * (move_data_loc) stays on the caller's field_t. */

@@ -75,7 +75,7 @@ def test_every_binding_matches_the_header():
     assert len(binds) >= 50, len(binds)
     # what the shim does NOT bind: the fused extension entry points (a Fortran solver that does not know them keeps
     # calling the base operators) and the debugging / bench helpers
-    extensions = {"x3d2c_tds_solve_sum", "x3d2c_tds_solve_dual", "x3d2c_tds_solve_axpy", "x3d2c_tds_solve_r",
+    extensions = {"x3d2c_transeq_r", "x3d2c_transeq_r_fused", "x3d2c_tds_solve_sum", "x3d2c_tds_solve_dual", "x3d2c_tds_solve_axpy", "x3d2c_tds_solve_r",
                   "x3d2c_tds_solve_sum_r", "x3d2c_tds_solve_dual_r", "x3d2c_tds_solve_axpy_r", "x3d2c_reorder_x2yz", "x3d2c_sum_yzintox", "x3d2c_sum_yzintox_lincomb",
                   "x3d2c_veclincomb", "x3d2c_copy_data_to_f_async", "x3d2c_copy_f_to_data_async", "x3d2c_lane_record",
                       "x3d2c_lane_wait", "x3d2c_lane_sync", "x3d2c_launch_count", "x3d2c_stream", "x3d2c_version", "x3d2c_poisson_get_spectrum"}

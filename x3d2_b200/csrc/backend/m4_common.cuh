@@ -77,8 +77,9 @@ bool tile_shape(int n, int* L, int* NT);
 bool make_map5(CUtensorMap* m, const double* field, int layout_dir, int line_dir, int L, int nseg,
                const x3d2c_ctx* ctx, int* nb);
 
-// x-line tiles (16 x per 128-byte row, L lanes in y, nseg segments) of a field stored in DIR_Y, as a 5-D tensor
-// (x in segment, y, half of the 32-x row, x block, z) with 128-byte swizzle (tds_m4.cu: XT kernels)
-bool make_map_xt(CUtensorMap* m, const double* field, int layout_dir, int L, int nseg, const x3d2c_ctx* ctx);
+// Line tiles whose line runs along the CONTIGUOUS index of the field's layout: x lines of a DIR_Y field (16 x per
+// 128-byte row, L lanes in y) or y lines of a DIR_X field (16 y per row, L lanes in x), as a 5-D tensor
+// (point in segment, lane, half of the 32-point row, block, z) with 128-byte swizzle (tds_m4.cu: XT kernels)
+bool make_map_xt(CUtensorMap* m, const double* field, int layout_dir, int line_dir, int L, int nseg, const x3d2c_ctx* ctx);
 
 }  // namespace m4

@@ -87,16 +87,23 @@ bool tile_shape(int n, int* L, int* NT) {
   }
 }
 
-bool make_map_xt(CUtensorMap* m, const double* field, int layout_dir, int L, int nseg, const x3d2c_ctx* ctx) {
+bool make_map_xt(CUtensorMap* m, const double* field, int layout_dir, int line_dir, int L, int nseg, const x3d2c_ctx* ctx) {
   EncodeFn enc = encode_fn();
-  if (!enc || layout_dir != X3D2C_DIR_Y) return false;
-  const cuuint64_t R = (cuuint64_t)SZ * 8;  // one row of 32 x
-  const cuuint64_t nxb = ctx->nx_pad / SZ, nyp = ctx->ny_pad, nz = ctx->nz_pad;
-  if ((cuuint64_t)nseg != 2 * nxb) return false;  // the line is the whole padded x extent
-  // DIR_Y: idx = x_l + 32 * (y + ny_pad * (xb + nxb * z))
-  const cuuint64_t dims[5] = {16, nyp, 2, nxb, nz};
-  const cuuint64_t strides[4] = {R, 128, nyp * R, nxb * nyp * R};
-  const cuuint32_t box[5] = {16, (cuuint32_t)L, 2, (cuuint32_t)nxb, 1};
+  if (!enc) return false;
+  const cuuint64_t R = (cuuint64_t)SZ * 8;  // one row of 32 points
+  const cuuint64_t nxp = ctx->nx_pad, nyp = ctx->ny_pad, nz = ctx->nz_pad;
+  cuuint64_t lanes, blocks;  // extent of the lane index, 32-point blocks along the line
+  if (line_dir == X3D2C_DIR_X && layout_dir == X3D2C_DIR_Y) {         // idx = x_l + 32 * (y + ny_pad * (xb + nxb * z))
+    lanes = nyp; blocks = nxp / SZ;
+  } else if (line_dir == X3D2C_DIR_Y && layout_dir == X3D2C_DIR_X) {  // idx = y_l + 32 * (x + nx_pad * (yb + nyb * z))
+    lanes = nxp; blocks = nyp / SZ;
+  } else {
+    return false;
+  }
+  if ((cuuint64_t)nseg != 2 * blocks) return false;  // the line is the whole padded extent
+  const cuuint64_t dims[5] = {16, lanes, 2, blocks, nz};
+  const cuuint64_t strides[4] = {R, 128, lanes * R, blocks * lanes * R};
+  const cuuint32_t box[5] = {16, (cuuint32_t)L, 2, (cuuint32_t)blocks, 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, const_cast<double*>(field), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,

@@ -372,7 +372,7 @@ int tds_pair_m3(x3d2c_ctx* ctx, int dir, int mode, double* out_a, double* out_b,
                 const double* in_b, const x3d2c_tdsops* ta, const x3d2c_tdsops* tb, double scale_a);
 int transeq_m4(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, const double* u, const double* v,
                const double* w, double nu, const x3d2c_tdsops* der1st, const x3d2c_tdsops* der1st_sym,
-               const x3d2c_tdsops* der2nd, const x3d2c_tdsops* der2nd_sym);
+               const x3d2c_tdsops* der2nd, const x3d2c_tdsops* der2nd_sym, int lay_in, bool dry_run = false);
 int transeq_m3(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, const double* u, const double* v,
                const double* w, double nu, const x3d2c_tdsops* der1st, const x3d2c_tdsops* der1st_sym,
                const x3d2c_tdsops* der2nd, const x3d2c_tdsops* der2nd_sym);
@@ -544,7 +544,7 @@ int x3d2c_transeq(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, c
                     der2nd_sym->n_tds == der1st->n_tds, "x3d2c_transeq: operators must share n_tds == n_rhs");
   const int P = ctx->cfg.nproc_dir[dir - 1];
   if (!ctx->strict) {
-    int rc = transeq_m4(ctx, dir, du, dv, dw, u, v, w, nu, der1st, der1st_sym, der2nd, der2nd_sym);  // TMA tiles
+    int rc = transeq_m4(ctx, dir, du, dv, dw, u, v, w, nu, der1st, der1st_sym, der2nd, der2nd_sym, dir);  // TMA tiles
     const bool tma = rc != X3D2C_EUNSUPPORTED;
     if (!tma) rc = transeq_m3(ctx, dir, du, dv, dw, u, v, w, nu, der1st, der1st_sym, der2nd, der2nd_sym);
     if (rc != X3D2C_EUNSUPPORTED) {
@@ -622,6 +622,46 @@ int x3d2c_transeq(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, c
 // the roles (du, dud, d2u) of transeq_dist_component (:299-338). `sync`: exchange the velocity halos too (the first
 // species of a direction); otherwise the halos received by the previous call are reused, as in the reference.
 // Reference-order kernels (one scalar per call has a third of the arithmetic intensity of the fused momentum kernel).
+
+int x3d2c_transeq_r_fused(x3d2c_ctx* ctx, int dir, const x3d2c_tdsops* der1st, const x3d2c_tdsops* der1st_sym,
+                          const x3d2c_tdsops* der2nd, const x3d2c_tdsops* der2nd_sym, int rdr_in) {
+  if (!ctx || !der1st || !der1st_sym || !der2nd || !der2nd_sym || dir < 1 || dir > 3 || ctx->strict) return 0;
+  if (!rdr_in || rdr_in % 10 != dir || rdr_in / 10 < 1 || rdr_in / 10 > 3) return 0;
+  static const bool off = std::getenv("X3D2C_NO_XT") != nullptr || std::getenv("X3D2C_NO_TRANSEQ_XT") != nullptr;
+  if (off) return 0;
+  double* f = ctx->halo;  // any valid device address: the dry run only encodes tensor maps
+  return transeq_m4(ctx, dir, f, f, f, f, f, f, 1.0, der1st, der1st_sym, der2nd, der2nd_sym, rdr_in / 10, true) == X3D2C_OK;
+}
+
+int x3d2c_transeq_r(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, const double* u, const double* v,
+                    const double* w, double nu, const x3d2c_tdsops* der1st, const x3d2c_tdsops* der1st_sym,
+                    const x3d2c_tdsops* der2nd, const x3d2c_tdsops* der2nd_sym, int rdr_in) {
+  X3D2C_ENTER(ctx);
+  X3D2C_REQUIRE(ctx && du && dv && dw && u && v && w && der1st && der1st_sym && der2nd && der2nd_sym,
+                "x3d2c_transeq_r: null argument");
+  X3D2C_REQUIRE(dir >= 1 && dir <= 3, "x3d2c_transeq_r: dir must be DIR_X/Y/Z");
+  if (!rdr_in) return x3d2c_transeq(ctx, dir, du, dv, dw, u, v, w, nu, der1st, der1st_sym, der2nd, der2nd_sym);
+  X3D2C_REQUIRE(rdr_in % 10 == dir && rdr_in / 10 >= 1 && rdr_in / 10 <= 3 && rdr_in / 10 != dir,
+                "x3d2c_transeq_r: rdr_in must be a reorder code that ends in dir");
+  static const bool trace = std::getenv("X3D2C_TRACE") != nullptr;
+  if (!ctx->strict) {  // y lines reading the x layout through swizzled tiles (transeq_m4.cu)
+    int rc = transeq_m4(ctx, dir, du, dv, dw, u, v, w, nu, der1st, der1st_sym, der2nd, der2nd_sym, rdr_in / 10);
+    if (rc != X3D2C_EUNSUPPORTED) {
+      if (trace) std::fprintf(stderr, "[x3d2c] transeq_r dir=%d rdr_in=%d -> inputs through the swizzled tensor maps\n", dir, rdr_in);
+      return rc;
+    }
+  }
+  if (trace) std::fprintf(stderr, "[x3d2c] transeq_r dir=%d rdr_in=%d -> reorder + transeq\n", dir, rdr_in);
+  int rc;
+  const double* in[3] = {u, v, w};
+  for (int f = 0; f < 3; ++f) {
+    if ((rc = ensure_scratch_slot(ctx, 2 + f))) return rc;
+    if ((rc = x3d2c_reorder(ctx, rdr_in, ctx->scratch[2 + f], in[f]))) return rc;
+  }
+  return x3d2c_transeq(ctx, dir, du, dv, dw, ctx->scratch[2], ctx->scratch[3], ctx->scratch[4], nu, der1st, der1st_sym, der2nd,
+                       der2nd_sym);
+}
+
 int x3d2c_transeq_species(x3d2c_ctx* ctx, int dir, double* dspec, const double* uvw, const double* spec, double nu,
                           const x3d2c_tdsops* der1st, const x3d2c_tdsops* der1st_sym, const x3d2c_tdsops* der2nd,
                           int sync) {

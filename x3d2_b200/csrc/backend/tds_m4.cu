@@ -602,9 +602,9 @@ int tds_m4(x3d2c_ctx* ctx, int dir, int mode, double* out_a, double* out_b, cons
     if (!(xt == 1 && mode == SINGLE) && !(xt == 2 && (mode == SINGLE || mode == AXPY))) return X3D2C_EUNSUPPORTED;
     const int lay_native = dir;
     if (xt == 1) {
-      if (!map(&p.in_a, in_a, lay_native) || !make_map_xt(&p.out_a, out_a, lay_out, L, nseg, ctx)) return X3D2C_EUNSUPPORTED;
+      if (!map(&p.in_a, in_a, lay_native) || !make_map_xt(&p.out_a, out_a, lay_out, dir, L, nseg, ctx)) return X3D2C_EUNSUPPORTED;
     } else {
-      if (!make_map_xt(&p.in_a, in_a, lay_in, L, nseg, ctx) || !map(&p.out_a, out_a, lay_native)) return X3D2C_EUNSUPPORTED;
+      if (!make_map_xt(&p.in_a, in_a, lay_in, dir, L, nseg, ctx) || !map(&p.out_a, out_a, lay_native)) return X3D2C_EUNSUPPORTED;
       if (mode == AXPY && !map(&p.in_b, in_b, lay_native)) return X3D2C_EUNSUPPORTED;
     }
     p.tiles = G * (SZ / L);

@@ -32,7 +32,7 @@ constexpr int NS = 9;  // recurrences per tile: 3 fields x (d f, d(f conv), d2 f
 struct Params4 {
   CUtensorMap in[3];   // in[0] is the line-aligned velocity (conv)
   CUtensorMap out[3];
-  int tiles;
+  int tiles, nb;       // nb: XTIN only, line groups per z plane (tile coordinates of the swizzled input maps)
   Op o_du, o_dud, o_d2u;  // du, dud scaled by -1/2; d2u unscaled (reference-order stencil)
   double d2u_scale;       // nu * fw of the second derivative
   // rank-split direction only: received halos (SZ, 4, 3, G) and carries (SZ, 3, 9, G)
@@ -52,7 +52,19 @@ struct Stage { static constexpr int doubles = ((12 + NT / L - 1) / (NT / L)) * 4
 // One velocity component of one tile. fF / fC: offsets of the field and conv tiles ([16][NT] each); cz: offset of the
 // carry arrays ze[3][NT], ys[3][NT]. oFm / oCm: base of the four rows before the own segment (field / conv), oFp / oCp:
 // base of the four rows after it; xp / xn: neighbouring ranks' carries of this field's recurrences (DIST).
-template <int L, int NT, bool SELF, bool DIST>
+// XTIN: the input tiles are 128-byte-swizzled [segment][lane][16] boxes of fields kept in the x layout (y lines reading
+// the velocity without an x2y reorder; see tds_m4.cu "XT"). Row r = threadIdx.x holds the thread's own points; element kk
+// of row rr sits at rr * 16 + (((kk >> 1) ^ (rr & 7)) << 1) + (kk & 1). The results are written in the direction's own
+// layout as usual.
+template <int L, int NT>
+__device__ __forceinline__ int sw_off(const int t, const int r, const int q) {  // window element t of thread r
+  constexpr int nseg = NT / L;
+  const int rr = t < 4 ? (q == 0 ? r + NT - L : r - L) : (t < S + 4 ? r : (q == nseg - 1 ? r - (NT - L) : r + L));
+  const int kk = t < 4 ? S - 4 + t : (t < S + 4 ? t - 4 : t - S - 4);
+  return rr * 16 + (((kk >> 1) ^ (rr & 7)) << 1) + (kk & 1);
+}
+
+template <int L, int NT, bool SELF, bool DIST, bool XTIN = false>
 __device__ __forceinline__ void component4(const int fF, const int fC, const int cz, const Params4& p, const int q,
                                            const int l, const int b0, const int oFm, const int oCm, const int oFp,
                                            const int oCp, const int xp, const int xn) {
@@ -61,6 +73,12 @@ __device__ __forceinline__ void component4(const int fF, const int fC, const int
   {
     double wf[9], wp[9];
     auto load = [&](int t, double& f, double& pr) {  // window element t: row j0 - 4 + t
+      if (XTIN) {
+        const int o = sw_off<L, NT>(t, b0, q);
+        f = smem4[fF + o];
+        pr = f * (SELF ? f : smem4[fC + o]);
+        return;
+      }
       const int oF = t < 4 ? oFm + t * NT : (t < S + 4 ? fF + b0 + (t - 4) * NT : oFp + (t - S - 4) * NT);
       const int oC = t < 4 ? oCm + t * NT : (t < S + 4 ? fC + b0 + (t - 4) * NT : oCp + (t - S - 4) * NT);
       f = smem4[oF];
@@ -112,10 +130,23 @@ __device__ __forceinline__ void component4(const int fF, const int fC, const int
   {
     double zi, yi;
     carries<L, DIST>(cz + 0 * NT + l, cz + 3 * NT + l, L, xp, xn, p.o_du, q, nseg, zi, yi);
+    if (XTIN) {
+      // conv comes from the swizzled tile; the result goes to the same memory in the direction's own layout, so for the
+      // line-aligned component (conv == the field itself) every thread must have read before anyone writes
 #pragma unroll
-    for (int k = 0; k < S; ++k) {
-      const double du = fma(p.o_du.Cp[k], yi, fma(p.o_du.W[k], zi, z1[k]));
-      smem4[fF + b0 + k * NT] = fma(smem4[fC + b0 + k * NT], du, z2[k]);
+      for (int k = 0; k < S; ++k) {
+        const double du = fma(p.o_du.Cp[k], yi, fma(p.o_du.W[k], zi, z1[k]));
+        z2[k] = fma(smem4[fC + sw_off<L, NT>(k + 4, b0, q)], du, z2[k]);
+      }
+      if (SELF) __syncthreads();
+#pragma unroll
+      for (int k = 0; k < S; ++k) smem4[fF + b0 + k * NT] = z2[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        const double du = fma(p.o_du.Cp[k], yi, fma(p.o_du.W[k], zi, z1[k]));
+        smem4[fF + b0 + k * NT] = fma(smem4[fC + b0 + k * NT], du, z2[k]);
+      }
     }
   }
   fence_async_smem();  // F was written through the generic proxy, the TMA store reads through the async proxy
@@ -124,8 +155,9 @@ __device__ __forceinline__ void component4(const int fF, const int fC, const int
 
 // shared memory: [2 buffers][3 fields][16][NT] | carries ze[3][NT], ys[3][NT] | 2 mbarriers (16 B)
 //                DIST: | halo staging (Stage::doubles) | neighbour carries [2 buffers][prev 27 rows | next 27 rows][L]
-template <int L, int NT, bool DIST>
+template <int L, int NT, bool DIST, bool XTIN = false>
 __global__ void __launch_bounds__(NT, 1) transeq_m4_kernel(const __grid_constant__ Params4 p) {
+  static_assert(!(DIST && XTIN), "swizzled inputs are not combined with rank-split lines");
   constexpr int nseg = NT / L, fd = S * NT, tpg = SZ / L, cpr = L / 2;
   constexpr int cz = 6 * fd;                           // carries
   constexpr int hs0 = cz + 6 * NT + 2;                 // halo staging (after the two mbarriers)
@@ -140,7 +172,14 @@ __global__ void __launch_bounds__(NT, 1) transeq_m4_kernel(const __grid_constant
     const unsigned bar = buf ? bar1 : bar0;
     mbar_expect_tx(bar, 3 * tile_bytes);
 #pragma unroll
-    for (int f = 0; f < 3; ++f) tma_load_4d(saddr(smem4 + (3 * buf + f) * fd), &p.in[f], bar, l0, 0, 0, grp);
+    for (int f = 0; f < 3; ++f) {
+      if (XTIN) {  // (0, x of the first lane, 0, 0, z)
+        const int c4 = grp / p.nb, c3 = grp - c4 * p.nb;
+        tma_load_5d(saddr(smem4 + (3 * buf + f) * fd), &p.in[f], bar, 0, SZ * c3 + l0, 0, 0, c4);
+      } else {
+        tma_load_4d(saddr(smem4 + (3 * buf + f) * fd), &p.in[f], bar, l0, 0, 0, grp);
+      }
+    }
   };
   auto stage_neighbours = [&](int buf, int tile) {  // all threads: halo rows and neighbour carries of one tile
     const int grp = tile / tpg, l0 = (tile - grp * tpg) * L;
@@ -200,12 +239,12 @@ __global__ void __launch_bounds__(NT, 1) transeq_m4_kernel(const __grid_constant
     const int xp = xb0 + buf * xbuf + l, xn = xp + NS * EXP_ROWS * L;
     constexpr int xf = 3 * EXP_ROWS * L;  // three recurrences per field
     const int m0 = before(0), a0 = after(0);
-    component4<L, NT, false, DIST>(bo + 1 * fd, bo, cz, p, q, l, b0, before(1), m0, after(1), a0, xp + xf, xn + xf);
+    component4<L, NT, false, DIST, XTIN>(bo + 1 * fd, bo, cz, p, q, l, b0, before(1), m0, after(1), a0, xp + xf, xn + xf);
     store_field(1);
-    component4<L, NT, false, DIST>(bo + 2 * fd, bo, cz, p, q, l, b0, before(2), m0, after(2), a0, xp + 2 * xf,
-                                   xn + 2 * xf);
+    component4<L, NT, false, DIST, XTIN>(bo + 2 * fd, bo, cz, p, q, l, b0, before(2), m0, after(2), a0, xp + 2 * xf,
+                                         xn + 2 * xf);
     store_field(2);
-    component4<L, NT, true, DIST>(bo, bo, cz, p, q, l, b0, m0, m0, a0, a0, xp, xn);
+    component4<L, NT, true, DIST, XTIN>(bo, bo, cz, p, q, l, b0, m0, m0, a0, a0, xp, xn);
     store_field(0);
     const int nn = tile + 2 * gridDim.x;
     if (nn < p.tiles) {
@@ -220,21 +259,21 @@ __global__ void __launch_bounds__(NT, 1) transeq_m4_kernel(const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-template <int L, int NT, bool DIST>
+template <int L, int NT, bool DIST, bool XTIN = false>
 int launch4(x3d2c_ctx* ctx, const Params4& p) {
   constexpr size_t smem = sizeof(double) * (6 * S * NT + 6 * NT + 2 +
                                             (DIST ? Stage<L, NT>::doubles + 2 * 2 * NS * EXP_ROWS * L : 0));
   static int per_sm_dev[x3d2c::kMaxDevices] = {};  // once per device
   int& per_sm = per_sm_dev[ctx->device];
   if (!per_sm) {
-    X3D2C_CHECK_CUDA(cudaFuncSetAttribute(transeq_m4_kernel<L, NT, DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    X3D2C_CHECK_CUDA(cudaFuncSetAttribute(transeq_m4_kernel<L, NT, DIST, XTIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
-    X3D2C_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, transeq_m4_kernel<L, NT, DIST>, NT, smem));
+    X3D2C_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, transeq_m4_kernel<L, NT, DIST, XTIN>, NT, smem));
     if (per_sm < 1) per_sm = 1;
   }
   int grid = num_sms(ctx) * per_sm;
   if (grid > p.tiles) grid = p.tiles;
-  transeq_m4_kernel<L, NT, DIST><<<grid, NT, smem, ctx->stream>>>(p);
+  transeq_m4_kernel<L, NT, DIST, XTIN><<<grid, NT, smem, ctx->stream>>>(p);
   X3D2C_CHECK_LAUNCH(ctx);
   return X3D2C_OK;
 }
@@ -485,9 +524,11 @@ bool dist_shape(int n, int* L, int* NT) {
 
 namespace x3d2c {
 
+// lay_in: the layout u, v, w are stored in; != dir only for y lines reading the x layout (swizzled input tiles).
+// dry_run: all checks, no launch.
 int transeq_m4(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, const double* u, const double* v,
                const double* w, double nu, const x3d2c_tdsops* der1st, const x3d2c_tdsops* der1st_sym,
-               const x3d2c_tdsops* der2nd, const x3d2c_tdsops* der2nd_sym) {
+               const x3d2c_tdsops* der2nd, const x3d2c_tdsops* der2nd_sym, int lay_in, bool dry_run) {
   static const bool disabled = std::getenv("X3D2C_NO_TMA") != nullptr;
   if (disabled) return X3D2C_EUNSUPPORTED;
   if (!same_tables(der1st, der1st_sym) || !same_tables(der2nd, der2nd_sym)) return X3D2C_EUNSUPPORTED;
@@ -495,6 +536,8 @@ int transeq_m4(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, cons
   const int n = der1st->n_tds, nseg = n / S;
   const bool split = ctx->cfg.nproc_dir[dir - 1] > 1 || ctx->force_dist;
   if (split && !dist_supported(ctx, dir, n)) return X3D2C_EUNSUPPORTED;
+  const bool xtin = lay_in != dir;
+  if (xtin && (dir != X3D2C_DIR_Y || lay_in != X3D2C_DIR_X || split)) return X3D2C_EUNSUPPORTED;
   int L = 0, NT = 0;
   if (!(split ? dist_shape(n, &L, &NT) : tile_shape(n, &L, &NT))) return X3D2C_EUNSUPPORTED;
   Params4 p{};
@@ -513,10 +556,21 @@ int transeq_m4(x3d2c_ctx* ctx, int dir, double* du, double* dv, double* dw, cons
   else if (dir == X3D2C_DIR_Y) { out[0] = dv; out[1] = du; out[2] = dw; in[0] = v; in[1] = u; in[2] = w; }
   else { out[0] = dw; out[1] = du; out[2] = dv; in[0] = w; in[1] = u; in[2] = v; }
   const int G = ctx->n_groups[dir], n_pad = ctx->n_pad(dir);
-  for (int f = 0; f < 3; ++f)
-    if (!make_line_map(&p.in[f], in[f], L, nseg, n_pad, G) || !make_line_map(&p.out[f], out[f], L, nseg, n_pad, G))
+  for (int f = 0; f < 3; ++f) {
+    if (xtin ? !make_map_xt(&p.in[f], in[f], lay_in, dir, L, nseg, ctx) : !make_line_map(&p.in[f], in[f], L, nseg, n_pad, G))
       return X3D2C_EUNSUPPORTED;
+    if (!make_line_map(&p.out[f], out[f], L, nseg, n_pad, G)) return X3D2C_EUNSUPPORTED;
+  }
   p.tiles = G * (SZ / L);
+  p.nb = ctx->nx_pad / SZ;
+  if (dry_run) return X3D2C_OK;  // the call qualifies (x3d2c_transeq_r_fused)
+  if (xtin) {
+    if (L == 32) return launch4<32, 128, false, true>(ctx, p);
+    if (L == 16) return launch4<16, 128, false, true>(ctx, p);
+    if (L == 8) return launch4<8, 128, false, true>(ctx, p);
+    if (NT == 128) return launch4<4, 128, false, true>(ctx, p);
+    return launch4<4, 256, false, true>(ctx, p);
+  }
   if (!split) {
     if (L == 32) return launch4<32, 128, false>(ctx, p);
     if (L == 16) return launch4<16, 128, false>(ctx, p);

@@ -264,6 +264,16 @@ class Backend {  // cuda_c_backend_t: every method is one deferred procedure of 
                              dp.der2nd.h, dp.der2nd_sym.h));
     du.data_loc = u.data_loc; dv.data_loc = v.data_loc; dw.data_loc = w.data_loc;  // omp/backend.f90:333
   }
+  // reorder(u, v, w; rdr_in) + transeq in `dir`; transeq_r_fused: the backend does it without a reorder pass
+  bool transeq_r_fused(int dir, const DevDirps& dp, int rdr_in) {
+    return x3d2c_transeq_r_fused(ctx, dir, dp.der1st.h, dp.der1st_sym.h, dp.der2nd.h, dp.der2nd_sym.h, rdr_in) == 1;
+  }
+  void transeq_r(int dir, Field& du, Field& dv, Field& dw, const Field& u, const Field& v, const Field& w, double nu,
+                 const DevDirps& dp, int rdr_in) {
+    X3D2H_CALL(x3d2c_transeq_r(ctx, dir, du.dev, dv.dev, dw.dev, u.dev, v.dev, w.dev, nu, dp.der1st.h, dp.der1st_sym.h,
+                               dp.der2nd.h, dp.der2nd_sym.h, rdr_in));
+    du.data_loc = u.data_loc; dv.data_loc = v.data_loc; dw.data_loc = w.data_loc;
+  }
   void transeq_x(Field& du, Field& dv, Field& dw, const Field& u, const Field& v, const Field& w, double nu, const DevDirps& dp) { transeq(DIR_X, du, dv, dw, u, v, w, nu, dp); }
   void transeq_y(Field& du, Field& dv, Field& dw, const Field& u, const Field& v, const Field& w, double nu, const DevDirps& dp) { transeq(DIR_Y, du, dv, dw, u, v, w, nu, dp); }
   void transeq_z(Field& du, Field& dv, Field& dw, const Field& u, const Field& v, const Field& w, double nu, const DevDirps& dp) { transeq(DIR_Z, du, dv, dw, u, v, w, nu, dp); }
@@ -911,13 +921,19 @@ class Sim {
                      const Field& ww) {
     Allocator& A = allocator;
     backend.transeq_x(du, dv, dw, uu, vv, ww, nu, xdirps);
-    // u, v, w into both pencil layouts with one read each (reference: 3 x reorder X2Y here, 3 x reorder X2Z below)
-    Field *u_y = A.get_block(DIR_Y), *v_y = A.get_block(DIR_Y), *w_y = A.get_block(DIR_Y);
     Field *u_z = A.get_block(DIR_Z), *v_z = A.get_block(DIR_Z), *w_z = A.get_block(DIR_Z);
-    backend.reorder_x2yz(*u_y, *u_z, uu); backend.reorder_x2yz(*v_y, *v_z, vv); backend.reorder_x2yz(*w_y, *w_z, ww);
     for (int i = 0; i < 3; ++i) dy[i] = A.get_block(DIR_Y);
-    backend.transeq_y(*dy[0], *dy[1], *dy[2], *u_y, *v_y, *w_y, nu, ydirps);
-    A.release_block(u_y); A.release_block(v_y); A.release_block(w_y);
+    if (backend.transeq_r_fused(DIR_Y, ydirps, RDR_X2Y)) {
+      // the y sweep reads the x-layout velocity itself (swizzled tiles): only the z copies are made
+      backend.transeq_r(DIR_Y, *dy[0], *dy[1], *dy[2], uu, vv, ww, nu, ydirps, RDR_X2Y);
+      backend.reorder(*u_z, uu, RDR_X2Z); backend.reorder(*v_z, vv, RDR_X2Z); backend.reorder(*w_z, ww, RDR_X2Z);
+    } else {
+      // u, v, w into both pencil layouts with one read each (reference: 3 x reorder X2Y here, 3 x reorder X2Z below)
+      Field *u_y = A.get_block(DIR_Y), *v_y = A.get_block(DIR_Y), *w_y = A.get_block(DIR_Y);
+      backend.reorder_x2yz(*u_y, *u_z, uu); backend.reorder_x2yz(*v_y, *v_z, vv); backend.reorder_x2yz(*w_y, *w_z, ww);
+      backend.transeq_y(*dy[0], *dy[1], *dy[2], *u_y, *v_y, *w_y, nu, ydirps);
+      A.release_block(u_y); A.release_block(v_y); A.release_block(w_y);
+    }
     for (int i = 0; i < 3; ++i) dz[i] = A.get_block(DIR_Z);
     backend.transeq_z(*dz[0], *dz[1], *dz[2], *u_z, *v_z, *w_z, nu, zdirps);
     A.release_block(u_z); A.release_block(v_z); A.release_block(w_z);
