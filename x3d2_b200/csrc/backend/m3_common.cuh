@@ -239,48 +239,6 @@ struct InlineCarries {
 __device__ __forceinline__ void push_carry(double* dst, double v) {
   asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst), "d"(v) : "memory");
 }
-__device__ __forceinline__ double take_carry(double* src) {
-  unsigned long long v;
-  long long t0 = 0;
-  for (unsigned spins = 0;; ++spins) {
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
-    if (v != x3d2c::kCarrySentinel) break;
-    if (spins == 64) t0 = clock64();
-    if (spins > 64) {
-      __nanosleep(40);
-      if (clock64() - t0 > 40000000000ll) {  // ~20 s: the neighbour is gone; fail instead of hanging the device
-        printf("x3d2c: carry exchange timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-        __trap();
-      }
-    }
-  }
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(src), "l"(x3d2c::kCarrySentinel) : "memory");
-  return __longlong_as_double((long long)v);
-}
-
-// One recurrence of one tile. ze / ys: shared offsets of the carries of segment 0 (lane applied, L doubles between
-// segments); slot: offset of row 0 of this recurrence for this thread's lane in the (SZ, EXP_ROWS, ns, G) arrays;
-// xp / xn: shared offsets (lane applied) where carries() expects the rows from the previous / next rank.
-// Pushing and polling are separate so that a kernel can put other work between them (the neighbour needs about as
-// long as this rank to reach the same tile, and the stores take a few microseconds over NVLink).
-template <int L>
-__device__ __forceinline__ void push_carries_inline(const InlineCarries& c, const size_t slot, const int ze, const int ys,
-                                                    const Op& o, const int q, const int nseg) {
-  const int r = q - (nseg - DMAX);
-  if (r >= 0) {
-    push_carry(c.to_next + slot + (size_t)r * SZ, smem[ze + q * L]);
-  } else if (q < DMAX) {
-    // what this rank's first segments add to yin of the previous rank's segment nseg' - 3 + q (see carries())
-    double acc = 0.0;
-#pragma unroll
-    for (int d = 1; d <= DMAX; ++d)
-      if (q + d - DMAX >= 0) acc = fma(o.yw[d - 1], smem[ys + (q + d - DMAX) * L], acc);
-#pragma unroll
-    for (int m = 1; m <= DMAX - 1; ++m)
-      if (q + m - DMAX >= 0) acc = fma(o.om[m + DMAX - 1], smem[ze + (q + m - DMAX) * L], acc);
-    push_carry(c.to_prev + slot + (size_t)q * SZ, acc);
-  }
-}
 // N slots at once: all loads are in flight together, so that a poll whose data has arrived costs one trip to L2
 template <int N>
 __device__ __forceinline__ void take_carries(double* const (&src)[N], double (&out)[N]) {
@@ -328,17 +286,27 @@ __device__ __forceinline__ void poll_carries_inline(const InlineCarries& c, cons
     for (int i = 0; i < N; ++i) smem[x + i * xstride] = v[i];
   }
 }
+// One recurrence of one tile. ze / ys: shared offsets of the carries of segment 0 (lane applied, L doubles between
+// segments); slot: offset of row 0 of this recurrence for this thread's lane in the (SZ, EXP_ROWS, ns, G) arrays.
+// Pushing and polling are separate so that a kernel can put other work between them (the neighbour needs about as
+// long as this rank to reach the same tile, and the stores take a few microseconds over NVLink).
 template <int L>
-__device__ __forceinline__ void poll_carries_inline(const InlineCarries& c, const size_t slot, const int q, const int nseg,
-                                                    const int xp, const int xn) {
-  poll_carries_inline<L, 1>(c, slot, 0, q, nseg, xp, xn, 0);
-}
-template <int L>
-__device__ __forceinline__ void exchange_carries_inline(const InlineCarries& c, const size_t slot, const int ze,
-                                                        const int ys, const Op& o, const int q, const int nseg,
-                                                        const int xp, const int xn) {
-  push_carries_inline<L>(c, slot, ze, ys, o, q, nseg);
-  poll_carries_inline<L>(c, slot, q, nseg, xp, xn);
+__device__ __forceinline__ void push_carries_inline(const InlineCarries& c, const size_t slot, const int ze, const int ys,
+                                                    const Op& o, const int q, const int nseg) {
+  const int r = q - (nseg - DMAX);
+  if (r >= 0) {
+    push_carry(c.to_next + slot + (size_t)r * SZ, smem[ze + q * L]);
+  } else if (q < DMAX) {
+    // what this rank's first segments add to yin of the previous rank's segment nseg' - 3 + q (see carries())
+    double acc = 0.0;
+#pragma unroll
+    for (int d = 1; d <= DMAX; ++d)
+      if (q + d - DMAX >= 0) acc = fma(o.yw[d - 1], smem[ys + (q + d - DMAX) * L], acc);
+#pragma unroll
+    for (int m = 1; m <= DMAX - 1; ++m)
+      if (q + m - DMAX >= 0) acc = fma(o.om[m + DMAX - 1], smem[ze + (q + m - DMAX) * L], acc);
+    push_carry(c.to_prev + slot + (size_t)q * SZ, acc);
+  }
 }
 
 // The terms of carries() that come from the neighbouring ranks (zero for all but the first / last DMAX segments)
