@@ -79,6 +79,10 @@ int x3d2h_init_tgv(x3d2h_sim* sim);
 int x3d2h_set_velocity(x3d2h_sim* sim, const double* u, const double* v, const double* w);
 int x3d2h_get_velocity(x3d2h_sim* sim, double* u, double* v, double* w);
 /* base_case_t%run loop body (src/case/base_case.f90:246-289), nsteps full time steps, asynchronous */
+/* the channel case's per-sub-stage hooks (src/case/channel.f90:59-228) around every following step: bulk-velocity
+ * correction (field_volume_integral + field_shift towards 2/3), rotation forcing (omega_rot while the step counter is
+ * below n_rotate), wall rows of u, v, w reset from zero boundary fields (inlet_noise = 0) before the pressure correction */
+int x3d2h_set_case_channel(x3d2h_sim* sim, double omega_rot, int n_rotate);
 int x3d2h_step(x3d2h_sim* sim, int nsteps);
 /* n independent batches, one time step each: batch b = upload (u_in, v_in, w_in) -> step -> download into (u_out, v_out,
  * w_out); uploads and downloads run on the backend's copy lanes and overlap the kernels of the neighbouring batches.

@@ -648,6 +648,58 @@ class World {
     }
   }
 
+  // omp/backend.f90:1023-1066: sum over the un-padded entries of a DIR_X field (all ranks)
+  double field_volume_integral(const WField& f) {
+    if (f.data_loc == NULL_LOC) fail("You must set the data_loc before calling volume integral.");
+    if (f.dir != DIR_X) fail("Volume integral can only be called on DIR_X fields.");
+    const int npad = n_pad(DIR_X);
+    double s = 0.0;
+    for (int r = 0; r < P; ++r) {
+      int dims[3];
+      get_dims_dataloc(dims, f.data_loc, rm[r].vert_dims, rm[r].cell_dims);
+      const int stacked = (dims[1] - 1) / SZ + 1;
+      double sum_p = 0.0;
+      for (int k_j = 1; k_j <= stacked; ++k_j)
+        for (int k_i = 1; k_i <= dims[2]; ++k_i) {
+          const int k = k_j + (k_i - 1) * stacked;
+          const double* g = f.r[r].data() + (size_t)SZ * npad * (k - 1);
+          double sum_pncl = 0.0;
+          for (int j = 1; j <= dims[0]; ++j)
+            for (int i = 0; i < std::min(SZ, dims[1] - (k_j - 1) * SZ); ++i) sum_pncl = sum_pncl + ORC_AT(g, i, j);
+          sum_p = sum_p + sum_pncl;
+        }
+      s += sum_p;  // MPI_Allreduce SUM (:1063)
+    }
+    return s;
+  }
+  // omp/backend.f90:893-901: the whole padded block
+  void field_shift(WField& f, double a) {
+    for (int r = 0; r < P; ++r)
+      for (double& x : f.r[r]) x = x + a;
+  }
+  // omp/backend.f90:954-1021, Y_FACE branch (:1003-1014): both walls of a DIR_X field from f_start
+  void field_set_y_face_from_field(WField& f, const WField& f_start) {
+    if (f.dir != DIR_X || f_start.dir != DIR_X) fail("field_set_face_from_field: only supported for DIR_X fields.");
+    if (f.data_loc == NULL_LOC) fail("field_set_face_from_field: requires a valid data_loc.");
+    const int npad = n_pad(DIR_X);
+    for (int r = 0; r < P; ++r) {
+      int dims[3];
+      get_dims_dataloc(dims, f.data_loc, rm[r].vert_dims, rm[r].cell_dims);
+      const int n_mod = (dims[1] - 1) % SZ + 1, n_y_blocks = (dims[1] - 1) / SZ + 1;
+      for (int z = 1; z <= dims[2]; ++z) {
+        const int k_start = 1 + (z - 1) * n_y_blocks, k_end = n_y_blocks + (z - 1) * n_y_blocks;
+        double* gs = f.r[r].data() + (size_t)SZ * npad * (k_start - 1);
+        double* ge = f.r[r].data() + (size_t)SZ * npad * (k_end - 1);
+        const double* ss = f_start.r[r].data() + (size_t)SZ * npad * (k_start - 1);
+        const double* se = f_start.r[r].data() + (size_t)SZ * npad * (k_end - 1);
+        for (int j = 1; j <= dims[0]; ++j) {
+          ORC_AT(gs, 0, j) = ORC_AT(ss, 0, j);
+          ORC_AT(ge, n_mod - 1, j) = ORC_AT(se, n_mod - 1, j);
+        }
+      }
+    }
+  }
+
   // ---------------------------------------------------------------- set/get through DIR_C (backend.f90:402-466)
   // global Cartesian array g(nx_g, ny_g, nz_g) of the data_loc extents (x fastest, unpadded)
   void set_field_from_global(WField& f, const double* g, int data_loc) {
@@ -1380,15 +1432,56 @@ class World {
   }
 
   // case/base_case.f90:246-289, one full time step (all sub-stages)
+  // ---- the channel case's hooks (case/channel.f90:59-228) around the generic loop of base_case.f90:262-289.
+  // Wall values: zero (inlet_noise = 0, the parity configuration of SURVEY.md F5) unless set_wall_bc() gave others.
+  // The bulk velocity is reduced once (P = 1 semantics; channel.f90:76-78 reduces field_volume_integral's already global
+  // value a second time, which only matters for P > 1, where the reference's Poisson solver stops anyway).
+  int case_kind = 0;  // 0: none (TGV, generic), 1: channel
+  double omega_rot = 0.0;
+  int n_rotate = 0, iter = 1;
+  WField *bc_u = nullptr, *bc_v = nullptr, *bc_w = nullptr;
+  void set_case_channel(double omega, int n_rot) {
+    case_kind = 1;
+    omega_rot = omega;
+    n_rotate = n_rot;
+    if (!bc_u) {
+      bc_u = get_block(DIR_X, VERT); bc_v = get_block(DIR_X, VERT); bc_w = get_block(DIR_X, VERT);
+      for (WField* b : {bc_u, bc_v, bc_w})
+        for (auto& rr : b->r) std::fill(rr.begin(), rr.end(), 0.0);
+    }
+  }
+  void define_BC() {  // channel.f90:59-80
+    if (case_kind != 1) return;
+    double ub = field_volume_integral(*u);
+    ub = ub / ((double)gm.global_cell_dims[0] * gm.global_cell_dims[1] * gm.global_cell_dims[2]);
+    const double can = 2.0 / 3.0 - ub;
+    field_shift(*u, can);
+  }
+  void forcings(WField& du, WField& dv) {  // channel.f90:189-204
+    if (case_kind != 1 || omega_rot == 0.0 || iter >= n_rotate) return;
+    vecadd(-omega_rot, *v, 1.0, du);
+    vecadd(omega_rot, *u, 1.0, dv);
+  }
+  void apply_BC() {  // channel.f90:211-228
+    if (case_kind != 1) return;
+    field_set_y_face_from_field(*u, *bc_u);
+    field_set_y_face_from_field(*v, *bc_v);
+    field_set_y_face_from_field(*w, *bc_w);
+  }
+
   void step() {
     WField* curr[3] = {u, v, w};
     for (int sub = 1; sub <= ti_nstage; ++sub) {
+      define_BC();
       WField* deriv[3] = {get_block(DIR_X), get_block(DIR_X), get_block(DIR_X)};
       transeq_default(*deriv[0], *deriv[1], *deriv[2], *u, *v, *w);
+      forcings(*deriv[0], *deriv[1]);
       if (ti_is_ab) adams_bashforth(curr, deriv, dt); else runge_kutta(curr, deriv, dt);
       for (int i = 0; i < 3; ++i) release_block(deriv[i]);
+      apply_BC();
       pressure_correction(*u, *v, *w);
     }
+    iter = iter + 1;
   }
 
   // case/tgv.f90:41-72 via base_case.f90:set_init (:139-179)

@@ -266,6 +266,12 @@ int orc_world_get_uvw(void* h, double* u, double* v, double* w) {
   return 0;
   ORC_CATCH(1)
 }
+int orc_world_set_case_channel(void* h, double omega_rot, int n_rotate) {
+  ORC_TRY
+  ((World*)h)->set_case_channel(omega_rot, n_rotate);
+  return 0;
+  ORC_CATCH(1)
+}
 int orc_world_step(void* h, int nsteps) {
   ORC_TRY
   for (int i = 0; i < nsteps; ++i) ((World*)h)->step();

@@ -52,6 +52,7 @@ def _load():
         orc_world_set_uvw=[C.c_void_p, _dp, _dp, _dp],
         orc_world_get_uvw=[C.c_void_p, _dp, _dp, _dp],
         orc_world_step=[C.c_void_p, C.c_int],
+        orc_world_set_case_channel=[C.c_void_p, C.c_double, C.c_int],
         orc_world_monitor=[C.c_void_p, _dp],
         orc_world_transeq=[C.c_void_p] + [_dp] * 6,
         orc_world_transeq_dir=[C.c_void_p, C.c_int] + [_dp] * 6,
@@ -222,6 +223,10 @@ class World:
         u, v, w = self._out(), self._out(), self._out()
         _chk(lib().orc_world_get_uvw(self.h, _p(u), _p(v), _p(w)))
         return u, v, w
+
+    def set_case_channel(self, omega_rot=0.0, n_rotate=0):
+        """case/channel.f90 hooks around every sub-stage: bulk-velocity correction, rotation forcing, wall values (zero)."""
+        _chk(lib().orc_world_set_case_channel(self.h, omega_rot, n_rotate))
 
     def step(self, n=1):
         _chk(lib().orc_world_step(self.h, n))

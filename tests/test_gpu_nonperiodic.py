@@ -197,6 +197,33 @@ def test_channel_like_steps_vs_oracle(oracle, x3d2, stretching, beta, strict):
     sim.close()
 
 
+@pytest.mark.parametrize("strict", [False, True], ids=["fast", "strict"])
+def test_channel_case_steps_vs_oracle(oracle, x3d2, strict):
+    """Two RK3 steps of the channel case (case/channel.f90 hooks: bulk-velocity correction, rotation forcing, wall rows
+    reset) on the stretched channel mesh against the oracle running the same hooks."""
+    dims, L = (64, 65, 32), (4.0, 2.0, 2.0)
+    kw = _wall_y(dims, L, "top-bottom", 0.259065151, Re=4200.0, dt=0.005)
+    sim, ref = x3d2.Sim(dims, strict=strict, **kw), oracle.World(dims, **kw)
+    nz, ny, nx = sim.shape()
+    y = ref.geo(1)["vert_coords"][None, :, None]
+    x = (np.arange(nx) * (L[0] / nx))[None, None, :]
+    z = (np.arange(nz) * (L[2] / nz))[:, None, None]
+    wall = (1 - (y - 1.0) ** 2)
+    u = wall * (1 + 0.1 * np.sin(2 * np.pi * x / L[0]) * np.cos(2 * np.pi * z / L[2]))
+    v = 0.05 * wall ** 2 * np.cos(2 * np.pi * x / L[0]) * np.sin(2 * np.pi * z / L[2])
+    w = 0.05 * wall * np.sin(4 * np.pi * x / L[0]) * np.sin(2 * np.pi * z / L[2]) + 0 * y
+    for s in (sim, ref):
+        s.set_uvw(u, v, w)
+        s.set_case_channel(0.3, 2)  # rotation during the first step only
+        s.step(2)
+    a, b = sim.get_uvw(), ref.get_uvw()
+    scale = max(np.abs(q).max() for q in b)
+    err = max(np.abs(p - q).max() for p, q in zip(a, b)) / scale
+    print("channel case,", "strict" if strict else "fast", "rel err %.2e" % err)
+    assert err < 1e-12
+    sim.close()
+
+
 # ---------------------------------------------------------------------------- generic segment-parallel kernels (tds_g.cu)
 @pytest.mark.parametrize("dims,stretching,beta,bcs", [
     ((64, 257, 32), "top-bottom", 0.259065151, ((0, 0), (2, 2), (0, 0))),   # channel lines (BASELINE.json configs[4])

@@ -261,3 +261,53 @@ def test_poisson_010_stretched_inverts_the_discrete_operator(oracle, stretching,
     assert np.abs(d - f).max() <= 1e-11 * np.abs(f).max()    # and pointwise
     dp = p - p0
     assert np.abs(dp - dp.mean()).max() <= 1e-12
+
+
+@pytest.mark.parametrize("stretching,beta", [("uniform", 1.0), ("top-bottom", 0.259065151)])
+def test_channel_case_hooks(oracle, stretching, beta):
+    """The channel case's hooks (case/channel.f90:59-228) inside the oracle's step, against the same sub-stage assembled
+    by hand from the oracle's own operators: bulk-velocity shift towards 2/3 (field_volume_integral over the vertices
+    divided by the number of cells, then field_shift on the whole field), transeq, rotation forcing, Euler update, wall
+    rows reset to the (zero) wall values, pressure correction."""
+    dims, L, dt, om = (32, 33, 16), (4.0, 2.0, 2.0), 0.002, 0.3
+    kw = dict(L=L, bcs=((0, 0), (2, 2), (0, 0)), stretching=("uniform", stretching, "uniform"), beta=(1.0, beta, 1.0),
+              Re=4200.0, dt=dt, time_intg="AB1")
+    a, b = oracle.World(dims, **kw), oracle.World(dims, **kw)
+    nz, ny, nx = a.shape()
+    y = a.geo(1)["vert_coords"][None, :, None]
+    x = (np.arange(nx) * (L[0] / nx))[None, None, :]
+    z = (np.arange(nz) * (L[2] / nz))[:, None, None]
+    wall = 1 - (y - 1.0) ** 2
+    u = wall * (1 + 0.1 * np.sin(2 * np.pi * x / L[0]) * np.cos(2 * np.pi * z / L[2]))
+    v = 0.05 * wall ** 2 * np.cos(2 * np.pi * x / L[0]) * np.sin(2 * np.pi * z / L[2])
+    w = 0.05 * wall * np.sin(4 * np.pi * x / L[0]) * np.sin(2 * np.pi * z / L[2]) + 0 * y
+    a.set_uvw(u, v, w)
+    a.set_case_channel(om, 10)
+    a.step(1)
+    got = a.get_uvw()
+    n_cell = nx * (ny - 1) * nz
+    u1 = u + (2.0 / 3.0 - u.sum() / n_cell)
+    du, dv, dw = b.transeq(u1, v, w)
+    du = du - om * v
+    dv = dv + om * u1
+    new = [u1 + dt * du, v + dt * dv, w + dt * dw]
+    for f in new:
+        f[:, 0, :] = 0.0
+        f[:, -1, :] = 0.0
+    b.set_uvw(*new)
+    b.pressure_correction()
+    exp = b.get_uvw()
+    scale = max(np.abs(e).max() for e in exp)
+    assert max(np.abs(g - e).max() for g, e in zip(got, exp)) <= 1e-13 * scale
+    # the hooks are not a no-op: without them the step gives something else
+    c = oracle.World(dims, **kw)
+    c.set_uvw(u, v, w)
+    c.step(1)
+    assert max(np.abs(g - e).max() for g, e in zip(got, c.get_uvw())) > 1e-5 * scale
+    # rotation stops at n_rotate: from step n_rotate on the forcing is off (iter < n_rotate, channel.f90:197)
+    d, e = oracle.World(dims, **kw), oracle.World(dims, **kw)
+    for wd, nrot in ((d, 1), (e, 0)):
+        wd.set_uvw(u, v, w)
+        wd.set_case_channel(om, nrot)
+        wd.step(1)
+    assert all(np.array_equal(p, q) for p, q in zip(d.get_uvw(), e.get_uvw()))

@@ -196,6 +196,11 @@ class Sim:
         _chk(self._h.x3d2h_get_velocity(self.h, _p(u), _p(v), _p(w)))
         return u, v, w
 
+    def set_case_channel(self, omega_rot=0.0, n_rotate=0):
+        """case/channel.f90 hooks around every sub-stage of the following steps: bulk-velocity correction, rotation forcing,
+        wall rows reset (zero wall values)."""
+        _chk(self._h.x3d2h_set_case_channel(self.h, omega_rot, n_rotate))
+
     def step(self, n=1):
         _chk(self._h.x3d2h_step(self.h, n))
 

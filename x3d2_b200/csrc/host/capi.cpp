@@ -181,6 +181,11 @@ int x3d2h_get_velocity(x3d2h_sim* sim, double* u, double* v, double* w) {
   S.get_field(u, *S.u, VERT); S.get_field(v, *S.v, VERT); S.get_field(w, *S.w, VERT);
   H_CATCH
 }
+int x3d2h_set_case_channel(x3d2h_sim* sim, double omega_rot, int n_rotate) {
+  H_TRY
+  sim->s->set_case_channel(omega_rot, n_rotate);
+  H_CATCH
+}
 int x3d2h_step(x3d2h_sim* sim, int nsteps) {
   H_TRY
   for (int i = 0; i < nsteps; ++i) sim->s->step();

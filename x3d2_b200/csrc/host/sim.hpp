@@ -365,6 +365,20 @@ class Backend {  // cuda_c_backend_t: every method is one deferred procedure of 
   void sum_yintox(Field& u, const Field& u_) { X3D2H_CALL(x3d2c_sum_yintox(ctx, u.dev, u_.dev)); }
   void sum_zintox(Field& u, const Field& u_) { X3D2H_CALL(x3d2c_sum_zintox(ctx, u.dev, u_.dev)); }
   void sum_yzintox(Field& u, const Field& u_y, const Field& u_z) { X3D2H_CALL(x3d2c_sum_yzintox(ctx, u.dev, u_y.dev, u_z.dev)); }
+  // backend.f90:255-308 (channel case): volume integral of a DIR_X field, shift, wall rows from a field
+  double field_volume_integral(const Field& f) {
+    if (f.data_loc == NULL_LOC) fail("You must set the data_loc before calling volume integral.");
+    if (f.dir != DIR_X) fail("Volume integral can only be called on DIR_X fields.");
+    double s = 0.0;
+    X3D2H_CALL(x3d2c_field_volume_integral(ctx, f.data_loc, f.dev, &s));
+    return s;
+  }
+  void field_shift(Field& f, double a) { X3D2H_CALL(x3d2c_field_shift(ctx, f.dev, a)); }
+  void field_set_face_from_field(Field& f, const Field& f_start, double c_end, int face, double flow_rate_diff = 0.0) {
+    if (f.dir != DIR_X || f_start.dir != DIR_X) fail("field_set_face_from_field: only supported for DIR_X fields.");
+    if (f.data_loc == NULL_LOC) fail("field_set_face_from_field: requires a valid data_loc.");
+    X3D2H_CALL(x3d2c_field_set_face_from_field(ctx, f.dev, f_start.dev, f.data_loc, c_end, face, flow_rate_diff));
+  }
   // sum_yzintox(u, u_y, u_z) + veclincomb(out, base, terms + (c_u, u)) in one pass
   void sum_yzintox_lincomb(Field& u, const Field& u_y, const Field& u_z, bool store_u, Field& out, const Field& base,
                            const std::vector<std::pair<double, const Field*>>& terms, double c_u) {
@@ -1177,27 +1191,66 @@ class Sim {
     ti_istep = ti_istep + 1;
   }
 
-  // base_case.f90:246-289: one time step = nstage x (transeq, time integration, pressure correction)
+  // ---- the channel case's hooks (case/channel.f90:59-228) around the generic loop. Wall values: zero (inlet_noise = 0,
+  // the parity configuration). The bulk velocity is reduced once (see the oracle's note on channel.f90:76-78).
+  int case_kind = 0;  // 0: none (TGV, generic), 1: channel
+  double omega_rot = 0.0;
+  int n_rotate = 0, iter = 1;
+  Field *bc_u = nullptr, *bc_v = nullptr, *bc_w = nullptr;
+  void set_case_channel(double omega, int n_rot) {
+    case_kind = 1;
+    omega_rot = omega;
+    n_rotate = n_rot;
+    if (!bc_u) {
+      bc_u = allocator.get_block(DIR_X, VERT); bc_v = allocator.get_block(DIR_X, VERT); bc_w = allocator.get_block(DIR_X, VERT);
+      for (Field* b : {bc_u, bc_v, bc_w}) { X3D2H_CALL(x3d2c_field_fill(ctx, b->dev, 0.0)); b->data_loc = VERT; }
+    }
+  }
+  void define_BC() {  // channel.f90:59-80
+    if (case_kind != 1) return;
+    double ub = backend.field_volume_integral(*u);
+    ub = ub / ((double)mesh.global_cell_dims[0] * mesh.global_cell_dims[1] * mesh.global_cell_dims[2]);
+    backend.field_shift(*u, 2.0 / 3.0 - ub);
+  }
+  void forcings(Field& du, Field& dv) {  // channel.f90:189-204
+    if (case_kind != 1 || omega_rot == 0.0 || iter >= n_rotate) return;
+    backend.vecadd(-omega_rot, *v, 1.0, du);
+    backend.vecadd(omega_rot, *u, 1.0, dv);
+  }
+  void apply_BC() {  // channel.f90:211-228
+    if (case_kind != 1) return;
+    backend.field_set_face_from_field(*u, *bc_u, 0.0, Y_FACE);
+    backend.field_set_face_from_field(*v, *bc_v, 0.0, Y_FACE);
+    backend.field_set_face_from_field(*w, *bc_w, 0.0, Y_FACE);
+  }
+
+  // base_case.f90:246-289: one time step = nstage x (define_BC, transeq, forcings, time integration, apply_BC, pressure
+  // correction)
   void step() {
     Field* curr[3] = {u, v, w};
     for (int sub = 1; sub <= ti_nstage; ++sub) {
+      define_BC();
       Field* deriv[3] = {allocator.get_block(DIR_X), allocator.get_block(DIR_X), allocator.get_block(DIR_X)};
       if (!base_ops() && !ti_is_ab && !(cfg.flags & X3D2C_FLAG_STRICT)) {  // Runge-Kutta, fast mode: the y / z sums of
         // transeq are taken inside the update pass
         Field *dy[3], *dz[3];
         transeq_parts(*deriv[0], *deriv[1], *deriv[2], dy, dz, *u, *v, *w);
+        forcings(*deriv[0], *deriv[1]);  // linear source terms may join the x contribution before the sums
         runge_kutta(curr, deriv, dt, dy, dz);
         for (int i = 0; i < 3; ++i) { allocator.release_block(dy[i]); allocator.release_block(dz[i]); }
       } else {
         transeq_default(*deriv[0], *deriv[1], *deriv[2], *u, *v, *w);
+        forcings(*deriv[0], *deriv[1]);
         if (base_ops()) { if (ti_is_ab) adams_bashforth_base(curr, deriv, dt); else runge_kutta_base(curr, deriv, dt); }
         else if (ti_is_ab) adams_bashforth(curr, deriv, dt);
         else runge_kutta(curr, deriv, dt);
       }
       u = curr[0]; v = curr[1]; w = curr[2];  // the integrators may continue in another block
       for (int i = 0; i < 3; ++i) allocator.release_block(deriv[i]);
+      apply_BC();
       pressure_correction(*u, *v, *w);
     }
+    iter = iter + 1;
   }
 
   // Independent batches streamed through one time step each (ensemble members, parameter sweeps): batch b's velocity is

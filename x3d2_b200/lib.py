@@ -72,6 +72,7 @@ def load():
         x3d2h_init_tgv=[C.c_void_p],
         x3d2h_set_velocity=[C.c_void_p, _dp, _dp, _dp],
         x3d2h_get_velocity=[C.c_void_p, _dp, _dp, _dp],
+        x3d2h_set_case_channel=[C.c_void_p, C.c_double, C.c_int],
         x3d2h_step=[C.c_void_p, C.c_int],
         x3d2h_step_batches=[C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp],
         x3d2h_sync=[C.c_void_p],
