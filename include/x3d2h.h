@@ -119,6 +119,11 @@ int x3d2h_tds_fused_r(x3d2h_sim* sim, const char* mode, int dir, const char* op_
                       double* out_b);
 int x3d2h_divergence(x3d2h_sim* sim, const double* u, const double* v, const double* w, double* div);
 int x3d2h_gradient(x3d2h_sim* sim, const double* p, double* gx, double* gy, double* gz);
+/* vector_calculus_t%interpl_c2v with the interpl_p2v operators (src/vector_calculus.f90:334-378, src/postprocess/
+ * postprocess.f90:184-189): p at the cell centres -> out at the vertices; vector_calculus_t%laplacian with the der2nd
+ * operators (src/vector_calculus.f90:380-437): u and out at the vertices */
+int x3d2h_interpl_c2v(x3d2h_sim* sim, const double* p, double* out);
+int x3d2h_laplacian(x3d2h_sim* sim, const double* u, double* out);
 int x3d2h_curl(x3d2h_sim* sim, const double* u, const double* v, const double* w, double* ox, double* oy, double* oz);
 int x3d2h_poisson(x3d2h_sim* sim, const double* f, double* p);
 int x3d2h_pressure_correction(x3d2h_sim* sim);

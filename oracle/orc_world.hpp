@@ -869,6 +869,36 @@ class World {
     release_block(p_sx_x); release_block(dpdy_sx_x); release_block(dpdz_sx_x);
   }
 
+  // vector_calculus.f90:334-378 with the operators of postprocess.f90:184-189 (interpl_p2v in z, y, x): cell centres
+  // (DIR_Z, CELL) -> vertices (DIR_X, VERT)
+  void interpl_c2v(WField& p_out, const WField& p) {
+    if (p_out.dir != DIR_X || p.dir != DIR_Z) fail("interpl_c2v: output must be in DIR_X, input must be in DIR_Z layout.");
+    WField* p_sy_z = get_block(DIR_Z);
+    tds_solve(*p_sy_z, p, op(zdirps, &Dirps::interpl_p2v));
+    WField* p_sy_y = get_block(DIR_Y);
+    reorder(*p_sy_y, *p_sy_z, RDR_Z2Y); release_block(p_sy_z);
+    WField* p_out_y = get_block(DIR_Y);
+    tds_solve(*p_out_y, *p_sy_y, op(ydirps, &Dirps::interpl_p2v)); release_block(p_sy_y);
+    WField* p_out_x = get_block(DIR_X);
+    reorder(*p_out_x, *p_out_y, RDR_Y2X); release_block(p_out_y);
+    tds_solve(p_out, *p_out_x, op(xdirps, &Dirps::interpl_p2v)); release_block(p_out_x);
+  }
+  // vector_calculus.f90:380-437 with der2nd in x, y, z: DIR_X in, DIR_X out
+  void laplacian(WField& lapl_u, const WField& uu) {
+    if (uu.dir != DIR_X || lapl_u.dir != DIR_X) fail("laplacian: outputs and inputs must be in DIR_X layout.");
+    tds_solve(lapl_u, uu, op(xdirps, &Dirps::der2nd));
+    WField *u_y = get_block(DIR_Y), *d2u_y = get_block(DIR_Y);
+    reorder(*u_y, uu, RDR_X2Y);
+    tds_solve(*d2u_y, *u_y, op(ydirps, &Dirps::der2nd));
+    sum_yintox(lapl_u, *d2u_y);
+    release_block(u_y); release_block(d2u_y);
+    WField *u_z = get_block(DIR_Z), *d2u_z = get_block(DIR_Z);
+    reorder(*u_z, uu, RDR_X2Z);
+    tds_solve(*d2u_z, *u_z, op(zdirps, &Dirps::der2nd));
+    sum_zintox(lapl_u, *d2u_z);
+    release_block(u_z); release_block(d2u_z);
+  }
+
   // vector_calculus.f90:40-140
   void curl(WField& o_i, WField& o_j, WField& o_k, const WField& uu, const WField& vv, const WField& ww) {
     auto xd = op(xdirps, &Dirps::der1st), yd = op(ydirps, &Dirps::der1st), zd = op(zdirps, &Dirps::der1st);

@@ -402,6 +402,28 @@ int orc_world_gradient(void* h, const double* p, double* gx, double* gy, double*
   return 0;
   ORC_CATCH(1)
 }
+int orc_world_interpl_c2v(void* h, const double* p, double* out) {
+  ORC_TRY
+  auto* W = (World*)h;
+  WField *fp = W->get_block(DIR_Z), *a = W->get_block(DIR_X);
+  W->set_field_from_global(*fp, p, CELL);
+  W->interpl_c2v(*a, *fp);
+  W->get_field_to_global(out, *a, VERT);
+  for (WField* f : {fp, a}) W->release_block(f);
+  return 0;
+  ORC_CATCH(1)
+}
+int orc_world_laplacian(void* h, const double* u, double* out) {
+  ORC_TRY
+  auto* W = (World*)h;
+  WField *fu = W->get_block(DIR_X), *a = W->get_block(DIR_X);
+  W->set_field_from_global(*fu, u, VERT);
+  W->laplacian(*a, *fu);
+  W->get_field_to_global(out, *a, VERT);
+  for (WField* f : {fu, a}) W->release_block(f);
+  return 0;
+  ORC_CATCH(1)
+}
 int orc_world_curl(void* h, const double* u, const double* v, const double* w, double* ox, double* oy, double* oz) {
   ORC_TRY
   auto* W = (World*)h;

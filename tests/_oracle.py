@@ -61,6 +61,8 @@ def _load():
         orc_world_tds_solve=[C.c_void_p, C.c_int, C.c_char_p, C.c_int, _dp, _dp, _ip],
         orc_world_divergence=[C.c_void_p] + [_dp] * 4,
         orc_world_gradient=[C.c_void_p] + [_dp] * 4,
+        orc_world_interpl_c2v=[C.c_void_p, _dp, _dp],
+        orc_world_laplacian=[C.c_void_p, _dp, _dp],
         orc_world_curl=[C.c_void_p] + [_dp] * 6,
         orc_world_poisson=[C.c_void_p, _dp, _dp],
         orc_world_fft_roundtrip=[C.c_void_p, _dp, _dp, _dp],
@@ -286,6 +288,20 @@ class World:
         a, b, c = self._out(), self._out(), self._out()
         _chk(lib().orc_world_gradient(self.h, _p(p), _p(a), _p(b), _p(c)))
         return a, b, c
+
+    def interpl_c2v(self, p):
+        """vector_calculus_t%interpl_c2v with the interpl_p2v operators (postprocess.f90:184-189): CELL -> VERT."""
+        p = _f(p)
+        a = self._out()
+        _chk(lib().orc_world_interpl_c2v(self.h, _p(p), _p(a)))
+        return a
+
+    def laplacian(self, u):
+        """vector_calculus_t%laplacian with the der2nd operators: VERT -> VERT."""
+        u = _f(u)
+        a = self._out()
+        _chk(lib().orc_world_laplacian(self.h, _p(u), _p(a)))
+        return a
 
     def curl(self, u, v, w):
         u, v, w = _f(u), _f(v), _f(w)

@@ -92,3 +92,16 @@ def test_step_batches_equals_set_step_get(x3d2):
     with pytest.raises(RuntimeError, match="needs padding"):
         sim.step_batches(1, a, a)
     sim.close()
+
+
+@pytest.mark.parametrize("dims,bcs", [((64, 64, 64), None), ((128, 64, 32), None), ((64, 65, 32), ((0, 0), (2, 2), (0, 0)))])
+@pytest.mark.parametrize("strict", [False, True], ids=["fast", "strict"])
+def test_interpl_c2v_and_laplacian_vs_oracle(oracle, x3d2, dims, bcs, strict):
+    """vector_calculus_t%interpl_c2v (through-reorder solves on the fast path) and %laplacian against the oracle."""
+    kw = dict(bcs=bcs) if bcs else {}
+    sim, ref = x3d2.Sim(dims, strict=strict, **kw), oracle.World(dims, **kw)
+    p = rnd(sim.shape(1110), 41)
+    u = rnd(sim.shape(), 42)
+    for got, exp in ((sim.interpl_c2v(p), ref.interpl_c2v(p)), (sim.laplacian(u), ref.laplacian(u))):
+        assert np.array_equal(got, exp) if strict else rel(got, exp) < TOL
+    sim.close()

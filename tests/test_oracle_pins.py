@@ -311,3 +311,18 @@ def test_channel_case_hooks(oracle, stretching, beta):
         wd.set_case_channel(om, nrot)
         wd.step(1)
     assert all(np.array_equal(p, q) for p, q in zip(d.get_uvw(), e.get_uvw()))
+
+
+def test_interpl_c2v_and_laplacian_known_answers(oracle):
+    """vector_calculus_t%interpl_c2v (cell centres -> vertices, the pressure output path of postprocess.f90:166-197) and
+    %laplacian against analytic fields on a periodic box: sixth-order schemes, so (k dx)^6 accuracy."""
+    n = 64
+    W = oracle.World((n, n, n))
+    d = 2 * np.pi / n
+    xv = (np.arange(n) * d)
+    xc = xv + 0.5 * d
+    f = lambda x, y, z: np.cos(x) * np.sin(2 * y) * np.cos(z)
+    pc = f(xc[None, None, :], xc[None, :, None], xc[:, None, None])
+    pv = f(xv[None, None, :], xv[None, :, None], xv[:, None, None])
+    assert np.abs(W.interpl_c2v(pc) - pv).max() < 20 * (2 * d) ** 6
+    assert np.abs(W.laplacian(pv) + 6.0 * pv).max() < 6.0 * 20 * (2 * d) ** 6

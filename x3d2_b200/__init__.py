@@ -307,6 +307,20 @@ class Sim:
         _chk(self._h.x3d2h_divergence(self.h, _p(u), _p(v), _p(w), _p(d)))
         return d
 
+    def interpl_c2v(self, p):
+        """vector_calculus_t%interpl_c2v (cell centres -> vertices, interpl_p2v operators)."""
+        p = _f(p, self.shape(CELL))
+        a = self._out()
+        _chk(self._h.x3d2h_interpl_c2v(self.h, _p(p), _p(a)))
+        return a
+
+    def laplacian(self, u):
+        """vector_calculus_t%laplacian (der2nd operators) of a vertex field."""
+        u = _f(u, self.shape())
+        a = self._out()
+        _chk(self._h.x3d2h_laplacian(self.h, _p(u), _p(a)))
+        return a
+
     def gradient(self, p):
         p = _f(p, self.shape(CELL))
         a, b, c = self._out(), self._out(), self._out()

@@ -366,6 +366,26 @@ int x3d2h_gradient(x3d2h_sim* sim, const double* p, double* gx, double* gy, doub
   S.get_field(gx, *a, VERT); S.get_field(gy, *b, VERT); S.get_field(gz, *c, VERT);
   H_CATCH
 }
+int x3d2h_interpl_c2v(x3d2h_sim* sim, const double* p, double* out) {
+  H_TRY
+  Sim& S = *sim->s;
+  Tmp t(S.allocator);
+  Field *fp = t.get(DIR_Z), *a = t.get(DIR_X);
+  S.set_field(*fp, p, CELL);
+  S.interpl_c2v(*a, *fp);
+  S.get_field(out, *a, VERT);
+  H_CATCH
+}
+int x3d2h_laplacian(x3d2h_sim* sim, const double* u, double* out) {
+  H_TRY
+  Sim& S = *sim->s;
+  Tmp t(S.allocator);
+  Field *fu = t.get(DIR_X), *a = t.get(DIR_X);
+  S.set_field(*fu, u, VERT);
+  S.laplacian(*a, *fu);
+  S.get_field(out, *a, VERT);
+  H_CATCH
+}
 int x3d2h_curl(x3d2h_sim* sim, const double* u, const double* v, const double* w, double* ox, double* oy, double* oz) {
   H_TRY
   Sim& S = *sim->s;

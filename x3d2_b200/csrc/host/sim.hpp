@@ -1008,6 +1008,40 @@ class Sim {
     A.release_block(p_sx_y); A.release_block(dpdy_sx_y); A.release_block(dpdz_sx_y);
   }
 
+  // vector_calculus.f90:334-378 with the operators of postprocess.f90:184-189: cell centres (DIR_Z, CELL) -> vertices
+  // (DIR_X, VERT). The z2y and y2x reorders are part of the neighbouring solves (tds_solve_r).
+  void interpl_c2v(Field& p_out, const Field& p) {
+    if (p_out.dir != DIR_X || p.dir != DIR_Z)
+      fail("Error in interpl_c2v input/output field dirs: output must be in DIR_X, input must be in DIR_Z layout.");
+    Allocator& A = allocator;
+    Field* p_sy_y = A.get_block(DIR_Y);
+    backend.tds_solve_r(DIR_Z, *p_sy_y, p, zdirps.interpl_p2v, 0, RDR_Z2Y);
+    Field* p_out_y = A.get_block(DIR_Y);
+    backend.tds_solve(*p_out_y, *p_sy_y, ydirps.interpl_p2v);
+    A.release_block(p_sy_y);
+    backend.tds_solve_r(DIR_X, p_out, *p_out_y, xdirps.interpl_p2v, RDR_Y2X, 0);
+    A.release_block(p_out_y);
+  }
+  // postprocess.f90:166-197: pressure at the vertices, rescaled from the pseudo-pressure p'/dt... (vecadd(1/dt, p, 0, p))
+  void pressure_vert(Field& p_out, const Field& p) {
+    interpl_c2v(p_out, p);
+    backend.vecadd(1.0 / dt, p_out, 0.0, p_out);
+  }
+  // vector_calculus.f90:380-437 with der2nd in x, y, z: DIR_X in, DIR_X out, evaluated at the input's data_loc
+  void laplacian(Field& lapl_u, const Field& uu) {
+    if (uu.dir != DIR_X || lapl_u.dir != DIR_X)
+      fail("Error in laplacian input/output field dirs: outputs and inputs must be in DIR_X layout.");
+    Allocator& A = allocator;
+    backend.tds_solve(lapl_u, uu, xdirps.der2nd);
+    Field *u_y = A.get_block(DIR_Y), *u_z = A.get_block(DIR_Z);
+    backend.reorder_x2yz(*u_y, *u_z, uu);
+    Field *d2u_y = A.get_block(DIR_Y), *d2u_z = A.get_block(DIR_Z);
+    backend.tds_solve(*d2u_y, *u_y, ydirps.der2nd);
+    backend.tds_solve(*d2u_z, *u_z, zdirps.der2nd);
+    backend.sum_yzintox(lapl_u, *d2u_y, *d2u_z);
+    A.release_block(u_y); A.release_block(u_z); A.release_block(d2u_y); A.release_block(d2u_z);
+  }
+
   // vector_calculus.f90:40-140
   void curl(Field& o_i, Field& o_j, Field& o_k, const Field& uu, const Field& vv, const Field& ww) {
     Allocator& A = allocator;

@@ -89,6 +89,8 @@ def load():
         x3d2h_tds_fused_r=[C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int,
                            _dp, _dp, _dp, _dp],
         x3d2h_divergence=[C.c_void_p] + [_dp] * 4,
+        x3d2h_interpl_c2v=[C.c_void_p, _dp, _dp],
+        x3d2h_laplacian=[C.c_void_p, _dp, _dp],
         x3d2h_gradient=[C.c_void_p] + [_dp] * 4,
         x3d2h_curl=[C.c_void_p] + [_dp] * 6,
         x3d2h_poisson=[C.c_void_p, _dp, _dp],
